@@ -1,0 +1,191 @@
+"""CPU oracle SHT with healpy-compatible signatures (test infrastructure only; parity unpinned, see
+oracle/__init__.py).  Legendre stage: oracle/csht.c through ctypes.  Ring FFT stage: numpy (pocketfft).
+
+Replaces, for tests and the CPU baseline only, the healpy calls of the reference hot path:
+`hp.alm2map`, `hp.map2alm(iter=0)`, `hp.alm2map_spin`, `hp.map2alm_spin`
+(/root/reference/plancklens/shts.py:33-35, utils_spin.py:21-34).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from . import ref_geom as rg
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    """Compile oracle/csht.c -> oracle/_build/libcsht.so (gcc + OpenMP)."""
+    so = os.path.join(_HERE, '_build', 'libcsht.so')
+    src = os.path.join(_HERE, 'csht.c')
+    if (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(['make', '-C', _HERE, '-s'])
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, '_build', 'libcsht.so')
+        if not os.path.exists(so):
+            build()
+        L = ctypes.CDLL(so)
+        ip = ctypes.POINTER(ctypes.c_int)
+        dp = ctypes.POINTER(ctypes.c_double)
+        vp = ctypes.c_void_p
+        ldp = ctypes.POINTER(ctypes.c_longdouble)
+        L.csht_synth.argtypes = [ctypes.c_int] * 4 + [ip, ip, dp, ldp, ldp, vp, vp, vp, vp, ctypes.c_int]
+        L.csht_anal.argtypes = [ctypes.c_int] * 4 + [ip, ip, dp, ldp, ldp, dp, vp, vp, vp, vp, ctypes.c_int]
+        L.csht_max_threads.restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def max_threads():
+    return _lib().csht_max_threads()
+
+
+class _Geom:
+    _cache = {}
+
+    def __init__(self, nside):
+        N = nside
+        self.nside = N
+        self.nphi, self.start, self.z, self.sth, self.phi0 = rg.ring_info(N)
+        self.nring = 4 * N - 1
+        self.npair = 2 * N
+        i = np.arange(1, 2 * N + 1)
+        self.rn = (i - 1).astype(np.int32)
+        self.rs = np.where(i < 2 * N, 4 * N - i - 1, -1).astype(np.int32)
+        # ring-pair geometry in x87 long double from the exact integer formulas: 1-z = i^2/(3N^2) in the cap,
+        # z = 2(2N-i)/(3N) in the belt.  log sin/cos(theta/2) are handed to C in long double so that the
+        # sin^m seed carries no m*eps amplification of a double-rounded angle.
+        il = i.astype(np.longdouble)
+        NL = np.longdouble(N)
+        omz = np.where(i < N, il * il / (3 * NL * NL), 1 - 2 * (2 * NL - il) / (3 * NL))
+        self.cth = np.ascontiguousarray((1 - omz).astype(np.float64))
+        self.lshalf = np.ascontiguousarray(0.5 * np.log(omz / 2))
+        self.lchalf = np.ascontiguousarray(0.5 * np.log(1 - omz / 2))
+        self.weight = np.full(self.npair, 4.0 * np.pi / (12 * N * N))
+
+    @classmethod
+    def get(cls, nside):
+        if nside not in cls._cache:
+            cls._cache[nside] = cls(nside)
+        return cls._cache[nside]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def legendre_synth(nside, spin, lmax, mmax, almG, almC=None, mstep=1):
+    """-> phase arrays X1 (, X2) of shape [nring, mmax+1]."""
+    g = _Geom.get(nside)
+    almG = np.ascontiguousarray(almG, dtype=np.complex128)
+    X1 = np.zeros((g.nring, mmax + 1), dtype=np.complex128)
+    X2 = np.zeros((g.nring, mmax + 1), dtype=np.complex128) if spin > 0 else None
+    if spin > 0:
+        almC = np.ascontiguousarray(almC, dtype=np.complex128)
+    _lib().csht_synth(spin, lmax, mmax, g.npair, _p(g.rn, ctypes.c_int), _p(g.rs, ctypes.c_int),
+                      _p(g.cth, ctypes.c_double), _p(g.lchalf, ctypes.c_longdouble), _p(g.lshalf, ctypes.c_longdouble),
+                      almG.ctypes.data, almC.ctypes.data if spin > 0 else None,
+                      X1.ctypes.data, X2.ctypes.data if spin > 0 else None, mstep)
+    return X1, X2
+
+
+def legendre_anal(nside, spin, lmax, mmax, X1, X2=None, mstep=1):
+    g = _Geom.get(nside)
+    nalm = rg.alm_getsize(lmax, mmax)
+    G = np.zeros(nalm, dtype=np.complex128)
+    C = np.zeros(nalm, dtype=np.complex128) if spin > 0 else None
+    X1 = np.ascontiguousarray(X1)
+    if spin > 0:
+        X2 = np.ascontiguousarray(X2)
+    _lib().csht_anal(spin, lmax, mmax, g.npair, _p(g.rn, ctypes.c_int), _p(g.rs, ctypes.c_int),
+                     _p(g.cth, ctypes.c_double), _p(g.lchalf, ctypes.c_longdouble), _p(g.lshalf, ctypes.c_longdouble),
+                     _p(g.weight, ctypes.c_double), X1.ctypes.data, X2.ctypes.data if spin > 0 else None,
+                     G.ctypes.data, C.ctypes.data if spin > 0 else None, mstep)
+    return G, C
+
+
+def phase2map(nside, X):
+    """Ring FFT stage of synthesis: X[ring, m] -> RING-ordered real map.
+    map_j = X_0 + 2 Re sum_{m>0} X_m e^{i m (phi0 + 2 pi j / nphi)}; m >= nphi/2 aliases onto the ring's band."""
+    g = _Geom.get(nside)
+    mmax = X.shape[1] - 1
+    out = np.empty(12 * nside * nside)
+    m = np.arange(mmax + 1)
+    # group rings of equal length (equatorial belt is one batch)
+    for n in np.unique(g.nphi):
+        rows = np.where(g.nphi == n)[0]
+        Xs = X[rows] * np.exp(1j * m[None, :] * g.phi0[rows][:, None])
+        d = np.zeros((rows.size, n), dtype=complex)       # full-length spectrum, Hermitian-completed
+        k = m % n
+        np.add.at(d, (slice(None), k), Xs)
+        kc = (-m[1:]) % n
+        np.add.at(d, (slice(None), kc), np.conj(Xs[:, 1:]))
+        x = np.fft.ifft(d, axis=1) * n
+        for a, r in enumerate(rows):
+            out[g.start[r]:g.start[r] + n] = x[a].real
+    return out
+
+
+def map2phase(nside, mp, mmax):
+    """Adjoint ring FFT: X[ring, m] = sum_j map_j e^{-i m phi_j} (no weights)."""
+    g = _Geom.get(nside)
+    X = np.empty((g.nring, mmax + 1), dtype=complex)
+    m = np.arange(mmax + 1)
+    for n in np.unique(g.nphi):
+        rows = np.where(g.nphi == n)[0]
+        x = np.stack([mp[g.start[r]:g.start[r] + n] for r in rows])
+        d = np.fft.fft(x, axis=1)
+        X[rows] = d[:, m % n] * np.exp(-1j * m[None, :] * g.phi0[rows][:, None])
+    return X
+
+
+# ------------------------------------------------------------------ healpy-compatible entry points
+def alm2map(alm, nside, lmax=None, mmax=None, **kw):
+    alm = np.asarray(alm)
+    if lmax is None:
+        lmax = rg.alm_getlmax(alm.size)
+    mmax = lmax if mmax is None else mmax
+    assert alm.size == rg.alm_getsize(lmax, mmax), (alm.size, lmax, mmax)
+    X1, _ = legendre_synth(nside, 0, lmax, mmax, alm)
+    return phase2map(nside, X1)
+
+
+def map2alm(m, lmax=None, mmax=None, iter=0, **kw):
+    assert iter == 0, 'the reference hot path always passes iter=0'
+    m = np.asarray(m, dtype=float)
+    nside = rg.npix2nside(m.size)
+    if lmax is None:
+        lmax = 3 * nside - 1
+    mmax = lmax if mmax is None else mmax
+    X = map2phase(nside, m, mmax)
+    G, _ = legendre_anal(nside, 0, lmax, mmax, X)
+    return G
+
+
+def alm2map_spin(alms, nside, spin, lmax, mmax=None):
+    assert spin > 0
+    mmax = lmax if mmax is None else mmax
+    X1, X2 = legendre_synth(nside, spin, lmax, mmax, alms[0], alms[1])
+    return [phase2map(nside, X1), phase2map(nside, X2)]
+
+
+def map2alm_spin(maps, spin, lmax=None, mmax=None):
+    assert spin > 0
+    m1 = np.asarray(maps[0], dtype=float)
+    m2 = np.asarray(maps[1], dtype=float)
+    nside = rg.npix2nside(m1.size)
+    if lmax is None:
+        lmax = 3 * nside - 1
+    mmax = lmax if mmax is None else mmax
+    X1 = map2phase(nside, m1, mmax)
+    X2 = map2phase(nside, m2, mmax)
+    G, C = legendre_anal(nside, spin, lmax, mmax, X1, X2)
+    return [G, C]
