@@ -1,0 +1,119 @@
+/* libplk_b200: C ABI of the B200 (sm_100a) spin-weighted spherical-harmonic-transform hot path of
+ * plancklens.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Every entry point returns 0 on success and a negative PLK_E* code otherwise (never throws);
+ * plk_last_error() returns a human-readable message for the calling thread.
+ *
+ * alm layout: healpy m-major triangular order, complex128 (re, im interleaved), mmax == lmax:
+ *   idx(l, m) = m (2 lmax + 1 - m) / 2 + l,  only m >= 0 stored.
+ * map layout: HEALPix RING order, float64, npix = 12 nside^2.
+ * Conventions (reference plancklens/utils_spin.py:1-14): spin 0 is the healpy scalar transform
+ * T = sum a_lm Y_lm;  spin s > 0 uses  (+s)a_lm = -(G_lm + i C_lm)  and returns (Re, Im) of the spin-s field
+ * (spin 2: (G, C) = (E, B) -> (Q, U)).  Analysis is the single-pass adjoint times 4 pi / npix
+ * (healpy map2alm(iter=0), uniform weights) -- the only form the reference hot path calls.
+ *
+ * "_dev" functions take DEVICE pointers and a cudaStream_t (passed as void*); the caller owns all buffers.
+ * "_host" functions take HOST pointers, stage through pinned memory and synchronise before returning.
+ *
+ * Reference interface each entry point replaces (paths relative to /root/reference):
+ *   plk_alm2map_*   spin 0: plancklens/shts.py:12,35 (hp.alm2map; call sites qcinv/opfilt_tt.py:187, qest.py:471,514)
+ *                   spin s: plancklens/shts.py:22,35 and utils_spin.py:21-27 (hp.alm2map_spin; opfilt_pp.py:260,
+ *                           qest.py:464,504,530,593,636, utils_qe.py:70)
+ *   plk_map2alm_*   spin 0: plancklens/shts.py:16,35 (hp.map2alm(iter=0); opfilt_tt.py:34,189, filt_simple.py:399)
+ *                   spin s: plancklens/shts.py:26,35 and utils_spin.py:29-34 (hp.map2alm_spin; opfilt_pp.py:265,314,
+ *                           qest.py:259,280, filt_simple.py:404, utils_qe.py:125)
+ *   fl_* arguments  fuse the hp.almxfl calls that bracket those transforms (opfilt_tt.py:185,190, qest.py:260-262,
+ *                   463, 494-503).
+ *   plk_almxfl_dev, plk_alm_axpy_dev, plk_alm_dot_dev, plk_alm_copy_dev, plk_alm_splice_dev
+ *                   hp.almxfl; cd_solve.py:75-86 vector updates; opfilt_tt.py:43-51 / opfilt_pp.py:27-34 dot_op;
+ *                   qcinv/util_alm.py:8-44 alm_copy / alm_splice.
+ *   plk_map_*       numpy per-pixel passes: opfilt_tt.py:193-205 (N^-1 and template projection),
+ *                   opfilt_pp.py:272-303, qest.py:256-257, 276-278 (QE leg products).
+ */
+#ifndef PLK_H
+#define PLK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plk_plan plk_plan;
+
+#define PLK_OK 0
+#define PLK_EINVAL (-1)   /* bad argument */
+#define PLK_ECUDA (-2)    /* CUDA runtime error (see plk_last_error) */
+#define PLK_ENOMEM (-3)
+#define PLK_ENODEV (-4)   /* no CUDA device / not sm_100 */
+
+const char *plk_last_error(void);
+int plk_version(void);
+/* number of CUDA kernels this library has launched in the calling process (all plans) */
+long long plk_launch_count(void);
+
+/* Builds geometry, ring-FFT tables and scratch for (nside, lmax, mmax) on the CURRENT device.
+ * nside: power of two, 1 <= nside <= 8192.  mmax must equal lmax (the only case the reference uses). */
+int plk_plan_create(plk_plan **plan, int nside, int lmax, int mmax);
+int plk_plan_destroy(plk_plan *plan);
+/* bytes of device memory currently held by the plan (tables + scratch) */
+long long plk_plan_device_bytes(const plk_plan *plan);
+int plk_plan_nside(const plk_plan *plan);
+int plk_plan_lmax(const plk_plan *plan);
+
+/* ---- transforms, device pointers.  alm2/map2/fl2 are ignored for spin 0.  alm2 may be NULL for spin > 0
+ *      (zero curl component).  fl1/fl2: optional per-l real factors (device, lmax+1 doubles) multiplied onto
+ *      alm1/alm2 before synthesis (after analysis); NULL = 1. */
+int plk_alm2map_dev(plk_plan *plan, int spin, const void *alm1, const void *alm2, const double *fl1,
+                    const double *fl2, double *map1, double *map2, void *stream);
+int plk_map2alm_dev(plk_plan *plan, int spin, const double *map1, const double *map2, const double *fl1,
+                    const double *fl2, void *alm1, void *alm2, void *stream);
+
+/* ---- transforms, host pointers (numpy arrays on the Python side) */
+int plk_alm2map_host(plk_plan *plan, int spin, const void *alm1, const void *alm2, double *map1, double *map2);
+int plk_map2alm_host(plk_plan *plan, int spin, const double *map1, const double *map2, void *alm1, void *alm2);
+
+/* ---- Legendre / ring-FFT stages on their own (profiling and tests).  X: [4 nside - 1][mmax + 1] complex128 */
+int plk_legendre_synth_dev(plk_plan *plan, int spin, const void *alm1, const void *alm2, const double *fl1,
+                           const double *fl2, void *X1, void *X2, void *stream);
+int plk_legendre_anal_dev(plk_plan *plan, int spin, const void *X1, const void *X2, const double *fl1,
+                          const double *fl2, void *alm1, void *alm2, void *stream);
+int plk_ring_synth_dev(plk_plan *plan, const void *X, double *map, void *stream);
+int plk_ring_anal_dev(plk_plan *plan, const double *map, void *X, void *stream);
+
+/* ---- alm BLAS-1 (device pointers; n = number of complex coefficients of an lmax/mmax=lmax triangle) */
+/* out[l,m] = fl[l] * in[l,m] (fl has nfl entries; l >= nfl multiplies by 0, as hp.almxfl); in == out allowed */
+int plk_almxfl_dev(int lmax, const void *in, const double *fl, int nfl, void *out, void *stream);
+/* y += a * x  (a read from device memory *a_dev if a_dev != NULL, else the host value a) */
+int plk_alm_axpy_dev(long long n, double a, const double *a_dev, const void *x, void *y, void *stream);
+/* result_dev[0] = sum_{l>=lmin} [ a_l0 b_l0 + 2 sum_{m>0} Re(a_lm conj b_lm) ]  (opfilt_tt/pp dot_op) */
+int plk_alm_dot_dev(int lmax, int lmin, const void *a, const void *b, double *result_dev, void *stream);
+/* copy with change of lmax (zero fill above lmax_in) */
+int plk_alm_copy_dev(int lmax_in, const void *in, int lmax_out, void *out, void *stream);
+/* out (lmax_hi) = lo for l <= lsplit, hi for l > lsplit */
+int plk_alm_splice_dev(int lmax_lo, const void *lo, int lmax_hi, const void *hi, int lsplit, void *out, void *stream);
+
+/* ---- per-pixel passes (device pointers, n pixels) */
+/* y = y * a            */
+int plk_map_mul_dev(long long n, double *y, const double *a, void *stream);
+/* QE leg products (qest.py:256-257): g *= t ; c *= t */
+int plk_map_mul2_dev(long long n, double *g, double *c, const double *t, void *stream);
+/* qest.py:276-278:  (re,im) = (q - i u)(g3 + i c3) - (q + i u)(g1 - i c1) */
+int plk_map_qe_pp_dev(long long n, const double *q, const double *u, const double *g3, const double *c3,
+                      const double *g1, const double *c1, double *re, double *im, void *stream);
+/* opfilt_pp.py:292-301: (q,u) <- [[nqq, nqu],[nqu, nuu]] (q,u) */
+int plk_map_ninv3_dev(long long n, double *q, double *u, const double *nqq, const double *nqu, const double *nuu,
+                      void *stream);
+/* template_removal.py dot()/accum() for monopole + dipole on a RING map of the plan's nside
+ * (opfilt_tt.py:193-205):
+ *   if w != NULL: m_p <- m_p w_p first (in place);  sums_dev[0..3] = sum_p m_p * {1, x_p, y_p, z_p} */
+int plk_map_modes_dot_dev(plk_plan *plan, double *m, const double *w, double *sums_dev, void *stream);
+/*   m_p -= w_p * sum_a mode_a(p) coef_a,  coef = pinv_dev (4x4 row-major, zero rows/cols for unused modes) @ sums_dev */
+int plk_map_modes_sub_dev(plk_plan *plan, double *m, const double *w, const double *sums_dev,
+                          const double *pinv_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLK_H */

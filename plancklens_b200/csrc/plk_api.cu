@@ -1,0 +1,560 @@
+// libplk_b200: plan management and C ABI (see include/plk.h).  sm_100a only.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/plk.h"
+#include "plk_blas.cuh"
+#include "plk_common.h"
+#include "plk_fft.cuh"
+#include "plk_legendre.cuh"
+#include "plk_tables.h"
+
+using namespace plk;
+
+// ------------------------------------------------------------------------------------------ errors / counters
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail(PLK_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCHED()                                                                                 \
+  do {                                                                                             \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess) return fail(PLK_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char *plk_last_error(void) { return g_err.c_str(); }
+extern "C" int plk_version(void) { return 100; }
+extern "C" long long plk_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------ plan
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct SpinDev {
+  bool ready = false;
+  DevSpin d{};
+  std::vector<void *> owned;
+};
+
+struct plk_plan {
+  int nside, lmax, mmax, npair, nring, device;
+  long long npix;
+  int pitch;  // phase array row pitch (complex elements)
+  HostGeom hg;
+  DevGeom g{};
+  DevFFT f{};
+  DevRings rings{};
+  int fft_smem = 0;
+  int *fft_order = nullptr;
+  int *morder = nullptr;
+  std::vector<void *> owned;
+  SpinDev spins[4];
+  DevBuf X1, X2, rec, part, partial, hostio[4];
+  long long table_bytes = 0;
+};
+
+template <class T>
+static int upload(plk_plan *p, const std::vector<T> &h, T **d, std::vector<void *> *owned = nullptr) {
+  const size_t b = std::max<size_t>(h.size() * sizeof(T), 16);
+  CK(cudaMalloc((void **)d, b));
+  (owned ? *owned : p->owned).push_back(*d);
+  p->table_bytes += b;
+  if (!h.empty()) CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+static int ensure(DevBuf &b, size_t bytes) {
+  if (b.bytes >= bytes) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.bytes = 0;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) return fail(PLK_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  b.bytes = bytes;
+  return 0;
+}
+
+static int nextpow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
+  if (!out) return fail(PLK_EINVAL, "plan pointer is NULL");
+  *out = nullptr;
+  if (nside < 1 || nside > 8192 || (nside & (nside - 1))) return fail(PLK_EINVAL, "nside must be a power of two in [1, 8192], got %d", nside);
+  if (lmax < 0 || lmax > 16384) return fail(PLK_EINVAL, "lmax out of range: %d", lmax);
+  if (mmax != lmax) return fail(PLK_EINVAL, "mmax (%d) must equal lmax (%d)", mmax, lmax);
+  int dev;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(PLK_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(PLK_ENODEV, "libplk_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+
+  plk_plan *p = new plk_plan();
+  p->nside = nside; p->lmax = lmax; p->mmax = mmax; p->device = dev;
+  p->hg = make_geom(nside);
+  const HostGeom &hg = p->hg;
+  p->npair = hg.npair; p->nring = hg.nring; p->npix = hg.npix;
+  p->pitch = (mmax + 1 + 1) & ~1;   // even: 32-byte aligned rows
+
+  // geometry
+  DevGeom &g = p->g;
+  g.nside = nside; g.npair = hg.npair; g.nring = hg.nring; g.npix = hg.npix;
+  double *d;
+#define UP(vec, field) do { int rc = upload(p, vec, &d); if (rc) { plk_plan_destroy(p); return rc; } field = d; } while (0)
+  UP(hg.cth, g.cth); UP(hg.sh_hi, g.sh_hi); UP(hg.sh_lo, g.sh_lo); UP(hg.ch_hi, g.ch_hi); UP(hg.ch_lo, g.ch_lo);
+#undef UP
+
+  // ring FFT tables
+  DevFFT &f = p->f;
+  f.nside = nside; f.npair = hg.npair; f.nring = hg.nring;
+  std::vector<int> M(hg.npair), shifted = hg.shifted, nphi = hg.nphi;
+  std::vector<long long> voff(hg.npair, -1), sn(hg.npair), ss(hg.npair);
+  long long vtot = 0;
+  int Mmax = 16;
+  std::vector<double> cost(hg.npair);
+  for (int ip = 0; ip < hg.npair; ++ip) {
+    const int q = hg.nphi[ip] / 4;
+    sn[ip] = hg.start_n[ip]; ss[ip] = hg.start_s[ip];
+    if (q <= kTinyQ) { M[ip] = 0; cost[ip] = 4.0 * q * (mmax + 1) * 20; }
+    else if ((q & (q - 1)) == 0) { M[ip] = q; cost[ip] = 4.0 * q * ilog2(q); }
+    else { M[ip] = nextpow2(2 * q - 1); voff[ip] = vtot; vtot += M[ip]; cost[ip] = 4.0 * 2.2 * M[ip] * ilog2(M[ip]); }
+    Mmax = std::max(Mmax, M[ip]);
+  }
+  f.Wn = Mmax;
+  std::vector<cplx> W(Mmax);
+  for (int k = 0; k < Mmax; ++k) {
+    long double a = -2.0L * 3.14159265358979323846264338327950288L * k / Mmax;
+    W[k] = mk((double)cosl(a), (double)sinl(a));
+  }
+  {
+    cplx *dW; int rc = upload(p, W, &dW); if (rc) { plk_plan_destroy(p); return rc; } f.W = dW;
+    int *di; long long *dl;
+    rc = upload(p, M, &di); if (rc) { plk_plan_destroy(p); return rc; } f.M = di;
+    rc = upload(p, nphi, &di); if (rc) { plk_plan_destroy(p); return rc; } f.nphi = di;
+    rc = upload(p, shifted, &di); if (rc) { plk_plan_destroy(p); return rc; } f.shifted = di;
+    rc = upload(p, voff, &dl); if (rc) { plk_plan_destroy(p); return rc; } f.voff = dl;
+    rc = upload(p, sn, &dl); if (rc) { plk_plan_destroy(p); return rc; } f.start_n = dl;
+    rc = upload(p, ss, &dl); if (rc) { plk_plan_destroy(p); return rc; } f.start_s = dl;
+    std::vector<int> order(hg.npair);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    rc = upload(p, order, &di); if (rc) { plk_plan_destroy(p); return rc; } p->fft_order = di; f.order = di;
+    std::vector<int> mo(mmax + 1);
+    std::iota(mo.begin(), mo.end(), 0);
+    rc = upload(p, mo, &di); if (rc) { plk_plan_destroy(p); return rc; } p->morder = di;
+  }
+  p->fft_smem = Mmax * (int)sizeof(cplx);
+  if (p->fft_smem > 227 * 1024) { plk_plan_destroy(p); return fail(PLK_EINVAL, "ring FFT needs %d bytes of shared memory", p->fft_smem); }
+  {
+    static int attr_smem = 0;   // the attribute is per function, not per plan: only ever raise it
+    if (p->fft_smem > attr_smem) {
+      cudaError_t e1 = cudaFuncSetAttribute(ring_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
+      cudaError_t e2 = cudaFuncSetAttribute(ring_anal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
+      cudaError_t e3 = cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { plk_plan_destroy(p); return fail(PLK_ECUDA, "cudaFuncSetAttribute(smem=%d) failed", p->fft_smem); }
+      attr_smem = p->fft_smem;
+    }
+  }
+  if (vtot > 0) {
+    cplx *dV;
+    cudaError_t ee = cudaMalloc((void **)&dV, (size_t)vtot * sizeof(cplx));
+    if (ee != cudaSuccess) { plk_plan_destroy(p); return fail(PLK_ENOMEM, "cudaMalloc(V) failed"); }
+    p->owned.push_back(dV); p->table_bytes += vtot * sizeof(cplx);
+    f.V = dV;
+    bluestein_setup_kernel<<<hg.npair, kFftThreads, p->fft_smem>>>(f, dV);
+    g_launches.fetch_add(1);
+    ee = cudaDeviceSynchronize();
+    if (ee != cudaSuccess) { plk_plan_destroy(p); return fail(PLK_ECUDA, "bluestein setup failed: %s", cudaGetErrorString(ee)); }
+  } else {
+    f.V = nullptr;
+  }
+
+  // per-ring table for the template (monopole / dipole) kernels
+  {
+    std::vector<long long> st(hg.nring);
+    std::vector<int> np(hg.nring), sh(hg.nring);
+    std::vector<double> z(hg.nring), sth(hg.nring);
+    for (int ip = 0; ip < hg.npair; ++ip) {
+      const int rn = ip, rs = hg.nring - 1 - ip;
+      st[rn] = hg.start_n[ip]; np[rn] = hg.nphi[ip]; sh[rn] = hg.shifted[ip]; z[rn] = hg.cth[ip]; sth[rn] = hg.sth[ip];
+      if (rs != rn) { st[rs] = hg.start_s[ip]; np[rs] = hg.nphi[ip]; sh[rs] = hg.shifted[ip]; z[rs] = -hg.cth[ip]; sth[rs] = hg.sth[ip]; }
+    }
+    long long *dl; int *di; double *dd;
+    int rc;
+    rc = upload(p, st, &dl); if (rc) { plk_plan_destroy(p); return rc; } p->rings.start = dl;
+    rc = upload(p, np, &di); if (rc) { plk_plan_destroy(p); return rc; } p->rings.nphi = di;
+    rc = upload(p, sh, &di); if (rc) { plk_plan_destroy(p); return rc; } p->rings.shifted = di;
+    rc = upload(p, z, &dd); if (rc) { plk_plan_destroy(p); return rc; } p->rings.z = dd;
+    rc = upload(p, sth, &dd); if (rc) { plk_plan_destroy(p); return rc; } p->rings.sth = dd;
+    p->rings.nring = hg.nring;
+  }
+  *out = p;
+  return PLK_OK;
+}
+
+extern "C" int plk_plan_destroy(plk_plan *p) {
+  if (!p) return PLK_OK;
+  for (void *q : p->owned) cudaFree(q);
+  for (auto &s : p->spins) for (void *q : s.owned) cudaFree(q);
+  for (DevBuf *b : {&p->X1, &p->X2, &p->rec, &p->part, &p->partial}) if (b->p) cudaFree(b->p);
+  for (auto &b : p->hostio) if (b.p) cudaFree(b.p);
+  delete p;
+  return PLK_OK;
+}
+
+extern "C" long long plk_plan_device_bytes(const plk_plan *p) {
+  if (!p) return 0;
+  long long b = p->table_bytes;
+  for (const DevBuf *x : {&p->X1, &p->X2, &p->rec, &p->part, &p->partial}) b += (long long)x->bytes;
+  for (auto &x : p->hostio) b += (long long)x.bytes;
+  return b;
+}
+extern "C" int plk_plan_nside(const plk_plan *p) { return p ? p->nside : 0; }
+extern "C" int plk_plan_lmax(const plk_plan *p) { return p ? p->lmax : 0; }
+
+// per-spin recurrence tables + seeds (built on first use)
+static int ensure_spin(plk_plan *p, int spin) {
+  if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
+  SpinDev &sd = p->spins[spin];
+  if (sd.ready) return 0;
+  SpinTables t = make_spin_tables(spin, p->lmax, p->mmax);
+  const size_t n = t.U.size();
+  std::vector<double2> uv(n);
+  for (size_t i = 0; i < n; ++i) uv[i] = make_double2(t.U[i], t.V[i]);
+  DevSpin &d = sd.d;
+  d.spin = spin; d.lmax = p->lmax; d.mmax = p->mmax;
+  int rc;
+  double2 *duv; double *dd; int *di; signed char *dc;
+#define UPS(vec, ptr, field) do { rc = upload(p, vec, &ptr, &sd.owned); if (rc) return rc; field = ptr; } while (0)
+  UPS(uv, duv, d.UV); UPS(t.alpha, dd, d.alpha); UPS(t.k_hi, dd, d.k_hi); UPS(t.k_lo, dd, d.k_lo);
+  UPS(t.k_e, di, d.k_e); UPS(t.pc, di, d.pc); UPS(t.ps, di, d.ps); UPS(t.sg_p, dc, d.sg_p); UPS(t.sg_m, dc, d.sg_m);
+#undef UPS
+  const size_t ns = (size_t)(p->mmax + 1) * p->npair;
+  auto dalloc = [&](void **q, size_t bytes) -> int {
+    cudaError_t e = cudaMalloc(q, bytes);
+    if (e != cudaSuccess) return fail(PLK_ENOMEM, "cudaMalloc(seeds, %zu) failed", bytes);
+    sd.owned.push_back(*q); p->table_bytes += bytes;
+    return 0;
+  };
+  if ((rc = dalloc((void **)&d.ks, ns * sizeof(int)))) return rc;
+  if ((rc = dalloc((void **)&d.s0, ns * sizeof(double)))) return rc;
+  if ((rc = dalloc((void **)&d.s1, ns * sizeof(double)))) return rc;
+  d.s2 = d.s3 = nullptr;
+  if (spin > 0) {
+    if ((rc = dalloc((void **)&d.s2, ns * sizeof(double)))) return rc;
+    if ((rc = dalloc((void **)&d.s3, ns * sizeof(double)))) return rc;
+  }
+  dim3 grid((p->npair + 127) / 128, p->mmax + 1);
+  if (spin == 0) seed_kernel<false><<<grid, 128>>>(p->g, d);
+  else seed_kernel<true><<<grid, 128>>>(p->g, d);
+  LAUNCHED();
+  CK(cudaDeviceSynchronize());
+  sd.ready = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ Legendre launches
+template <bool SPIN, bool SYNTH>
+static size_t leg_smem() {
+  size_t s = 128 + (size_t)kStages * StageBytes<SPIN, SYNTH>::stage;
+  if (!SYNTH) s += (size_t)2 * kNCW * kChunk * (SPIN ? 4 : 2) * sizeof(double);
+  return s;
+}
+static int pick_nr(const plk_plan *p, int nrmax) {
+  // enough blocks to cover the SMs a few times over; small grids get fewer pairs per thread
+  int nr = nrmax;
+  while (nr > 1) {
+    const long long tiles = (p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr);
+    if (tiles * (p->mmax + 1) >= 4 * 148 && p->npair >= kNCW * 32 * nr) break;
+    nr >>= 1;
+  }
+  return nr;
+}
+
+static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *alm2, const double *fl1,
+                          const double *fl2, cplx *X1, cplx *X2, cudaStream_t st) {
+  int rc = ensure_spin(p, spin);
+  if (rc) return rc;
+  const DevSpin &d = p->spins[spin].d;
+  const size_t nalm = (size_t)alm_size(p->lmax, p->mmax);
+  if ((rc = ensure(p->rec, nalm * (spin ? 32 : 16) + 64))) return rc;
+  dim3 pg((p->lmax + 256) / 256, p->mmax + 1);
+  if (spin == 0) prep_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, nullptr, fl1, nullptr, p->rec.p);
+  else prep_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, (const cplx *)alm2, fl1, fl2, p->rec.p);
+  LAUNCHED();
+  const int nr = pick_nr(p, spin ? 2 : 4);
+  dim3 grid((p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr), p->mmax + 1);
+  const int nthr = (kNCW + 1) * 32;
+#define SYN(SP, NR)                                                                                              \
+  legendre_synth_kernel<SP, NR><<<grid, nthr, leg_smem<SP, true>(), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, p->morder)
+  if (spin == 0) {
+    if (nr == 4) SYN(false, 4); else if (nr == 2) SYN(false, 2); else SYN(false, 1);
+  } else {
+    if (nr == 2) SYN(true, 2); else SYN(true, 1);
+  }
+#undef SYN
+  LAUNCHED();
+  return 0;
+}
+
+static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, const double *fl1, const double *fl2,
+                         void *alm1, void *alm2, cudaStream_t st) {
+  int rc = ensure_spin(p, spin);
+  if (rc) return rc;
+  const DevSpin &d = p->spins[spin].d;
+  const size_t nalm = (size_t)alm_size(p->lmax, p->mmax);
+  const int nv = spin ? 4 : 2;
+  const int nr = pick_nr(p, spin ? 2 : 4);
+  const int ntile = (p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr);
+  const long long stride = (long long)nalm * nv;
+  if ((rc = ensure(p->part, (size_t)ntile * stride * sizeof(double)))) return rc;
+  dim3 grid(ntile, p->mmax + 1);
+  const int nthr = (kNCW + 1) * 32;
+#define ANA(SP, NR)                                                                                              \
+  legendre_anal_kernel<SP, NR><<<grid, nthr, leg_smem<SP, false>(), st>>>(p->g, d, X1, X2, p->pitch, (double *)p->part.p, stride, p->morder)
+  if (spin == 0) {
+    if (nr == 4) ANA(false, 4); else if (nr == 2) ANA(false, 2); else ANA(false, 1);
+  } else {
+    if (nr == 2) ANA(true, 2); else ANA(true, 1);
+  }
+#undef ANA
+  LAUNCHED();
+  dim3 pg((p->lmax + 256) / 256, p->mmax + 1);
+  if (spin == 0) finish_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, nullptr, (cplx *)alm1, nullptr);
+  else finish_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, fl2, (cplx *)alm1, (cplx *)alm2);
+  LAUNCHED();
+  return 0;
+}
+
+static int ring_synth(plk_plan *p, const cplx *X, double *map, cudaStream_t st) {
+  ring_synth_kernel<<<p->npair, kFftThreads, p->fft_smem, st>>>(p->f, X, p->pitch, p->mmax, map);
+  LAUNCHED();
+  return 0;
+}
+static int ring_anal(plk_plan *p, const double *map, cplx *X, cudaStream_t st) {
+  const double w = 4.0 * M_PI / (double)p->npix;
+  ring_anal_kernel<<<p->npair, kFftThreads, p->fft_smem, st>>>(p->f, map, X, p->pitch, p->mmax, w);
+  LAUNCHED();
+  return 0;
+}
+static int ensure_phase(plk_plan *p, int ncomp) {
+  const size_t b = (size_t)p->nring * p->pitch * sizeof(cplx);
+  int rc = ensure(p->X1, b);
+  if (rc) return rc;
+  if (ncomp > 1 && (rc = ensure(p->X2, b))) return rc;
+  return 0;
+}
+
+#define CHECK_PLAN(p) do { if (!(p)) return fail(PLK_EINVAL, "plan is NULL"); } while (0)
+
+extern "C" int plk_legendre_synth_dev(plk_plan *p, int spin, const void *alm1, const void *alm2, const double *fl1,
+                                      const double *fl2, void *X1, void *X2, void *stream) {
+  CHECK_PLAN(p);
+  if (!alm1 || !X1 || (spin > 0 && !X2)) return fail(PLK_EINVAL, "NULL buffer");
+  return legendre_synth(p, spin, alm1, alm2, fl1, fl2, (cplx *)X1, (cplx *)X2, (cudaStream_t)stream);
+}
+extern "C" int plk_legendre_anal_dev(plk_plan *p, int spin, const void *X1, const void *X2, const double *fl1,
+                                     const double *fl2, void *alm1, void *alm2, void *stream) {
+  CHECK_PLAN(p);
+  if (!alm1 || !X1 || (spin > 0 && (!X2 || !alm2))) return fail(PLK_EINVAL, "NULL buffer");
+  return legendre_anal(p, spin, (const cplx *)X1, (const cplx *)X2, fl1, fl2, alm1, alm2, (cudaStream_t)stream);
+}
+extern "C" int plk_ring_synth_dev(plk_plan *p, const void *X, double *map, void *stream) {
+  CHECK_PLAN(p);
+  if (!X || !map) return fail(PLK_EINVAL, "NULL buffer");
+  return ring_synth(p, (const cplx *)X, map, (cudaStream_t)stream);
+}
+extern "C" int plk_ring_anal_dev(plk_plan *p, const double *map, void *X, void *stream) {
+  CHECK_PLAN(p);
+  if (!X || !map) return fail(PLK_EINVAL, "NULL buffer");
+  return ring_anal(p, map, (cplx *)X, (cudaStream_t)stream);
+}
+
+extern "C" int plk_alm2map_dev(plk_plan *p, int spin, const void *alm1, const void *alm2, const double *fl1,
+                               const double *fl2, double *map1, double *map2, void *stream) {
+  CHECK_PLAN(p);
+  if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
+  if (!alm1 || !map1 || (spin > 0 && !map2)) return fail(PLK_EINVAL, "NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_phase(p, spin ? 2 : 1);
+  if (rc) return rc;
+  if ((rc = legendre_synth(p, spin, alm1, alm2, fl1, fl2, (cplx *)p->X1.p, (cplx *)p->X2.p, st))) return rc;
+  if ((rc = ring_synth(p, (const cplx *)p->X1.p, map1, st))) return rc;
+  if (spin > 0 && (rc = ring_synth(p, (const cplx *)p->X2.p, map2, st))) return rc;
+  return PLK_OK;
+}
+
+extern "C" int plk_map2alm_dev(plk_plan *p, int spin, const double *map1, const double *map2, const double *fl1,
+                               const double *fl2, void *alm1, void *alm2, void *stream) {
+  CHECK_PLAN(p);
+  if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
+  if (!alm1 || !map1 || (spin > 0 && (!map2 || !alm2))) return fail(PLK_EINVAL, "NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_phase(p, spin ? 2 : 1);
+  if (rc) return rc;
+  if ((rc = ring_anal(p, map1, (cplx *)p->X1.p, st))) return rc;
+  if (spin > 0 && (rc = ring_anal(p, map2, (cplx *)p->X2.p, st))) return rc;
+  return legendre_anal(p, spin, (const cplx *)p->X1.p, (const cplx *)p->X2.p, fl1, fl2, alm1, alm2, st);
+}
+
+// ------------------------------------------------------------------------------------------ host-pointer variants
+extern "C" int plk_alm2map_host(plk_plan *p, int spin, const void *alm1, const void *alm2, double *map1, double *map2) {
+  CHECK_PLAN(p);
+  if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
+  if (!alm1 || !map1 || (spin > 0 && !map2)) return fail(PLK_EINVAL, "NULL buffer");
+  const size_t ab = (size_t)alm_size(p->lmax, p->mmax) * sizeof(cplx), mb = (size_t)p->npix * sizeof(double);
+  int rc;
+  if ((rc = ensure(p->hostio[0], ab)) || (rc = ensure(p->hostio[2], mb))) return rc;
+  CK(cudaMemcpy(p->hostio[0].p, alm1, ab, cudaMemcpyHostToDevice));
+  void *a2 = nullptr;
+  if (spin > 0) {
+    if ((rc = ensure(p->hostio[3], mb))) return rc;
+    if (alm2) {
+      if ((rc = ensure(p->hostio[1], ab))) return rc;
+      CK(cudaMemcpy(p->hostio[1].p, alm2, ab, cudaMemcpyHostToDevice));
+      a2 = p->hostio[1].p;
+    }
+  }
+  rc = plk_alm2map_dev(p, spin, p->hostio[0].p, a2, nullptr, nullptr, (double *)p->hostio[2].p, (double *)p->hostio[3].p, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(map1, p->hostio[2].p, mb, cudaMemcpyDeviceToHost));
+  if (spin > 0) CK(cudaMemcpy(map2, p->hostio[3].p, mb, cudaMemcpyDeviceToHost));
+  return PLK_OK;
+}
+
+extern "C" int plk_map2alm_host(plk_plan *p, int spin, const double *map1, const double *map2, void *alm1, void *alm2) {
+  CHECK_PLAN(p);
+  if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
+  if (!alm1 || !map1 || (spin > 0 && (!map2 || !alm2))) return fail(PLK_EINVAL, "NULL buffer");
+  const size_t ab = (size_t)alm_size(p->lmax, p->mmax) * sizeof(cplx), mb = (size_t)p->npix * sizeof(double);
+  int rc;
+  if ((rc = ensure(p->hostio[0], ab)) || (rc = ensure(p->hostio[2], mb))) return rc;
+  CK(cudaMemcpy(p->hostio[2].p, map1, mb, cudaMemcpyHostToDevice));
+  if (spin > 0) {
+    if ((rc = ensure(p->hostio[1], ab)) || (rc = ensure(p->hostio[3], mb))) return rc;
+    CK(cudaMemcpy(p->hostio[3].p, map2, mb, cudaMemcpyHostToDevice));
+  }
+  rc = plk_map2alm_dev(p, spin, (const double *)p->hostio[2].p, (const double *)p->hostio[3].p, nullptr, nullptr,
+                       p->hostio[0].p, p->hostio[1].p, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(alm1, p->hostio[0].p, ab, cudaMemcpyDeviceToHost));
+  if (spin > 0) CK(cudaMemcpy(alm2, p->hostio[1].p, ab, cudaMemcpyDeviceToHost));
+  return PLK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ BLAS-1 / pixel passes
+static double *g_scratch = nullptr;   // per-process reduction scratch (current device at first use)
+static const size_t kScratchDoubles = 1 << 17;
+static int scratch() {
+  if (g_scratch) return 0;
+  cudaError_t e = cudaMalloc((void **)&g_scratch, kScratchDoubles * sizeof(double));
+  if (e != cudaSuccess) return fail(PLK_ENOMEM, "cudaMalloc(scratch) failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+static int flat_grid(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
+
+extern "C" int plk_almxfl_dev(int lmax, const void *in, const double *fl, int nfl, void *out, void *stream) {
+  if (!in || !out || !fl || lmax < 0) return fail(PLK_EINVAL, "bad argument");
+  dim3 g((lmax + 256) / 256, lmax + 1);
+  almxfl_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax, (const cplx *)in, fl, nfl, (cplx *)out);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_axpy_dev(long long n, double a, const double *a_dev, const void *x, void *y, void *stream) {
+  if (!x || !y || n < 0) return fail(PLK_EINVAL, "bad argument");
+  axpy_kernel<<<flat_grid(2 * n), 256, 0, (cudaStream_t)stream>>>(2 * n, a, a_dev, (const double *)x, (double *)y);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_dot_dev(int lmax, int lmin, const void *a, const void *b, double *result_dev, void *stream) {
+  if (!a || !b || !result_dev || lmax < 0) return fail(PLK_EINVAL, "bad argument");
+  int rc = scratch();
+  if (rc) return rc;
+  if ((size_t)lmax + 1 > kScratchDoubles) return fail(PLK_EINVAL, "lmax too large");
+  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a, (const cplx *)b, g_scratch);
+  LAUNCHED();
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, lmax + 1, 1, result_dev);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_copy_dev(int lmax_in, const void *in, int lmax_out, void *out, void *stream) {
+  if (!in || !out) return fail(PLK_EINVAL, "NULL buffer");
+  dim3 g((lmax_out + 256) / 256, lmax_out + 1);
+  alm_copy_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax_in, (const cplx *)in, lmax_out, (cplx *)out);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_splice_dev(int lmax_lo, const void *lo, int lmax_hi, const void *hi, int lsplit, void *out,
+                                  void *stream) {
+  if (!lo || !hi || !out) return fail(PLK_EINVAL, "NULL buffer");
+  if (lsplit > lmax_lo || lsplit > lmax_hi) return fail(PLK_EINVAL, "lsplit exceeds lmax");
+  dim3 g((lmax_hi + 256) / 256, lmax_hi + 1);
+  alm_splice_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax_lo, (const cplx *)lo, lmax_hi, (const cplx *)hi, lsplit, (cplx *)out);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_map_mul_dev(long long n, double *y, const double *a, void *stream) {
+  if (!y || !a) return fail(PLK_EINVAL, "NULL buffer");
+  map_mul_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, y, a);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_map_mul2_dev(long long n, double *g, double *c, const double *t, void *stream) {
+  if (!g || !c || !t) return fail(PLK_EINVAL, "NULL buffer");
+  map_mul2_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, g, c, t);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_map_qe_pp_dev(long long n, const double *q, const double *u, const double *g3, const double *c3,
+                                 const double *g1, const double *c1, double *re, double *im, void *stream) {
+  if (!q || !u || !g3 || !c3 || !g1 || !c1 || !re || !im) return fail(PLK_EINVAL, "NULL buffer");
+  map_qe_pp_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, q, u, g3, c3, g1, c1, re, im);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_map_ninv3_dev(long long n, double *q, double *u, const double *nqq, const double *nqu,
+                                 const double *nuu, void *stream) {
+  if (!q || !u || !nqq || !nqu || !nuu) return fail(PLK_EINVAL, "NULL buffer");
+  map_ninv3_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, q, u, nqq, nqu, nuu);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_map_modes_dot_dev(plk_plan *p, double *m, const double *w, double *sums_dev, void *stream) {
+  CHECK_PLAN(p);
+  if (!m || !sums_dev) return fail(PLK_EINVAL, "NULL buffer");
+  int rc = ensure(p->partial, (size_t)4 * p->nring * sizeof(double));
+  if (rc) return rc;
+  modes_dot_kernel<<<p->nring, 256, 0, (cudaStream_t)stream>>>(p->rings, m, w, (double *)p->partial.p);
+  LAUNCHED();
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const double *)p->partial.p, p->nring, 4, sums_dev);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_map_modes_sub_dev(plk_plan *p, double *m, const double *w, const double *sums_dev,
+                                     const double *pinv_dev, void *stream) {
+  CHECK_PLAN(p);
+  if (!m || !sums_dev || !pinv_dev) return fail(PLK_EINVAL, "NULL buffer");
+  modes_sub_kernel<<<p->nring, 256, 0, (cudaStream_t)stream>>>(p->rings, m, w, sums_dev, pinv_dev);
+  LAUNCHED();
+  return PLK_OK;
+}

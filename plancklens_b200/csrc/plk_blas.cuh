@@ -1,0 +1,239 @@
+// HBM-bound helper kernels: alm pre/post scaling around the Legendre stage, alm BLAS-1 and per-pixel passes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "plk_common.h"
+#include "plk_legendre.cuh"
+
+namespace plk {
+
+// ------------------------------------------------------------------ synthesis input records
+// grid: (ceil((lmax+1)/256), mmax+1).  spin 0: rec = double2 alpha*fl1*a ; spin s: rec = double4 {H+, H-}
+template <bool SPIN>
+__global__ void prep_alm_kernel(DevSpin t, const cplx *__restrict__ a1, const cplx *__restrict__ a2,
+                                const double *__restrict__ fl1, const double *__restrict__ fl2, void *__restrict__ rec) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > t.lmax || l < m) return;
+  const int64_t i = alm_idx(t.lmax, l, m);
+  const double al = t.alpha[i];
+  const double s1 = al * (fl1 ? fl1[l] : 1.0);
+  if (!SPIN) {
+    const cplx a = a1[i];
+    reinterpret_cast<double2 *>(rec)[i] = make_double2(s1 * a.x, s1 * a.y);
+  } else {
+    const double s2 = al * (fl2 ? fl2[l] : 1.0);
+    const cplx g = a1[i];
+    const cplx c = a2 ? a2[i] : mk(0.0, 0.0);
+    const double gr = s1 * g.x, gi = s1 * g.y, cr = s2 * c.x, ci = s2 * c.y;
+    const double sg = (t.spin & 1) ? -1.0 : 1.0;
+    // H+ = -1/2 (G + iC) ; H- = -1/2 (-1)^s (G - iC)
+    reinterpret_cast<double4 *>(rec)[i] =
+        make_double4(-0.5 * (gr - ci), -0.5 * (gi + cr), -0.5 * sg * (gr + ci), -0.5 * sg * (gi - cr));
+  }
+}
+
+// ------------------------------------------------------------------ analysis output
+// sums the tile partials in fixed order and applies alpha, fl and the G/C recombination
+template <bool SPIN>
+__global__ void finish_alm_kernel(DevSpin t, const double *__restrict__ part, long long part_stride, int ntile,
+                                  const double *__restrict__ fl1, const double *__restrict__ fl2,
+                                  cplx *__restrict__ a1, cplx *__restrict__ a2) {
+  constexpr int NV = SPIN ? 4 : 2;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > t.lmax || l < m) return;
+  const int64_t i = alm_idx(t.lmax, l, m);
+  const int l0 = m > t.spin ? m : t.spin;
+  if (l < l0) {
+    a1[i] = mk(0.0, 0.0);
+    if (SPIN) a2[i] = mk(0.0, 0.0);
+    return;
+  }
+  double v[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = 0.0;
+  for (int tl = 0; tl < ntile; ++tl) {
+    const double *p = part + (size_t)tl * part_stride + (size_t)i * NV;
+    if (SPIN) {
+      const double4 q = *reinterpret_cast<const double4 *>(p);
+      v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+    } else {
+      const double2 q = *reinterpret_cast<const double2 *>(p);
+      v[0] += q.x; v[1] += q.y;
+    }
+  }
+  const double al = t.alpha[i];
+  const double s1 = al * (fl1 ? fl1[l] : 1.0);
+  if (!SPIN) {
+    a1[i] = mk(s1 * v[0], s1 * v[1]);
+  } else {
+    const double s2 = al * (fl2 ? fl2[l] : 1.0);
+    const double sg = (t.spin & 1) ? -1.0 : 1.0;
+    // +a = S+, -a' = (-1)^s S-;  G = -1/2 (+a + -a') ; C = i/2 (+a - -a')
+    const double pr = v[0], pi = v[1], mr = sg * v[2], mi = sg * v[3];
+    a1[i] = mk(-0.5 * s1 * (pr + mr), -0.5 * s1 * (pi + mi));
+    a2[i] = mk(-0.5 * s2 * (pi - mi), 0.5 * s2 * (pr - mr));
+  }
+}
+
+// ------------------------------------------------------------------ alm BLAS-1
+__global__ void almxfl_kernel(int lmax, const cplx *__restrict__ in, const double *__restrict__ fl, int nfl,
+                              cplx *__restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > lmax || l < m) return;
+  const int64_t i = alm_idx(lmax, l, m);
+  const double f = l < nfl ? fl[l] : 0.0;
+  const cplx a = in[i];
+  out[i] = mk(f * a.x, f * a.y);
+}
+
+__global__ void axpy_kernel(long long n2, double a, const double *__restrict__ a_dev, const double *__restrict__ x,
+                            double *__restrict__ y) {
+  const double aa = a_dev ? *a_dev : a;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fma(aa, x[i], y[i]);
+}
+
+PLK_D double block_sum(double v, double *sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = l < (blockDim.x >> 5) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;   // valid in thread 0
+}
+
+// one block per m: partial[m] = w_m sum_{l>=max(m,lmin)} Re(a conj b)
+__global__ void dot_partial_kernel(int lmax, int lmin, const cplx *__restrict__ a, const cplx *__restrict__ b,
+                                   double *__restrict__ partial) {
+  __shared__ double sh[32];
+  const int m = blockIdx.x;
+  double acc = 0.0;
+  const int lo = m > lmin ? m : lmin;
+  const int64_t base = alm_idx(lmax, 0, m);
+  for (int l = lo + threadIdx.x; l <= lmax; l += blockDim.x) {
+    const cplx x = a[base + l], y = b[base + l];
+    acc = fma(x.x, y.x, fma(x.y, y.y, acc));
+  }
+  double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[m] = (m == 0 ? 1.0 : 2.0) * r;
+}
+// fixed-order final reduction, nout independent sums laid out as partial[j * n + i]
+__global__ void final_sum_kernel(const double *__restrict__ partial, int n, int nout, double *__restrict__ out) {
+  __shared__ double sh[32];
+  for (int j = 0; j < nout; ++j) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[(size_t)j * n + i];
+    double r = block_sum(acc, sh);
+    if (threadIdx.x == 0) out[j] = r;
+  }
+}
+
+__global__ void alm_copy_kernel(int lmax_in, const cplx *__restrict__ in, int lmax_out, cplx *__restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > lmax_out || l < m) return;
+  out[alm_idx(lmax_out, l, m)] = (l <= lmax_in && m <= lmax_in) ? in[alm_idx(lmax_in, l, m)] : mk(0.0, 0.0);
+}
+__global__ void alm_splice_kernel(int lmax_lo, const cplx *__restrict__ lo, int lmax_hi, const cplx *__restrict__ hi,
+                                  int lsplit, cplx *__restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > lmax_hi || l < m) return;
+  const int64_t i = alm_idx(lmax_hi, l, m);
+  out[i] = (l <= lsplit) ? lo[alm_idx(lmax_lo, l, m)] : hi[i];
+}
+
+// ------------------------------------------------------------------ per-pixel passes
+__global__ void map_mul_kernel(long long n, double *__restrict__ y, const double *__restrict__ a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] *= a[i];
+}
+__global__ void map_mul2_kernel(long long n, double *__restrict__ g, double *__restrict__ c, const double *__restrict__ t) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double tt = t[i];
+    g[i] *= tt; c[i] *= tt;
+  }
+}
+__global__ void map_qe_pp_kernel(long long n, const double *__restrict__ q, const double *__restrict__ u,
+                                 const double *__restrict__ g3, const double *__restrict__ c3,
+                                 const double *__restrict__ g1, const double *__restrict__ c1, double *__restrict__ re,
+                                 double *__restrict__ im) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double Q = q[i], U = u[i];
+    // (Q - iU)(G3 + iC3) - (Q + iU)(G1 - iC1)
+    const double r = (Q * g3[i] + U * c3[i]) - (Q * g1[i] + U * c1[i]);
+    const double s = (Q * c3[i] - U * g3[i]) - (U * g1[i] - Q * c1[i]);
+    re[i] = r; im[i] = s;
+  }
+}
+__global__ void map_ninv3_kernel(long long n, double *__restrict__ q, double *__restrict__ u,
+                                 const double *__restrict__ nqq, const double *__restrict__ nqu,
+                                 const double *__restrict__ nuu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double Q = q[i], U = u[i];
+    q[i] = nqq[i] * Q + nqu[i] * U;
+    u[i] = nuu[i] * U + nqu[i] * Q;
+  }
+}
+
+// monopole / dipole templates: one block per ring; pixel direction from the ring geometry
+struct DevRings {
+  int nring;
+  const long long *start;   // [nring]
+  const int *nphi;          // [nring]
+  const int *shifted;       // [nring]
+  const double *z, *sth;    // [nring]
+};
+__global__ void modes_dot_kernel(DevRings r, double *__restrict__ m, const double *__restrict__ w,
+                                 double *__restrict__ partial) {
+  __shared__ double sh[32];
+  const int ir = blockIdx.x;
+  const int n = r.nphi[ir];
+  const long long st = r.start[ir];
+  const double z = r.z[ir], s = r.sth[ir];
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double v = m[st + j];
+    if (w) { v *= w[st + j]; m[st + j] = v; }
+    const cplx e = expipi_frac(r.shifted[ir] + 2 * j, n);
+    a0 += v; a1 = fma(v, s * e.x, a1); a2 = fma(v, s * e.y, a2); a3 = fma(v, z, a3);
+  }
+  double r0 = block_sum(a0, sh), r1 = block_sum(a1, sh), r2 = block_sum(a2, sh), r3 = block_sum(a3, sh);
+  if (threadIdx.x == 0) {
+    partial[0 * r.nring + ir] = r0; partial[1 * r.nring + ir] = r1;
+    partial[2 * r.nring + ir] = r2; partial[3 * r.nring + ir] = r3;
+  }
+}
+// m_p -= w_p * sum_a mode_a(p) coef_a,  coef = pinv(4x4, row-major) @ sums
+__global__ void modes_sub_kernel(DevRings r, double *__restrict__ m, const double *__restrict__ w,
+                                 const double *__restrict__ sums, const double *__restrict__ pinv) {
+  const int ir = blockIdx.x;
+  const int n = r.nphi[ir];
+  const long long st = r.start[ir];
+  const double z = r.z[ir], s = r.sth[ir];
+  double c[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    c[a] = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) c[a] = fma(pinv[a * 4 + b], sums[b], c[a]);
+  }
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const cplx e = expipi_frac(r.shifted[ir] + 2 * j, n);
+    const double pm = c[0] + c[1] * (s * e.x) + c[2] * (s * e.y) + c[3] * z;
+    const double ww = w ? w[st + j] : 1.0;
+    m[st + j] -= ww * pm;
+  }
+}
+
+}  // namespace plk

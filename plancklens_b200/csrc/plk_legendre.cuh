@@ -1,0 +1,550 @@
+// Legendre stage of the spin-weighted SHT for sm_100a: seed (ramp-up) kernel, synthesis and analysis kernels.
+//
+// Work decomposition: a thread owns NR iso-latitude ring PAIRS (north ring + southern twin share the
+// recurrence through  slam_lm(pi-theta) = (-1)^{l+m} (-s)lam_lm(theta) ), a block owns one m and a tile of
+// NCW*32*NR pairs, and walks l in chunks.  Per-l data (pre-scaled a_lm and the recurrence coefficients U,V)
+// are staged global->shared with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) by a producer
+// warp through a NSTAGE ring; the compute warps read them as broadcast LDS.128.
+//
+// FP64 pipe cost per (l, ring pair): spin 0: 1 DMUL + 3 DFMA ; spin s: 12 DFMA (2 coefficient, 2 recurrence,
+// 8 accumulate) -- the figures SURVEY.md section 8(d) uses for the roofline.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "plk_common.h"
+
+namespace plk {
+
+constexpr int kChunk = 128;      // l values per TMA stage (even)
+constexpr int kStages = 4;
+constexpr int kNCW = 4;          // compute warps per block
+constexpr int kSeedThrExp = -120;  // accumulation starts once |p_l| >= 2^-120 (libsharp itself uses 2^-60)
+
+struct DevGeom {
+  int nside, npair, nring;
+  long long npix;
+  const double *cth;
+  const double *sh_hi, *sh_lo, *ch_hi, *ch_lo;
+};
+
+struct DevSpin {
+  int spin, lmax, mmax;
+  const double2 *UV;       // [alm_idx]
+  const double *alpha;     // [alm_idx]
+  const double *k_hi, *k_lo;
+  const int *k_e, *pc, *ps;
+  const signed char *sg_p, *sg_m;
+  // seeds, [m * npair + ip]
+  int *ks;                 // first accumulated offset k = l - l0(m) (even); K(m) or more = skip
+  double *s0, *s1;         // p^+_{l-1}, p^+_l at l = l0 + ks
+  double *s2, *s3;         // p^-  (spin > 0)
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+PLK_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PLK_D void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+PLK_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+PLK_D void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PLK_D void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+PLK_D void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t a = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on an mbarrier.
+PLK_D void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+PLK_D void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------- seeds
+// One thread per (m, ring pair): evaluates the closed-form d^{l0} seed in extended-range double-double, runs the
+// normalised recurrence with a power-of-two scale until the true value is >= 2^kSeedThrExp, and stores the
+// (even) start offset together with the two (four) plain-double start values.
+template <bool SPIN>
+PLK_HD void seed_one(const DevGeom &g, const DevSpin &t, int m, int ip, int &ks_out, double &o0, double &o1, double &o2,
+                     double &o3) {
+  const int s = t.spin, lmax = t.lmax;
+  const int l0 = m > s ? m : s;
+  const int K = lmax - l0 + 1;
+  ks_out = K > 0 ? K : 0; o0 = o1 = o2 = o3 = 0.0;
+  if (K <= 0) return;
+  xdd ch = xdd_norm(g.ch_hi[ip], g.ch_lo[ip], 0);
+  xdd sh = xdd_norm(g.sh_hi[ip], g.sh_lo[ip], 0);
+  xdd kap; kap.hi = t.k_hi[m]; kap.lo = t.k_lo[m]; kap.e = t.k_e[m];
+  const int pc = t.pc[m], ps = t.ps[m];
+  xdd cpc = xdd_pow(ch, pc), sps = xdd_pow(sh, ps);
+  xdd sp = xdd_mul(kap, xdd_mul(cpc, sps));
+  double ap_m = 0.0, ap_c = (sp.hi + sp.lo) * (double)t.sg_p[m];
+  int ep = sp.e;
+  double am_m = 0.0, am_c = 0.0;
+  int em = 0;
+  if (SPIN) {
+    xdd cps = xdd_pow(ch, ps), spc = xdd_pow(sh, pc);
+    xdd sm = xdd_mul(kap, xdd_mul(cps, spc));
+    am_c = (sm.hi + sm.lo) * (double)t.sg_m[m];
+    em = sm.e;
+  }
+  const double x = g.cth[ip];
+  const double2 *UV = t.UV + alm_idx(lmax, 0, m);
+  const double big = ldexp(1.0, 128), small = ldexp(1.0, -128);
+  int k = 0;
+  for (;;) {
+    if ((k & 1) == 0) {
+      // true magnitudes: |a_c| * 2^e ; a_c in [2^-129, 2^128] (or 0)
+      bool okp = (ap_c != 0.0) && (ilogb(ap_c) + ep >= kSeedThrExp);
+      bool okm = SPIN && (am_c != 0.0) && (ilogb(am_c) + em >= kSeedThrExp);
+      if (okp || okm) break;
+    }
+    if (k >= K - 1) { ks_out = K; return; }   // never reaches the threshold inside the band: pair skipped for this m
+    const double2 uv = UV[l0 + k];
+    {
+      double tp = fma(x, uv.x, uv.y);
+      double n = fma(tp, ap_c, -ap_m);
+      ap_m = ap_c; ap_c = n;
+      if (fabs(ap_c) > big) { ap_c *= small; ap_m *= small; ep += 128; }
+    }
+    if (SPIN) {
+      double tm = fma(x, uv.x, -uv.y);
+      double n = fma(tm, am_c, -am_m);
+      am_m = am_c; am_c = n;
+      if (fabs(am_c) > big) { am_c *= small; am_m *= small; em += 128; }
+    }
+    ++k;
+  }
+  ks_out = k;
+  // ldexp of a denormal-range result flushes gracefully; both sequences are > 2^-400 here by construction
+  o0 = ldexp(ap_m, ep); o1 = ldexp(ap_c, ep);
+  if (SPIN) { o2 = ldexp(am_m, em); o3 = ldexp(am_c, em); }
+}
+
+template <bool SPIN>
+__global__ void seed_kernel(DevGeom g, DevSpin t) {
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (ip >= g.npair || m > t.mmax) return;
+  int ks; double a, b, c, d;
+  seed_one<SPIN>(g, t, m, ip, ks, a, b, c, d);
+  const size_t o = (size_t)m * g.npair + ip;
+  t.ks[o] = ks; t.s0[o] = a; t.s1[o] = b;
+  if (SPIN) { t.s2[o] = c; t.s3[o] = d; }
+}
+
+// ---------------------------------------------------------------------------------------------- shared layout
+template <bool SPIN, bool SYNTH>
+struct StageBytes {
+  // synthesis spin0: a' (16 B) + UV (16 B); spin: H+,H- (32 B) + UV (16 B); analysis: UV only
+  static constexpr int rec = SYNTH ? (SPIN ? 32 : 16) : 0;
+  static constexpr int per_l = rec + 16;
+  static constexpr int stage = per_l * kChunk;
+};
+
+struct PipeState {
+  uint64_t *full, *empty;
+};
+
+// Producer warp body: streams chunks [c0, nchunk) of row m into the stage ring.
+template <bool SPIN, bool SYNTH>
+PLK_D void producer_loop(unsigned char *stage_base, uint64_t *full, uint64_t *empty, const void *rec_row,
+                         const double2 *uv_row, int K, int c0, int nchunk, int nconsumers) {
+  using SB = StageBytes<SPIN, SYNTH>;
+  if ((threadIdx.x & 31) != 0) return;
+  for (int c = c0; c < nchunk; ++c) {
+    const int it = c - c0;
+    const int st = it % kStages;
+    if (it >= kStages) mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
+    const int k0 = c * kChunk;
+    const int n = min(kChunk, K - k0);
+    unsigned char *dst = stage_base + (size_t)st * SB::stage;
+    const uint32_t bytes = (uint32_t)n * SB::per_l;
+    mbar_expect_tx(&full[st], bytes);
+    if (SYNTH) tma_load_1d(dst, (const unsigned char *)rec_row + (size_t)k0 * SB::rec, (uint32_t)n * SB::rec, &full[st]);
+    tma_load_1d(dst + SB::rec * kChunk, uv_row + k0, (uint32_t)n * 16, &full[st]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- synthesis
+// rec rows: spin 0: double2 a'_l = alpha_l * fl_l * a_lm ; spin s: double4 {H+ re, H+ im, H- re, H- im} with
+//   H+ = -1/2 alpha (G + iC),  H- = -1/2 (-1)^s alpha (G - iC)        (prepared by prep_alm_kernel)
+// output phase arrays X1 (, X2): [ring][pitch] complex, map(phi) = X_0 + 2 Re sum_{m>0} X_m e^{i m phi}
+template <bool SPIN, int NR>
+__global__ void __launch_bounds__((kNCW + 1) * 32)
+legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *__restrict__ X1, cplx *__restrict__ X2,
+                      int pitch, const int *__restrict__ morder) {
+  using SB = StageBytes<SPIN, true>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + kStages;
+  int *s_kmin = reinterpret_cast<int *>(empty + kStages);
+  unsigned char *stage_base = smem + 128;
+
+  const int m = morder[blockIdx.y];
+  const int s = t.spin, lmax = t.lmax;
+  const int l0 = m > s ? m : s;
+  const int K = lmax - l0 + 1;
+  if (K <= 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_pairs = kNCW * 32 * NR;
+  const int pair0 = blockIdx.x * tile_pairs + warp * 32 * NR + lane;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kNCW); }
+    mbar_fence_init();
+    *s_kmin = 1 << 30;
+  }
+  __syncthreads();
+
+  // per-thread ring-pair state
+  int ks[NR];
+  double x[NR];
+  size_t so[NR];
+  int kw_min = 1 << 30, kw_max = -1;
+  if (warp < kNCW) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      const int ip = pair0 + 32 * j;
+      if (ip < g.npair) {
+        so[j] = (size_t)m * g.npair + ip;
+        ks[j] = t.ks[so[j]];
+        x[j] = g.cth[ip];
+      } else { so[j] = 0; ks[j] = 1 << 30; x[j] = 0.0; }
+      if (ks[j] < K) { kw_min = min(kw_min, ks[j]); kw_max = max(kw_max, ks[j]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kw_min = min(kw_min, __shfl_xor_sync(0xffffffffu, kw_min, o));
+      kw_max = max(kw_max, __shfl_xor_sync(0xffffffffu, kw_max, o));
+    }
+    if (lane == 0) atomicMin(s_kmin, kw_min);
+  }
+  __syncthreads();
+  const int kb_min = *s_kmin;
+  const size_t row = (size_t)alm_idx(lmax, l0, m);
+  const int nchunk = (K + kChunk - 1) / kChunk;
+  const int c0 = kb_min >= K ? nchunk : kb_min / kChunk;
+
+  if (warp == kNCW) {
+    const unsigned char *rec_row = (const unsigned char *)rec + row * SB::rec;
+    producer_loop<SPIN, true>(stage_base, full, empty, rec_row, t.UV + row, K, c0, nchunk, kNCW);
+    return;
+  }
+
+  // accumulators
+  double pc_[NR], pm_[NR], qc_[NR], qm_[NR];
+  double a0r[NR], a0i[NR], a1r[NR], a1i[NR];   // spin0: even / odd ; spin: north A+ (P), north A- (M)
+  double b0r[NR], b0i[NR], b1r[NR], b1i[NR];   // spin: south A+ (uses p-), south A- (uses p+)
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    pc_[j] = pm_[j] = qc_[j] = qm_[j] = 0.0;
+    a0r[j] = a0i[j] = a1r[j] = a1i[j] = b0r[j] = b0i[j] = b1r[j] = b1i[j] = 0.0;
+  }
+
+  for (int c = c0; c < nchunk; ++c) {
+    const int it = c - c0;
+    const int st = it % kStages;
+    mbar_wait(&full[st], (it / kStages) & 1);
+    const int k0 = c * kChunk;
+    const int kend = min(k0 + kChunk, K);
+    if (kend > kw_min) {
+      const unsigned char *sb = stage_base + (size_t)st * SB::stage;
+      const double2 *uvs = reinterpret_cast<const double2 *>(sb + SB::rec * kChunk);
+      int k = max(k0, kw_min);   // even
+      for (; k < kend; k += 2) {
+        if (k <= kw_max) {
+#pragma unroll
+          for (int j = 0; j < NR; ++j)
+            if (k == ks[j]) {
+              pm_[j] = t.s0[so[j]]; pc_[j] = t.s1[so[j]];
+              if (SPIN) { qm_[j] = t.s2[so[j]]; qc_[j] = t.s3[so[j]]; }
+            }
+        }
+        const int kk = k - k0;
+        const bool two = (k + 1 < kend);
+        if (!SPIN) {
+          const double2 *as = reinterpret_cast<const double2 *>(sb);
+          const double2 e = as[kk], ue = uvs[kk];
+          const double2 o = two ? as[kk + 1] : make_double2(0.0, 0.0);
+          const double2 uo = two ? uvs[kk + 1] : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            a0r[j] = fma(e.x, pc_[j], a0r[j]); a0i[j] = fma(e.y, pc_[j], a0i[j]);
+            double n1 = fma(x[j] * ue.x, pc_[j], -pm_[j]);
+            a1r[j] = fma(o.x, n1, a1r[j]); a1i[j] = fma(o.y, n1, a1i[j]);
+            double n2 = fma(x[j] * uo.x, n1, -pc_[j]);
+            if (two) { pm_[j] = n1; pc_[j] = n2; } else { pm_[j] = pc_[j]; pc_[j] = n1; }
+          }
+        } else {
+          const double4 *hs = reinterpret_cast<const double4 *>(sb);
+          const double4 he = hs[kk];
+          const double2 ue = uvs[kk];
+          const double4 ho = two ? hs[kk + 1] : make_double4(0.0, 0.0, 0.0, 0.0);
+          const double2 uo = two ? uvs[kk + 1] : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            // even offset: sigma = +1
+            a0r[j] = fma(he.x, pc_[j], a0r[j]); a0i[j] = fma(he.y, pc_[j], a0i[j]);   // north A+ += H+ p+
+            b1r[j] = fma(he.z, pc_[j], b1r[j]); b1i[j] = fma(he.w, pc_[j], b1i[j]);   // south A- += H- p+
+            a1r[j] = fma(he.z, qc_[j], a1r[j]); a1i[j] = fma(he.w, qc_[j], a1i[j]);   // north A- += H- p-
+            b0r[j] = fma(he.x, qc_[j], b0r[j]); b0i[j] = fma(he.y, qc_[j], b0i[j]);   // south A+ += H+ p-
+            double np = fma(fma(x[j], ue.x, ue.y), pc_[j], -pm_[j]);
+            double nq = fma(fma(x[j], ue.x, -ue.y), qc_[j], -qm_[j]);
+            // odd offset: sigma = -1 on the southern sums
+            a0r[j] = fma(ho.x, np, a0r[j]); a0i[j] = fma(ho.y, np, a0i[j]);
+            b1r[j] = fma(-ho.z, np, b1r[j]); b1i[j] = fma(-ho.w, np, b1i[j]);
+            a1r[j] = fma(ho.z, nq, a1r[j]); a1i[j] = fma(ho.w, nq, a1i[j]);
+            b0r[j] = fma(-ho.x, nq, b0r[j]); b0i[j] = fma(-ho.y, nq, b0i[j]);
+            double np2 = fma(fma(x[j], uo.x, uo.y), np, -pc_[j]);
+            double nq2 = fma(fma(x[j], uo.x, -uo.y), nq, -qc_[j]);
+            if (two) { pm_[j] = np; pc_[j] = np2; qm_[j] = nq; qc_[j] = nq2; }
+            else { pm_[j] = pc_[j]; pc_[j] = np; qm_[j] = qc_[j]; qc_[j] = nq; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+
+  // sigma at even offset is (-1)^{l0+m}
+  const double sg0 = ((l0 + m) & 1) ? -1.0 : 1.0;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    const int ip = pair0 + 32 * j;
+    if (ip >= g.npair) continue;
+    const int rn = ip, rs = g.nring - 1 - ip;
+    if (!SPIN) {
+      X1[(size_t)rn * pitch + m] = mk(a0r[j] + a1r[j], a0i[j] + a1i[j]);
+      if (rs != rn) X1[(size_t)rs * pitch + m] = mk(sg0 * (a0r[j] - a1r[j]), sg0 * (a0i[j] - a1i[j]));
+    } else {
+      // X1 = P + M ; X2 = -i (P - M)
+      X1[(size_t)rn * pitch + m] = mk(a0r[j] + a1r[j], a0i[j] + a1i[j]);
+      X2[(size_t)rn * pitch + m] = mk(a0i[j] - a1i[j], -(a0r[j] - a1r[j]));
+      if (rs != rn) {
+        X1[(size_t)rs * pitch + m] = mk(sg0 * (b0r[j] + b1r[j]), sg0 * (b0i[j] + b1i[j]));
+        X2[(size_t)rs * pitch + m] = mk(sg0 * (b0i[j] - b1i[j]), -sg0 * (b0r[j] - b1r[j]));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- analysis
+// Input phase arrays X1 (, X2): X_m(ring) = sum_j map_j e^{-i m phi_j} (unweighted).
+// Output partial sums part[tile][alm_idx(l,m)][NV] (NV = 2 doubles spin 0, 4 doubles spin s):
+//   spin 0:  S_l   = sum_pairs p_l (X_n + sigma_l X_s)
+//   spin s:  S+_l  = sum_pairs [p+ F+_n + sigma_l p- F+_s],  S-_l = sum_pairs [p- F-_n + sigma_l p+ F-_s],
+//            F+- = X1 +- i X2.   alpha, quadrature weight and the G/C recombination are applied by
+//            finish_alm_kernel, which also reduces over tiles (deterministic order).
+// Cross-lane reduction: 16 accumulators per lane (8 l x 2 or 4 l x 4) -> butterfly reduce-scatter
+// (8+4+2+1+1 shuffles) -> one value per lane pair -> per-warp shared slice -> summed over warps per chunk.
+template <bool SPIN>
+PLK_D void butterfly16(double (&v)[16], int lane) {
+#pragma unroll
+  for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < h) {
+        double send = up ? v[j] : v[j + h];
+        double keep = up ? v[j + h] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <bool SPIN, int NR>
+__global__ void __launch_bounds__((kNCW + 1) * 32)
+legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cplx *__restrict__ X2, int pitch,
+                     double *__restrict__ part, long long part_stride /* doubles per tile */,
+                     const int *__restrict__ morder) {
+  using SB = StageBytes<SPIN, false>;
+  constexpr int NV = SPIN ? 4 : 2;
+  constexpr int NB = 16 / NV;   // l values per butterfly batch
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + kStages;
+  int *s_kmin = reinterpret_cast<int *>(empty + kStages);
+  unsigned char *stage_base = smem + 128;
+  double *red = reinterpret_cast<double *>(stage_base + (size_t)kStages * SB::stage);  // [2][kNCW][kChunk*NV]
+
+  const int m = morder[blockIdx.y];
+  const int s = t.spin, lmax = t.lmax;
+  const int l0 = m > s ? m : s;
+  const int K = lmax - l0 + 1;
+  if (K <= 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_pairs = kNCW * 32 * NR;
+  const int pair0 = blockIdx.x * tile_pairs + warp * 32 * NR + lane;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kNCW); }
+    mbar_fence_init();
+    *s_kmin = 1 << 30;
+  }
+  __syncthreads();
+
+  int ks[NR];
+  double x[NR];
+  size_t so[NR];
+  // ring data: spin0: fe = Xn + sg0 Xs, fo = Xn - sg0 Xs ; spin: F+n, F-n, sg0 F+s, sg0 F-s
+  double f0r[NR], f0i[NR], f1r[NR], f1i[NR], f2r[NR], f2i[NR], f3r[NR], f3i[NR];
+  int kw_min = 1 << 30, kw_max = -1;
+  const double sg0 = ((l0 + m) & 1) ? -1.0 : 1.0;
+  if (warp < kNCW) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      const int ip = pair0 + 32 * j;
+      f0r[j] = f0i[j] = f1r[j] = f1i[j] = f2r[j] = f2i[j] = f3r[j] = f3i[j] = 0.0;
+      if (ip < g.npair) {
+        so[j] = (size_t)m * g.npair + ip;
+        ks[j] = t.ks[so[j]];
+        x[j] = g.cth[ip];
+        const int rn = ip, rs = g.nring - 1 - ip;
+        if (ks[j] < K) {
+          const cplx n1 = X1[(size_t)rn * pitch + m];
+          const cplx s1 = (rs != rn) ? X1[(size_t)rs * pitch + m] : mk(0.0, 0.0);
+          if (!SPIN) {
+            f0r[j] = n1.x + sg0 * s1.x; f0i[j] = n1.y + sg0 * s1.y;
+            f1r[j] = n1.x - sg0 * s1.x; f1i[j] = n1.y - sg0 * s1.y;
+          } else {
+            const cplx n2 = X2[(size_t)rn * pitch + m];
+            const cplx s2 = (rs != rn) ? X2[(size_t)rs * pitch + m] : mk(0.0, 0.0);
+            // F+ = X1 + i X2 ; F- = X1 - i X2
+            f0r[j] = n1.x - n2.y; f0i[j] = n1.y + n2.x;            // F+ north
+            f1r[j] = n1.x + n2.y; f1i[j] = n1.y - n2.x;            // F- north
+            f2r[j] = sg0 * (s1.x - s2.y); f2i[j] = sg0 * (s1.y + s2.x);   // sigma0 F+ south
+            f3r[j] = sg0 * (s1.x + s2.y); f3i[j] = sg0 * (s1.y - s2.x);   // sigma0 F- south
+          }
+        }
+      } else { so[j] = 0; ks[j] = 1 << 30; x[j] = 0.0; }
+      if (ks[j] < K) { kw_min = min(kw_min, ks[j]); kw_max = max(kw_max, ks[j]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kw_min = min(kw_min, __shfl_xor_sync(0xffffffffu, kw_min, o));
+      kw_max = max(kw_max, __shfl_xor_sync(0xffffffffu, kw_max, o));
+    }
+    if (lane == 0) atomicMin(s_kmin, kw_min);
+  }
+  __syncthreads();
+  const int kb_min = *s_kmin;
+  const size_t row = (size_t)alm_idx(lmax, l0, m);
+  const int nchunk = (K + kChunk - 1) / kChunk;
+  const int c0 = kb_min >= K ? nchunk : kb_min / kChunk;
+  double *prow = part + (size_t)blockIdx.x * part_stride + row * NV;
+
+  if (warp == kNCW) {
+    producer_loop<SPIN, false>(stage_base, full, empty, nullptr, t.UV + row, K, c0, nchunk, kNCW);
+    return;
+  }
+  // chunks before c0 carry no contribution from this tile: write zeros
+  for (int i = threadIdx.x; i < min(c0 * kChunk, K) * NV; i += kNCW * 32) prow[i] = 0.0;
+
+  double pc_[NR], pm_[NR], qc_[NR], qm_[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) pc_[j] = pm_[j] = qc_[j] = qm_[j] = 0.0;
+
+  for (int c = c0; c < nchunk; ++c) {
+    const int it = c - c0;
+    const int st = it % kStages;
+    mbar_wait(&full[st], (it / kStages) & 1);
+    const int k0 = c * kChunk;
+    const int kend = min(k0 + kChunk, K);
+    double *myred = red + ((size_t)(it & 1) * kNCW + warp) * (kChunk * NV);
+    const double2 *uvs = reinterpret_cast<const double2 *>(stage_base + (size_t)st * SB::stage);
+    if (kend <= kw_min) {
+      for (int i = lane; i < kChunk * NV; i += 32) myred[i] = 0.0;
+    } else {
+      for (int kb = k0; kb < k0 + kChunk; kb += NB) {
+        double acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+        if (kb + NB > kw_min && kb < kend) {
+#pragma unroll
+          for (int b = 0; b < NB; b += 2) {
+            const int k = kb + b;
+            if (k < kend) {
+              if (k <= kw_max && k >= kw_min) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j)
+                  if (k == ks[j]) {
+                    pm_[j] = t.s0[so[j]]; pc_[j] = t.s1[so[j]];
+                    if (SPIN) { qm_[j] = t.s2[so[j]]; qc_[j] = t.s3[so[j]]; }
+                  }
+              }
+              const bool two = (k + 1 < kend);
+              const double2 ue = uvs[k - k0];
+              const double2 uo = two ? uvs[k - k0 + 1] : make_double2(0.0, 0.0);
+#pragma unroll
+              for (int j = 0; j < NR; ++j) {
+                if (!SPIN) {
+                  acc[b * 2 + 0] = fma(pc_[j], f0r[j], acc[b * 2 + 0]);
+                  acc[b * 2 + 1] = fma(pc_[j], f0i[j], acc[b * 2 + 1]);
+                  double n1 = fma(x[j] * ue.x, pc_[j], -pm_[j]);
+                  acc[b * 2 + 2] = fma(n1, f1r[j], acc[b * 2 + 2]);
+                  acc[b * 2 + 3] = fma(n1, f1i[j], acc[b * 2 + 3]);
+                  double n2 = fma(x[j] * uo.x, n1, -pc_[j]);
+                  if (two) { pm_[j] = n1; pc_[j] = n2; } else { pm_[j] = pc_[j]; pc_[j] = n1; }
+                } else {
+                  // even offset (sigma = +sigma0 folded in f2,f3)
+                  acc[b * 4 + 0] = fma(pc_[j], f0r[j], fma(qc_[j], f2r[j], acc[b * 4 + 0]));   // S+ re
+                  acc[b * 4 + 1] = fma(pc_[j], f0i[j], fma(qc_[j], f2i[j], acc[b * 4 + 1]));   // S+ im
+                  acc[b * 4 + 2] = fma(qc_[j], f1r[j], fma(pc_[j], f3r[j], acc[b * 4 + 2]));   // S- re
+                  acc[b * 4 + 3] = fma(qc_[j], f1i[j], fma(pc_[j], f3i[j], acc[b * 4 + 3]));   // S- im
+                  double np = fma(fma(x[j], ue.x, ue.y), pc_[j], -pm_[j]);
+                  double nq = fma(fma(x[j], ue.x, -ue.y), qc_[j], -qm_[j]);
+                  // odd offset: southern terms change sign
+                  acc[b * 4 + 4] = fma(np, f0r[j], fma(-nq, f2r[j], acc[b * 4 + 4]));
+                  acc[b * 4 + 5] = fma(np, f0i[j], fma(-nq, f2i[j], acc[b * 4 + 5]));
+                  acc[b * 4 + 6] = fma(nq, f1r[j], fma(-np, f3r[j], acc[b * 4 + 6]));
+                  acc[b * 4 + 7] = fma(nq, f1i[j], fma(-np, f3i[j], acc[b * 4 + 7]));
+                  double np2 = fma(fma(x[j], uo.x, uo.y), np, -pc_[j]);
+                  double nq2 = fma(fma(x[j], uo.x, -uo.y), nq, -qc_[j]);
+                  if (two) { pm_[j] = np; pc_[j] = np2; qm_[j] = nq; qc_[j] = nq2; }
+                  else { pm_[j] = pc_[j]; pc_[j] = np; qm_[j] = qc_[j]; qc_[j] = nq; }
+                }
+              }
+            }
+          }
+          butterfly16<SPIN>(acc, lane);
+        }
+        // lanes (2i, 2i+1) hold value i of the batch: i = b*NV + v
+        if ((lane & 1) == 0) myred[(kb - k0) * NV + (lane >> 1)] = acc[0];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    named_bar_sync(1, kNCW * 32);
+    // sum the per-warp slices of this chunk and write the tile partial
+    const double *r0 = red + (size_t)(it & 1) * kNCW * (kChunk * NV);
+    const int nval = (kend - k0) * NV;
+    for (int i = threadIdx.x; i < nval; i += kNCW * 32) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < kNCW; ++w) sum += r0[(size_t)w * (kChunk * NV) + i];
+      prow[(size_t)k0 * NV + i] = sum;
+    }
+  }
+}
+
+}  // namespace plk
