@@ -1,0 +1,72 @@
+"""ctypes binding of libplk_b200.so (C ABI in include/plk.h).  Fails loudly: no CPU fallback exists."""
+import ctypes
+import os
+
+from . import _build
+
+_LIB = None
+
+c_int, c_ll, c_dbl, vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_void_p
+
+_SIGS = {
+    'plk_last_error': (ctypes.c_char_p, []),
+    'plk_version': (c_int, []),
+    'plk_launch_count': (c_ll, []),
+    'plk_plan_create': (c_int, [ctypes.POINTER(vp), c_int, c_int, c_int]),
+    'plk_plan_destroy': (c_int, [vp]),
+    'plk_plan_device_bytes': (c_ll, [vp]),
+    'plk_plan_nside': (c_int, [vp]),
+    'plk_plan_lmax': (c_int, [vp]),
+    'plk_alm2map_dev': (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, vp]),
+    'plk_map2alm_dev': (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, vp]),
+    'plk_alm2map_host': (c_int, [vp, c_int, vp, vp, vp, vp]),
+    'plk_map2alm_host': (c_int, [vp, c_int, vp, vp, vp, vp]),
+    'plk_legendre_synth_dev': (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, vp]),
+    'plk_legendre_anal_dev': (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, vp]),
+    'plk_ring_synth_dev': (c_int, [vp, vp, vp, vp]),
+    'plk_ring_anal_dev': (c_int, [vp, vp, vp, vp]),
+    'plk_almxfl_dev': (c_int, [c_int, vp, vp, c_int, vp, vp]),
+    'plk_alm_axpy_dev': (c_int, [c_ll, c_dbl, vp, vp, vp, vp]),
+    'plk_alm_dot_dev': (c_int, [c_int, c_int, vp, vp, vp, vp]),
+    'plk_alm_copy_dev': (c_int, [c_int, vp, c_int, vp, vp]),
+    'plk_alm_splice_dev': (c_int, [c_int, vp, c_int, vp, c_int, vp, vp]),
+    'plk_map_mul_dev': (c_int, [c_ll, vp, vp, vp]),
+    'plk_map_mul2_dev': (c_int, [c_ll, vp, vp, vp, vp]),
+    'plk_map_qe_pp_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'plk_map_ninv3_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp]),
+    'plk_map_modes_dot_dev': (c_int, [vp, vp, vp, vp, vp]),
+    'plk_map_modes_sub_dev': (c_int, [vp, vp, vp, vp, vp, vp]),
+}
+
+EXPORTS = tuple(_SIGS.keys())
+
+
+class PlkError(RuntimeError):
+    pass
+
+
+def load(path=None):
+    """dlopen the library and set argtypes; raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = path or _build.SO
+    if not os.path.exists(path):
+        raise PlkError("libplk_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "or `python -m plancklens_b200._build`; there is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)     # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PlkError("libplk_b200 error %d: %s" % (rc, load().plk_last_error().decode()))
+
+
+def launch_count():
+    return int(load().plk_launch_count())

@@ -1,0 +1,254 @@
+"""Device-side transform plans: thin Python carrier around the C ABI (include/plk.h).
+
+torch tensors are only carriers for device memory and streams; every FLOP runs in libplk_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, vp
+
+_PLANS = {}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.PlkError("plancklens_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def alm_size(lmax):
+    return (lmax + 1) * (lmax + 2) // 2
+
+
+def alm_lmax(size):
+    lmax = int(np.floor(np.sqrt(2 * size) - 1))
+    assert (lmax + 1) * (lmax + 2) // 2 == size, size
+    return lmax
+
+
+def _ptr(t):
+    return vp(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return vp(torch.cuda.current_stream().cuda_stream)
+
+
+def dev_alm(a, device=None):
+    """numpy / torch complex alm -> contiguous complex128 CUDA tensor."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device='cuda', dtype=torch.complex128).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128)).cuda()
+
+
+def dev_map(m):
+    if isinstance(m, torch.Tensor):
+        return m.to(device='cuda', dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(m, dtype=np.float64)).cuda()
+
+
+def dev_fl(fl, lmax):
+    """per-l factor padded / truncated to lmax+1 entries on the device (hp.almxfl zero-pads short fl)."""
+    if fl is None:
+        return None
+    if isinstance(fl, torch.Tensor):
+        fl = fl.detach().cpu().numpy()
+    out = np.zeros(lmax + 1)
+    n = min(lmax + 1, len(fl))
+    out[:n] = np.asarray(fl, dtype=float)[:n]
+    return torch.from_numpy(out).cuda()
+
+
+class Plan:
+    """One (nside, lmax) transform plan on the current CUDA device."""
+
+    def __init__(self, nside, lmax):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.nside, self.lmax = int(nside), int(lmax)
+        self.npix = 12 * self.nside ** 2
+        self.nalm = alm_size(self.lmax)
+        self.nring = 4 * self.nside - 1
+        self.pitch = (self.lmax + 2) & ~1
+        h = vp()
+        check(self.lib.plk_plan_create(ctypes.byref(h), self.nside, self.lmax, self.lmax))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                self.lib.plk_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def device_bytes(self):
+        return int(self.lib.plk_plan_device_bytes(self._h))
+
+    # ---- device tensors in / out
+    def alm2map(self, alm, fl=None, out=None):
+        assert alm.numel() == self.nalm, (alm.numel(), self.nalm)
+        out = torch.empty(self.npix, dtype=torch.float64, device='cuda') if out is None else out
+        check(self.lib.plk_alm2map_dev(self._h, 0, _ptr(alm), None, _ptr(fl), None, _ptr(out), None, _stream()))
+        return out
+
+    def alm2map_spin(self, glm, clm, spin, flg=None, flc=None, out=None):
+        assert spin in (1, 2, 3), spin
+        assert glm.numel() == self.nalm and (clm is None or clm.numel() == self.nalm)
+        if out is None:
+            out = (torch.empty(self.npix, dtype=torch.float64, device='cuda'),
+                   torch.empty(self.npix, dtype=torch.float64, device='cuda'))
+        check(self.lib.plk_alm2map_dev(self._h, spin, _ptr(glm), _ptr(clm), _ptr(flg), _ptr(flc),
+                                       _ptr(out[0]), _ptr(out[1]), _stream()))
+        return out
+
+    def map2alm(self, m, fl=None, out=None):
+        assert m.numel() == self.npix
+        out = torch.empty(self.nalm, dtype=torch.complex128, device='cuda') if out is None else out
+        check(self.lib.plk_map2alm_dev(self._h, 0, _ptr(m), None, _ptr(fl), None, _ptr(out), None, _stream()))
+        return out
+
+    def map2alm_spin(self, m1, m2, spin, flg=None, flc=None, out=None):
+        assert spin in (1, 2, 3), spin
+        assert m1.numel() == self.npix and m2.numel() == self.npix
+        if out is None:
+            out = (torch.empty(self.nalm, dtype=torch.complex128, device='cuda'),
+                   torch.empty(self.nalm, dtype=torch.complex128, device='cuda'))
+        check(self.lib.plk_map2alm_dev(self._h, spin, _ptr(m1), _ptr(m2), _ptr(flg), _ptr(flc),
+                                       _ptr(out[0]), _ptr(out[1]), _stream()))
+        return out
+
+    # ---- stages on their own (profiling / tests)
+    def new_phase(self):
+        return torch.zeros((self.nring, self.pitch), dtype=torch.complex128, device='cuda')
+
+    def legendre_synth(self, spin, a1, a2=None, fl1=None, fl2=None, X1=None, X2=None):
+        X1 = self.new_phase() if X1 is None else X1
+        X2 = (self.new_phase() if X2 is None else X2) if spin else None
+        check(self.lib.plk_legendre_synth_dev(self._h, spin, _ptr(a1), _ptr(a2), _ptr(fl1), _ptr(fl2),
+                                              _ptr(X1), _ptr(X2), _stream()))
+        return X1, X2
+
+    def legendre_anal(self, spin, X1, X2=None, fl1=None, fl2=None):
+        a1 = torch.empty(self.nalm, dtype=torch.complex128, device='cuda')
+        a2 = torch.empty(self.nalm, dtype=torch.complex128, device='cuda') if spin else None
+        check(self.lib.plk_legendre_anal_dev(self._h, spin, _ptr(X1), _ptr(X2), _ptr(fl1), _ptr(fl2),
+                                             _ptr(a1), _ptr(a2), _stream()))
+        return a1, a2
+
+    def ring_synth(self, X, out=None):
+        out = torch.empty(self.npix, dtype=torch.float64, device='cuda') if out is None else out
+        check(self.lib.plk_ring_synth_dev(self._h, _ptr(X), _ptr(out), _stream()))
+        return out
+
+    def ring_anal(self, m, X=None):
+        X = self.new_phase() if X is None else X
+        check(self.lib.plk_ring_anal_dev(self._h, _ptr(m), _ptr(X), _stream()))
+        return X
+
+    # ---- host (numpy) in / out through the library's own staging
+    def alm2map_host(self, spin, a1, a2=None):
+        a1 = np.ascontiguousarray(a1, dtype=np.complex128)
+        assert a1.size == self.nalm, (a1.size, self.nalm)
+        m1 = np.empty(self.npix)
+        m2 = np.empty(self.npix) if spin else None
+        if a2 is not None:
+            a2 = np.ascontiguousarray(a2, dtype=np.complex128)
+        check(self.lib.plk_alm2map_host(self._h, spin, vp(a1.ctypes.data), vp(a2.ctypes.data) if a2 is not None else None,
+                                        vp(m1.ctypes.data), vp(m2.ctypes.data) if spin else None))
+        return (m1, m2) if spin else m1
+
+    def map2alm_host(self, spin, m1, m2=None):
+        m1 = np.ascontiguousarray(m1, dtype=np.float64)
+        assert m1.size == self.npix
+        a1 = np.empty(self.nalm, dtype=np.complex128)
+        a2 = np.empty(self.nalm, dtype=np.complex128) if spin else None
+        if spin:
+            m2 = np.ascontiguousarray(m2, dtype=np.float64)
+        check(self.lib.plk_map2alm_host(self._h, spin, vp(m1.ctypes.data), vp(m2.ctypes.data) if spin else None,
+                                        vp(a1.ctypes.data), vp(a2.ctypes.data) if spin else None))
+        return (a1, a2) if spin else a1
+
+    # ---- template (monopole / dipole) passes
+    def modes_dot(self, m, w=None, out=None):
+        out = torch.empty(4, dtype=torch.float64, device='cuda') if out is None else out
+        check(self.lib.plk_map_modes_dot_dev(self._h, _ptr(m), _ptr(w), _ptr(out), _stream()))
+        return out
+
+    def modes_sub(self, m, w, sums, pinv):
+        check(self.lib.plk_map_modes_sub_dev(self._h, _ptr(m), _ptr(w), _ptr(sums), _ptr(pinv), _stream()))
+        return m
+
+
+def get_plan(nside, lmax):
+    key = (int(nside), int(lmax), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    if key not in _PLANS:
+        _PLANS[key] = Plan(nside, lmax)
+    return _PLANS[key]
+
+
+def clear_plans():
+    _PLANS.clear()
+
+
+# ---- alm BLAS-1 on device tensors
+def almxfl(alm, fl, out=None):
+    """hp.almxfl on a device alm; fl is a device float64 tensor (any length; l >= len(fl) -> 0)."""
+    lib = _lib.load()
+    lmax = alm_lmax(alm.numel())
+    out = torch.empty_like(alm) if out is None else out
+    check(lib.plk_almxfl_dev(lmax, _ptr(alm), _ptr(fl), int(fl.numel()), _ptr(out), _stream()))
+    return out
+
+
+def alm_axpy(y, x, a):
+    """y += a x ; a is a python float or a 1-element device tensor."""
+    lib = _lib.load()
+    if isinstance(a, torch.Tensor):
+        check(lib.plk_alm_axpy_dev(y.numel(), 0.0, _ptr(a), _ptr(x), _ptr(y), _stream()))
+    else:
+        check(lib.plk_alm_axpy_dev(y.numel(), float(a), None, _ptr(x), _ptr(y), _stream()))
+    return y
+
+
+def alm_dot(a, b, lmin=0, out=None):
+    lib = _lib.load()
+    lmax = alm_lmax(a.numel())
+    out = torch.empty(1, dtype=torch.float64, device='cuda') if out is None else out
+    check(lib.plk_alm_dot_dev(lmax, lmin, _ptr(a), _ptr(b), _ptr(out), _stream()))
+    return out
+
+
+def alm_copy(alm, lmax_out):
+    lib = _lib.load()
+    lmax_in = alm_lmax(alm.numel())
+    out = torch.empty(alm_size(lmax_out), dtype=torch.complex128, device='cuda')
+    check(lib.plk_alm_copy_dev(lmax_in, _ptr(alm), lmax_out, _ptr(out), _stream()))
+    return out
+
+
+def alm_splice(lo, hi, lsplit):
+    lib = _lib.load()
+    out = torch.empty_like(hi)
+    check(lib.plk_alm_splice_dev(alm_lmax(lo.numel()), _ptr(lo), alm_lmax(hi.numel()), _ptr(hi), lsplit, _ptr(out), _stream()))
+    return out
+
+
+def map_mul(y, a):
+    check(_lib.load().plk_map_mul_dev(y.numel(), _ptr(y), _ptr(a), _stream()))
+    return y
+
+
+def map_mul2(g, c, t):
+    check(_lib.load().plk_map_mul2_dev(g.numel(), _ptr(g), _ptr(c), _ptr(t), _stream()))
+
+
+def map_qe_pp(q, u, g3, c3, g1, c1, re, im):
+    check(_lib.load().plk_map_qe_pp_dev(q.numel(), _ptr(q), _ptr(u), _ptr(g3), _ptr(c3), _ptr(g1), _ptr(c1),
+                                       _ptr(re), _ptr(im), _stream()))
+
+
+def map_ninv3(q, u, nqq, nqu, nuu):
+    check(_lib.load().plk_map_ninv3_dev(q.numel(), _ptr(q), _ptr(u), _ptr(nqq), _ptr(nqu), _ptr(nuu), _stream()))
