@@ -94,6 +94,17 @@ int plk_alm_copy_dev(int lmax_in, const void *in, int lmax_out, void *out, void 
 /* out (lmax_hi) = lo for l <= lsplit, hi for l > lsplit */
 int plk_alm_splice_dev(int lmax_lo, const void *lo, int lmax_hi, const void *hi, int lsplit, void *out, void *stream);
 
+/* out = ca * x + cb * y  (y may be NULL);  eblm / cd_solve vector arithmetic (util_alm.py:66-86, cd_solve.py:57-86) */
+int plk_alm_lincomb_dev(long long n, double ca, const void *x, double cb, const void *y, void *out, void *stream);
+/* out[l,m] = sum_{j<nterm} fl[j][l] * in[j][l,m], nterm <= 4 (host arrays of device pointers): the Wiener-filter
+ * combinations of qest.py:582-588, 613-618 and the 2x2 per-l matrices of opfilt_pp.py:82-84, 101-105 */
+int plk_alm_combine_dev(int lmax, int nterm, const void *const *in, const double *const *fl, const int *nfl,
+                        void *out, void *stream);
+/* real-harmonic packing of the dense preconditioner (qcinv/dense.py:16-53) and its mat-vec (dense.py:118-119) */
+int plk_alm2rlm_dev(int lmax, const void *alm, double *rlm, void *stream);
+int plk_rlm2alm_dev(int lmax, const double *rlm, void *alm, void *stream);
+int plk_dense_matvec_dev(int n, const double *A, const double *x, double *y, void *stream);
+
 /* ---- per-pixel passes (device pointers, n pixels) */
 /* y = y * a            */
 int plk_map_mul_dev(long long n, double *y, const double *a, void *stream);

@@ -30,6 +30,11 @@ _SIGS = {
     'plk_alm_dot_dev': (c_int, [c_int, c_int, vp, vp, vp, vp]),
     'plk_alm_copy_dev': (c_int, [c_int, vp, c_int, vp, vp]),
     'plk_alm_splice_dev': (c_int, [c_int, vp, c_int, vp, c_int, vp, vp]),
+    'plk_alm_lincomb_dev': (c_int, [c_ll, c_dbl, vp, c_dbl, vp, vp, vp]),
+    'plk_alm_combine_dev': (c_int, [c_int, c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(c_int), vp, vp]),
+    'plk_alm2rlm_dev': (c_int, [c_int, vp, vp, vp]),
+    'plk_rlm2alm_dev': (c_int, [c_int, vp, vp, vp]),
+    'plk_dense_matvec_dev': (c_int, [c_int, vp, vp, vp, vp]),
     'plk_map_mul_dev': (c_int, [c_ll, vp, vp, vp]),
     'plk_map_mul2_dev': (c_int, [c_ll, vp, vp, vp, vp]),
     'plk_map_qe_pp_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

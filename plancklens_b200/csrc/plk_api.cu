@@ -163,7 +163,7 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
     std::iota(mo.begin(), mo.end(), 0);
     rc = upload(p, mo, &di); if (rc) { plk_plan_destroy(p); return rc; } p->morder = di;
   }
-  p->fft_smem = Mmax * (int)sizeof(cplx);
+  p->fft_smem = (Mmax + Mmax / 4) * (int)sizeof(cplx);   // work buffer + quarter-wave twiddles
   if (p->fft_smem > 227 * 1024) { plk_plan_destroy(p); return fail(PLK_EINVAL, "ring FFT needs %d bytes of shared memory", p->fft_smem); }
   {
     static int attr_smem = 0;   // the attribute is per function, not per plan: only ever raise it
@@ -188,6 +188,7 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
   } else {
     f.V = nullptr;
   }
+  f.mtop = nullptr;
 
   // per-ring table for the template (monopole / dipole) kernels
   {
@@ -268,6 +269,9 @@ static int ensure_spin(plk_plan *p, int spin) {
   if (spin == 0) seed_kernel<false><<<grid, 128>>>(p->g, d);
   else seed_kernel<true><<<grid, 128>>>(p->g, d);
   LAUNCHED();
+  if ((rc = dalloc((void **)&d.mtop, (size_t)p->npair * sizeof(int)))) return rc;
+  mtop_kernel<<<(p->npair + 127) / 128, 128>>>(p->g, d);
+  LAUNCHED();
   CK(cudaDeviceSynchronize());
   sd.ready = true;
   return 0;
@@ -279,6 +283,10 @@ static size_t leg_smem() {
   size_t s = 128 + (size_t)kStages * StageBytes<SPIN, SYNTH>::stage;
   if (!SYNTH) s += (size_t)2 * kNCW * kChunk * (SPIN ? 4 : 2) * sizeof(double);
   return s;
+}
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 static int pick_nr(const plk_plan *p, int nrmax) {
   // enough blocks to cover the SMs a few times over; small grids get fewer pairs per thread
@@ -302,7 +310,7 @@ static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *a
   if (spin == 0) prep_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, nullptr, fl1, nullptr, p->rec.p);
   else prep_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, (const cplx *)alm2, fl1, fl2, p->rec.p);
   LAUNCHED();
-  const int nr = pick_nr(p, spin ? 2 : 4);
+  const int nr = pick_nr(p, spin ? env_int("PLK_NR_SYNS", 2) : env_int("PLK_NR_SYN0", 4));
   dim3 grid((p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr), p->mmax + 1);
   const int nthr = (kNCW + 1) * 32;
 #define SYN(SP, NR)                                                                                              \
@@ -310,7 +318,7 @@ static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *a
   if (spin == 0) {
     if (nr == 4) SYN(false, 4); else if (nr == 2) SYN(false, 2); else SYN(false, 1);
   } else {
-    if (nr == 2) SYN(true, 2); else SYN(true, 1);
+    if (nr == 4) SYN(true, 4); else if (nr == 2) SYN(true, 2); else SYN(true, 1);
   }
 #undef SYN
   LAUNCHED();
@@ -324,7 +332,7 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   const DevSpin &d = p->spins[spin].d;
   const size_t nalm = (size_t)alm_size(p->lmax, p->mmax);
   const int nv = spin ? 4 : 2;
-  const int nr = pick_nr(p, spin ? 2 : 4);
+  const int nr = pick_nr(p, spin ? env_int("PLK_NR_ANAS", 2) : env_int("PLK_NR_ANA0", 4));
   const int ntile = (p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr);
   const long long stride = (long long)nalm * nv;
   if ((rc = ensure(p->part, (size_t)ntile * stride * sizeof(double)))) return rc;
@@ -335,7 +343,7 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   if (spin == 0) {
     if (nr == 4) ANA(false, 4); else if (nr == 2) ANA(false, 2); else ANA(false, 1);
   } else {
-    if (nr == 2) ANA(true, 2); else ANA(true, 1);
+    if (nr == 4) ANA(true, 4); else if (nr == 2) ANA(true, 2); else ANA(true, 1);
   }
 #undef ANA
   LAUNCHED();
@@ -346,14 +354,18 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   return 0;
 }
 
-static int ring_synth(plk_plan *p, const cplx *X, double *map, cudaStream_t st) {
-  ring_synth_kernel<<<p->npair, kFftThreads, p->fft_smem, st>>>(p->f, X, p->pitch, p->mmax, map);
+static int ring_synth(plk_plan *p, const cplx *X, double *map, cudaStream_t st, const int *mtop = nullptr) {
+  DevFFT f = p->f;
+  f.mtop = mtop;
+  ring_synth_kernel<<<p->npair, kFftThreads, p->fft_smem, st>>>(f, X, p->pitch, p->mmax, map);
   LAUNCHED();
   return 0;
 }
-static int ring_anal(plk_plan *p, const double *map, cplx *X, cudaStream_t st) {
+static int ring_anal(plk_plan *p, const double *map, cplx *X, cudaStream_t st, const int *mtop = nullptr) {
   const double w = 4.0 * M_PI / (double)p->npix;
-  ring_anal_kernel<<<p->npair, kFftThreads, p->fft_smem, st>>>(p->f, map, X, p->pitch, p->mmax, w);
+  DevFFT f = p->f;
+  f.mtop = mtop;
+  ring_anal_kernel<<<p->npair, kFftThreads, p->fft_smem, st>>>(f, map, X, p->pitch, p->mmax, w);
   LAUNCHED();
   return 0;
 }
@@ -399,8 +411,9 @@ extern "C" int plk_alm2map_dev(plk_plan *p, int spin, const void *alm1, const vo
   int rc = ensure_phase(p, spin ? 2 : 1);
   if (rc) return rc;
   if ((rc = legendre_synth(p, spin, alm1, alm2, fl1, fl2, (cplx *)p->X1.p, (cplx *)p->X2.p, st))) return rc;
-  if ((rc = ring_synth(p, (const cplx *)p->X1.p, map1, st))) return rc;
-  if (spin > 0 && (rc = ring_synth(p, (const cplx *)p->X2.p, map2, st))) return rc;
+  const int *mtop = p->spins[spin].d.mtop;
+  if ((rc = ring_synth(p, (const cplx *)p->X1.p, map1, st, mtop))) return rc;
+  if (spin > 0 && (rc = ring_synth(p, (const cplx *)p->X2.p, map2, st, mtop))) return rc;
   return PLK_OK;
 }
 
@@ -412,8 +425,10 @@ extern "C" int plk_map2alm_dev(plk_plan *p, int spin, const double *map1, const 
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ensure_phase(p, spin ? 2 : 1);
   if (rc) return rc;
-  if ((rc = ring_anal(p, map1, (cplx *)p->X1.p, st))) return rc;
-  if (spin > 0 && (rc = ring_anal(p, map2, (cplx *)p->X2.p, st))) return rc;
+  if ((rc = ensure_spin(p, spin))) return rc;
+  const int *mtop = p->spins[spin].d.mtop;
+  if ((rc = ring_anal(p, map1, (cplx *)p->X1.p, st, mtop))) return rc;
+  if (spin > 0 && (rc = ring_anal(p, map2, (cplx *)p->X2.p, st, mtop))) return rc;
   return legendre_anal(p, spin, (const cplx *)p->X1.p, (const cplx *)p->X2.p, fl1, fl2, alm1, alm2, st);
 }
 
@@ -555,6 +570,48 @@ extern "C" int plk_map_modes_sub_dev(plk_plan *p, double *m, const double *w, co
   CHECK_PLAN(p);
   if (!m || !sums_dev || !pinv_dev) return fail(PLK_EINVAL, "NULL buffer");
   modes_sub_kernel<<<p->nring, 256, 0, (cudaStream_t)stream>>>(p->rings, m, w, sums_dev, pinv_dev);
+  LAUNCHED();
+  return PLK_OK;
+}
+
+extern "C" int plk_alm_lincomb_dev(long long n, double ca, const void *x, double cb, const void *y, void *out, void *stream) {
+  if (!x || !out || n < 0) return fail(PLK_EINVAL, "bad argument");
+  lincomb_kernel<<<flat_grid(2 * n), 256, 0, (cudaStream_t)stream>>>(2 * n, ca, (const double *)x, cb, (const double *)y, (double *)out);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_combine_dev(int lmax, int nterm, const void *const *in, const double *const *fl, const int *nfl,
+                                   void *out, void *stream) {
+  if (nterm < 1 || nterm > 4 || !in || !fl || !nfl || !out) return fail(PLK_EINVAL, "bad argument");
+  AlmTerms t;
+  t.nterm = nterm;
+  for (int j = 0; j < 4; ++j) { t.in[j] = nullptr; t.fl[j] = nullptr; t.nfl[j] = 0; }
+  for (int j = 0; j < nterm; ++j) {
+    if (!in[j] || !fl[j]) return fail(PLK_EINVAL, "NULL term");
+    t.in[j] = (const cplx *)in[j]; t.fl[j] = fl[j]; t.nfl[j] = nfl[j];
+  }
+  dim3 g((lmax + 256) / 256, lmax + 1);
+  alm_combine_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax, t, (cplx *)out);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm2rlm_dev(int lmax, const void *alm, double *rlm, void *stream) {
+  if (!alm || !rlm) return fail(PLK_EINVAL, "NULL buffer");
+  dim3 g((lmax + 256) / 256, lmax + 1);
+  alm2rlm_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax, (const cplx *)alm, rlm);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_rlm2alm_dev(int lmax, const double *rlm, void *alm, void *stream) {
+  if (!alm || !rlm) return fail(PLK_EINVAL, "NULL buffer");
+  dim3 g((lmax + 256) / 256, lmax + 1);
+  rlm2alm_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax, rlm, (cplx *)alm);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_dense_matvec_dev(int n, const double *A, const double *x, double *y, void *stream) {
+  if (!A || !x || !y || n < 1) return fail(PLK_EINVAL, "bad argument");
+  matvec_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(n, A, x, y);
   LAUNCHED();
   return PLK_OK;
 }

@@ -236,4 +236,63 @@ __global__ void modes_sub_kernel(DevRings r, double *__restrict__ m, const doubl
   }
 }
 
+// out = ca * a + cb * b on 2n doubles (b may be null: out = ca * a)
+__global__ void lincomb_kernel(long long n2, double ca, const double *__restrict__ a, double cb,
+                               const double *__restrict__ b, double *__restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+    out[i] = b ? fma(cb, b[i], ca * a[i]) : ca * a[i];
+}
+
+// out[l,m] = sum_j fl_j[l] * in_j[l,m], j < nterm <= 4 (Wiener-filter style combinations: C^EE E + C^TE T ...)
+struct AlmTerms {
+  const cplx *in[4];
+  const double *fl[4];
+  int nfl[4];
+  int nterm;
+};
+__global__ void alm_combine_kernel(int lmax, AlmTerms t, cplx *__restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > lmax || l < m) return;
+  const int64_t i = alm_idx(lmax, l, m);
+  double re = 0.0, im = 0.0;
+  for (int j = 0; j < t.nterm; ++j) {
+    const double f = l < t.nfl[j] ? t.fl[j][l] : 0.0;
+    const cplx a = t.in[j][i];
+    re = fma(f, a.x, re); im = fma(f, a.y, im);
+  }
+  out[i] = mk(re, im);
+}
+
+// real-harmonic packing used by the dense preconditioner (reference: qcinv/dense.py:16-53)
+__global__ void alm2rlm_kernel(int lmax, const cplx *__restrict__ alm, double *__restrict__ rlm) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > lmax || l < m) return;
+  const cplx a = alm[alm_idx(lmax, l, m)];
+  const double rt2 = 1.4142135623730951;
+  if (m == 0) rlm[(size_t)l * l] = a.x;
+  else { rlm[(size_t)l * l + 2 * m - 1] = a.x * rt2; rlm[(size_t)l * l + 2 * m] = a.y * rt2; }
+}
+__global__ void rlm2alm_kernel(int lmax, const double *__restrict__ rlm, cplx *__restrict__ alm) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > lmax || l < m) return;
+  const double ir2 = 0.70710678118654757;
+  alm[alm_idx(lmax, l, m)] = (m == 0) ? mk(rlm[(size_t)l * l], 0.0)
+                                      : mk(rlm[(size_t)l * l + 2 * m - 1] * ir2, rlm[(size_t)l * l + 2 * m] * ir2);
+}
+// y = A x, A row-major n x n; one warp per row, fixed summation order
+__global__ void matvec_kernel(int n, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double *a = A + (size_t)row * n;
+  double acc = 0.0;
+  for (int j = lane; j < n; j += 32) acc = fma(a[j], x[j], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[row] = acc;
+}
+
 }  // namespace plk

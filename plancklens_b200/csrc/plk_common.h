@@ -58,6 +58,20 @@ PLK_HD cplx expipi_frac(int64_t a, int64_t n) {
   return mk(c, s);
 }
 
+// same with 32-bit integer arithmetic (|a| < 2^31, n < 2^30): the form the ring kernels use
+PLK_HD cplx expipi32(int a, int n) {
+  const int two_n = 2 * n;
+  int r = a % two_n;
+  if (r < 0) r += two_n;
+#if defined(__CUDA_ARCH__)
+  double s, c;
+  sincospi((double)r / (double)n, &s, &c);
+  return mk(c, s);
+#else
+  return expipi_frac(r, n);
+#endif
+}
+
 // ---------------------------------------------------------------- extended-range double-double (setup only)
 // value = (hi + lo) * 2^e, hi normalised to [0.5, 1)
 struct xdd {

@@ -33,6 +33,7 @@ struct DevFFT {
   const int *shifted;       // [npair] 1: phi0 = pi/nphi
   const long long *start_n, *start_s;   // [npair] first pixel of the north / south ring (-1: none)
   const int *order;         // [npair] block -> ring pair, most expensive first
+  const int *mtop;          // [npair] highest m the Legendre stage touches on this pair (or null = mmax)
 };
 
 PLK_HD int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
@@ -42,52 +43,66 @@ PLK_HD int bitrev(int v, int bits) {
   return (int)r;
 }
 
-// twiddle e^{sign * 2 pi i * num / L}, L | Wn
+PLK_HD int lg2(int v) {   // exact log2 of a power of two
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(v);
+#else
+  return 31 - __builtin_clz((unsigned)v);
+#endif
+}
+
+// twiddle e^{sign * 2 pi i * num / L}, 0 <= num < L, from a QUARTER-wave table W[k] = e^{-2 pi i k / Wn}, k < Wn/4
+// (kept in shared memory by the kernels): the other quadrants follow from W[k + Wn/4] = -i W[k].
+// All sizes are powers of two and enter as log2 so that no integer division is generated.
 template <int SIGN>
-PLK_HD cplx tw(const cplx *W, int Wn, int num, int L) {
-  cplx w = W[(size_t)num * (Wn / L)];
+PLK_HD cplx tw(const cplx *W, int lgWn, int num, int lgL) {
+  const int idx = num << (lgWn - lgL);
+  const int quad = idx >> (lgWn - 2);
+  cplx w = W[idx & ((1 << (lgWn - 2)) - 1)];
+  if (quad & 1) w = mul_mi(w);
+  if (quad & 2) w = mk(-w.x, -w.y);
   return SIGN < 0 ? w : conj(w);
 }
 
 // ------------------------------------------------------------------ in-place shared-memory FFT stages
 // "tid/nthr" explicit so the very same code can be driven from a host loop in tests.
 template <int SIGN>
-PLK_HD void dif_r2_stage(cplx *u, int M, const cplx *W, int Wn, int tid, int nthr) {
-  const int H = M >> 1;
+PLK_HD void dif_r2_stage(cplx *u, int M, const cplx *W, int lgWn, int tid, int nthr) {
+  const int H = M >> 1, lgM = lg2(M);
   for (int i = tid; i < H; i += nthr) {
     cplx a = u[i], b = u[i + H];
     u[i] = a + b;
-    u[i + H] = (a - b) * tw<SIGN>(W, Wn, i, M);
+    u[i + H] = (a - b) * tw<SIGN>(W, lgWn, i, lgM);
   }
 }
 // fused pair of radix-2 DIF stages on sub-transforms of length L (bit-reversal compatible ordering)
 template <int SIGN>
-PLK_HD void dif_r4_stage(cplx *u, int M, int L, const cplx *W, int Wn, int tid, int nthr) {
-  const int Q = L >> 2;
+PLK_HD void dif_r4_stage(cplx *u, int M, int L, const cplx *W, int lgWn, int tid, int nthr) {
+  const int Q = L >> 2, lgL = lg2(L), lgQ = lgL - 2;
   for (int b = tid; b < (M >> 2); b += nthr) {
-    const int grp = b / Q, j = b - grp * Q;
-    cplx *p = u + (size_t)grp * L + j;
+    const int grp = b >> lgQ, j = b & (Q - 1);
+    cplx *p = u + ((size_t)grp << lgL) + j;
     cplx a0 = p[0], a1 = p[Q], a2 = p[2 * Q], a3 = p[3 * Q];
     cplx t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = a1 - a3;
     t3 = SIGN < 0 ? mul_mi(t3) : mul_i(t3);
     p[0] = t0 + t2;
-    p[Q] = (t0 - t2) * tw<SIGN>(W, Wn, 2 * j, L);
-    p[2 * Q] = (t1 + t3) * tw<SIGN>(W, Wn, j, L);
-    p[3 * Q] = (t1 - t3) * tw<SIGN>(W, Wn, 3 * j, L);
+    p[Q] = (t0 - t2) * tw<SIGN>(W, lgWn, 2 * j, lgL);
+    p[2 * Q] = (t1 + t3) * tw<SIGN>(W, lgWn, j, lgL);
+    p[3 * Q] = (t1 - t3) * tw<SIGN>(W, lgWn, 3 * j, lgL);
   }
 }
 // fused pair of radix-2 DIT stages producing sub-transforms of length L (input: two levels of bit reversal below)
 template <int SIGN>
-PLK_HD void dit_r4_stage(cplx *u, int M, int L, const cplx *W, int Wn, int tid, int nthr) {
-  const int Q = L >> 2;
+PLK_HD void dit_r4_stage(cplx *u, int M, int L, const cplx *W, int lgWn, int tid, int nthr) {
+  const int Q = L >> 2, lgL = lg2(L), lgQ = lgL - 2;
   for (int b = tid; b < (M >> 2); b += nthr) {
-    const int grp = b / Q, j = b - grp * Q;
-    cplx *p = u + (size_t)grp * L + j;
+    const int grp = b >> lgQ, j = b & (Q - 1);
+    cplx *p = u + ((size_t)grp << lgL) + j;
     cplx e0 = p[0], e1 = p[Q], e2 = p[2 * Q], e3 = p[3 * Q];
-    const cplx w2 = tw<SIGN>(W, Wn, 2 * j, L);
+    const cplx w2 = tw<SIGN>(W, lgWn, 2 * j, lgL);
     cplx e1w = e1 * w2, e3w = e3 * w2;
     cplx f0 = e0 + e1w, f1 = e0 - e1w, f2 = e2 + e3w, f3 = e2 - e3w;
-    const cplx w1 = tw<SIGN>(W, Wn, j, L);
+    const cplx w1 = tw<SIGN>(W, lgWn, j, lgL);
     cplx f2w = f2 * w1;
     cplx f3w = f3 * w1;
     f3w = SIGN < 0 ? mul_mi(f3w) : mul_i(f3w);   // w^{j + L/4}
@@ -98,10 +113,10 @@ PLK_HD void dit_r4_stage(cplx *u, int M, int L, const cplx *W, int Wn, int tid, 
   }
 }
 template <int SIGN>
-PLK_HD void dit_r2_stage(cplx *u, int M, const cplx *W, int Wn, int tid, int nthr) {
-  const int H = M >> 1;
+PLK_HD void dit_r2_stage(cplx *u, int M, const cplx *W, int lgWn, int tid, int nthr) {
+  const int H = M >> 1, lgM = lg2(M);
   for (int i = tid; i < H; i += nthr) {
-    cplx a = u[i], b = u[i + H] * tw<SIGN>(W, Wn, i, M);
+    cplx a = u[i], b = u[i + H] * tw<SIGN>(W, lgWn, i, lgM);
     u[i] = a + b;
     u[i + H] = a - b;
   }
@@ -136,16 +151,18 @@ struct BlockCtx {
 template <int SIGN, class Ctx>
 PLK_HD void fft_dif(Ctx ctx, cplx *u, int M, const cplx *W, int Wn) {
   int L = M;
-  if (ilog2(M) & 1) { dif_r2_stage<SIGN>(u, M, W, Wn, ctx.tid(), ctx.nthr()); ctx.sync(); L >>= 1; }
-  for (; L >= 4; L >>= 2) { dif_r4_stage<SIGN>(u, M, L, W, Wn, ctx.tid(), ctx.nthr()); ctx.sync(); }
+  const int lgWn = lg2(Wn);
+  if (lg2(M) & 1) { dif_r2_stage<SIGN>(u, M, W, lgWn, ctx.tid(), ctx.nthr()); ctx.sync(); L >>= 1; }
+  for (; L >= 4; L >>= 2) { dif_r4_stage<SIGN>(u, M, L, W, lgWn, ctx.tid(), ctx.nthr()); ctx.sync(); }
 }
 // bit-reversed order in -> natural order out
 template <int SIGN, class Ctx>
 PLK_HD void fft_dit(Ctx ctx, cplx *u, int M, const cplx *W, int Wn) {
-  const bool odd = ilog2(M) & 1;
+  const bool odd = lg2(M) & 1;
   const int Ltop = odd ? (M >> 1) : M;
-  for (int L = 4; L <= Ltop; L <<= 2) { dit_r4_stage<SIGN>(u, M, L, W, Wn, ctx.tid(), ctx.nthr()); ctx.sync(); }
-  if (odd) { dit_r2_stage<SIGN>(u, M, W, Wn, ctx.tid(), ctx.nthr()); ctx.sync(); }
+  const int lgWn = lg2(Wn);
+  for (int L = 4; L <= Ltop; L <<= 2) { dit_r4_stage<SIGN>(u, M, L, W, lgWn, ctx.tid(), ctx.nthr()); ctx.sync(); }
+  if (odd) { dit_r2_stage<SIGN>(u, M, W, lgWn, ctx.tid(), ctx.nthr()); ctx.sync(); }
 }
 
 // ------------------------------------------------------------------ fold / unfold helpers
@@ -165,7 +182,7 @@ PLK_HD cplx fold_bin(const cplx *X, int mmax, int n, int k, int shifted) {
 // E^{(a)}_{k'} = e^{(2a)}_{k'} + i e^{(2a+1)}_{k'},  e^{(r)} = w_n^{r k'} sum_c i^{rc} d_{k'+qc},
 // d_k = e^{i pi k/n * shifted} D(k)
 PLK_HD cplx synth_input(const cplx *X, int mmax, int n, int q, int kp, int shifted, int a) {
-  const cplx g = expipi_frac(kp, n);          // e^{i pi k'/n}
+  const cplx g = expipi32(kp, n);             // e^{i pi k'/n}
   const cplx g2 = g * g;                      // w_n^{k'}
   cplx d[4];
   // e^{i pi (k'+qc)/n} = g * e^{i pi c/4}
@@ -192,7 +209,7 @@ PLK_HD cplx synth_input(const cplx *X, int mmax, int n, int q, int kp, int shift
   return e0 + mul_i(e1);
 }
 
-PLK_HD cplx chirp(int t, int q) { return expipi_frac((int64_t)t * t, q); }   // b_t = e^{i pi t^2/q}
+PLK_HD cplx chirp(int t, int q) { return expipi32(t * t, q); }   // b_t = e^{i pi t^2/q}, t < 2^15
 
 // In-place inverse-sign length-q DFT of buf[0..q): Z_k = sum_t z_t e^{+2 pi i t k/q}.
 // On return Z_k = fetchZ(buf, k, ...).
@@ -207,6 +224,13 @@ PLK_HD void idft_q(Ctx ctx, cplx *buf, int q, int M, const cplx *W, int Wn, cons
     fft_dit<+1>(ctx, buf, M, W, Wn);
   }
 }
+// copies the quarter-wave twiddles of an M-point transform next to the work buffer: tws[k] = e^{-2 pi i k/M}, k < M/4
+template <class Ctx>
+PLK_HD void load_twiddles(Ctx ctx, cplx *tws, int M, const cplx *Wg, int Wng) {
+  const int st = Wng / M;
+  for (int k = ctx.tid(); k < (M >> 2); k += ctx.nthr()) tws[k] = Wg[(size_t)k * st];
+  ctx.sync();
+}
 PLK_HD cplx fetchZ(const cplx *buf, int k, int q, int M, int bits) {
   if (M == q) return buf[bitrev(k, bits)];
   return (1.0 / (double)M) * (chirp(k, q) * buf[k]);
@@ -214,11 +238,15 @@ PLK_HD cplx fetchZ(const cplx *buf, int k, int q, int M, int bits) {
 
 // ------------------------------------------------------------------ synthesis: X[ring][m] -> pixels
 template <class Ctx>
-PLK_HD void ring_synth_body(Ctx ctx, const DevFFT &f, int ip, const cplx *X, int pitch, int mmax, double *map,
+PLK_HD void ring_synth_body(Ctx ctx, const DevFFT &f, int ip, const cplx *X, int pitch, int mmax_in, double *map,
                             cplx *buf) {
   const int n = f.nphi[ip], q = n >> 2, M = f.M[ip], shifted = f.shifted[ip];
   const int bits = ilog2(M > 0 ? M : 1);
   const cplx *Vq = (f.voff[ip] >= 0) ? f.V + f.voff[ip] : nullptr;
+  // rows of X are exactly zero above mtop (pairs the Legendre stage skips): do not fold them
+  const int mmax = f.mtop ? (f.mtop[ip] < mmax_in ? f.mtop[ip] : mmax_in) : mmax_in;
+  cplx *tws = buf + M;
+  if (M > 0) load_twiddles(ctx, tws, M, f.W, f.Wn);
   for (int half = 0; half < 2; ++half) {
     const long long start = half == 0 ? f.start_n[ip] : f.start_s[ip];
     if (start < 0) continue;
@@ -230,7 +258,7 @@ PLK_HD void ring_synth_body(Ctx ctx, const DevFFT &f, int ip, const cplx *X, int
       for (int j = ctx.tid(); j < n; j += ctx.nthr()) {
         double acc = Xr[0].x;
         for (int m = 1; m <= mmax; ++m) {
-          cplx e = expipi_frac((int64_t)m * (shifted + 2 * j), n);
+          cplx e = expipi32(m * (shifted + 2 * j), n);
           acc += 2.0 * (Xr[m].x * e.x - Xr[m].y * e.y);
         }
         out[j] = acc;
@@ -247,7 +275,7 @@ PLK_HD void ring_synth_body(Ctx ctx, const DevFFT &f, int ip, const cplx *X, int
         buf[i] = v;
       }
       ctx.sync();
-      idft_q(ctx, buf, q, M, f.W, f.Wn, Vq);
+      idft_q(ctx, buf, q, M, tws, M, Vq);
       for (int t = ctx.tid(); t < q; t += ctx.nthr()) {
         cplx y = fetchZ(buf, t, q, M, bits);
         out[4 * t + 2 * a] = y.x;
@@ -261,11 +289,15 @@ PLK_HD void ring_synth_body(Ctx ctx, const DevFFT &f, int ip, const cplx *X, int
 // ------------------------------------------------------------------ analysis: pixels -> X[ring][m]
 // X_m = wgt * sum_j map_j e^{-i m phi_j}
 template <class Ctx>
-PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, cplx *X, int pitch, int mmax,
+PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, cplx *X, int pitch, int mmax_in,
                            double wgt, cplx *buf) {
   const int n = f.nphi[ip], q = n >> 2, M = f.M[ip], shifted = f.shifted[ip];
   const int bits = ilog2(M > 0 ? M : 1);
   const cplx *Vq = (f.voff[ip] >= 0) ? f.V + f.voff[ip] : nullptr;
+  // the Legendre stage never reads X above mtop on this pair
+  const int mmax = f.mtop ? (f.mtop[ip] < mmax_in ? f.mtop[ip] : mmax_in) : mmax_in;
+  cplx *tws = buf + M;
+  if (M > 0) load_twiddles(ctx, tws, M, f.W, f.Wn);
   for (int half = 0; half < 2; ++half) {
     const long long start = half == 0 ? f.start_n[ip] : f.start_s[ip];
     if (start < 0) continue;
@@ -276,7 +308,7 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
       for (int m = ctx.tid(); m <= mmax; m += ctx.nthr()) {
         cplx acc = mk(0.0, 0.0);
         for (int j = 0; j < n; ++j) {
-          cplx e = expipi_frac(-(int64_t)m * (shifted + 2 * j), n);
+          cplx e = expipi32(-m * (shifted + 2 * j), n);
           acc = acc + in[j] * e;
         }
         Xr[m] = wgt * acc;
@@ -293,7 +325,7 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
         buf[i] = v;
       }
       ctx.sync();
-      idft_q(ctx, buf, q, M, f.W, f.Wn, Vq);
+      idft_q(ctx, buf, q, M, tws, M, Vq);
       // Y_k = conj(Z_k);  S^{(2a)}_k = (Y_k + conj Y_{q-k})/2,  S^{(2a+1)}_k = (Y_k - conj Y_{q-k})/(2i)
       // D_k = sum_r w_n^{-r k} S^{(r)}_{k mod q} ;  X_m = wgt e^{-i pi m/n * shifted} D_{m mod n}
       for (int m = ctx.tid(); m <= mmax; m += ctx.nthr()) {
@@ -303,7 +335,7 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
         const cplx Yc = fetchZ(buf, kq, q, M, bits);           // conj(Y_{q-k})
         const cplx S0 = 0.5 * (Yk + Yc);
         const cplx S1 = mul_mi(0.5 * (Yk - Yc));
-        const cplx g = expipi_frac(-(int64_t)k, n);            // e^{-i pi k/n}
+        const cplx g = expipi32(-k, n);                        // e^{-i pi k/n}
         const cplx g2 = g * g;                                 // w_n^{-k}
         cplx wr = mk(1.0, 0.0);
         for (int i = 0; i < 2 * a; ++i) wr = wr * g2;          // w_n^{-2a k}
@@ -331,7 +363,9 @@ PLK_HD void bluestein_setup_body(Ctx ctx, const DevFFT &f, int ip, cplx *Vout, c
     buf[i] = v;
   }
   ctx.sync();
-  fft_dif<-1>(ctx, buf, M, f.W, f.Wn);
+  cplx *tws = buf + M;
+  load_twiddles(ctx, tws, M, f.W, f.Wn);
+  fft_dif<-1>(ctx, buf, M, tws, M);
   for (int i = ctx.tid(); i < M; i += ctx.nthr()) Vout[f.voff[ip] + i] = buf[i];
 }
 

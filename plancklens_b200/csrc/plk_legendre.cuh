@@ -38,6 +38,7 @@ struct DevSpin {
   int *ks;                 // first accumulated offset k = l - l0(m) (even); K(m) or more = skip
   double *s0, *s1;         // p^+_{l-1}, p^+_l at l = l0 + ks
   double *s2, *s3;         // p^-  (spin > 0)
+  int *mtop;               // [npair] highest m with a non-skipped seed on this pair (-1: none)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -66,6 +67,19 @@ PLK_D void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
   } while (!ok);
+}
+PLK_D bool mbar_try(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 // 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on an mbarrier.
 PLK_D void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
@@ -149,6 +163,18 @@ __global__ void seed_kernel(DevGeom g, DevSpin t) {
   if (SPIN) { t.s2[o] = c; t.s3[o] = d; }
 }
 
+// highest m each ring pair takes part in (the ring-FFT stage folds / unfolds nothing above it)
+__global__ void mtop_kernel(DevGeom g, DevSpin t) {
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= g.npair) return;
+  int top = -1;
+  for (int m = t.mmax; m >= 0; --m) {
+    const int l0 = m > t.spin ? m : t.spin;
+    if (t.ks[(size_t)m * g.npair + ip] < t.lmax - l0 + 1) { top = m; break; }
+  }
+  t.mtop[ip] = top;
+}
+
 // ---------------------------------------------------------------------------------------------- shared layout
 template <bool SPIN, bool SYNTH>
 struct StageBytes {
@@ -158,20 +184,20 @@ struct StageBytes {
   static constexpr int stage = per_l * kChunk;
 };
 
-struct PipeState {
-  uint64_t *full, *empty;
-};
-
-// Producer warp body: streams chunks [c0, nchunk) of row m into the stage ring.
+// Producer warp body: streams chunks [c0, nchunk) of row m into the stage ring.  One lane works; while the
+// ring is full it sleeps (nanosleep back-off) instead of burning issue slots the FP64 warps need.
 template <bool SPIN, bool SYNTH>
 PLK_D void producer_loop(unsigned char *stage_base, uint64_t *full, uint64_t *empty, const void *rec_row,
-                         const double2 *uv_row, int K, int c0, int nchunk, int nconsumers) {
+                         const double2 *uv_row, int K, int c0, int nchunk) {
   using SB = StageBytes<SPIN, SYNTH>;
   if ((threadIdx.x & 31) != 0) return;
   for (int c = c0; c < nchunk; ++c) {
     const int it = c - c0;
     const int st = it % kStages;
-    if (it >= kStages) mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
+    if (it >= kStages) {
+      const uint32_t par = ((it / kStages) - 1) & 1;
+      while (!mbar_try(&empty[st], par)) __nanosleep(400);
+    }
     const int k0 = c * kChunk;
     const int n = min(kChunk, K - k0);
     unsigned char *dst = stage_base + (size_t)st * SB::stage;
@@ -244,7 +270,7 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
 
   if (warp == kNCW) {
     const unsigned char *rec_row = (const unsigned char *)rec + row * SB::rec;
-    producer_loop<SPIN, true>(stage_base, full, empty, rec_row, t.UV + row, K, c0, nchunk, kNCW);
+    producer_loop<SPIN, true>(stage_base, full, empty, rec_row, t.UV + row, K, c0, nchunk);
     return;
   }
 
@@ -264,11 +290,19 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
     mbar_wait(&full[st], (it / kStages) & 1);
     const int k0 = c * kChunk;
     const int kend = min(k0 + kChunk, K);
+    unsigned char *sb = stage_base + (size_t)st * SB::stage;
+    if ((kend & 1) && kend == K) {
+      // odd row length: the (k, k+1) loop below reads one record past the row; make it a zero record
+      if (lane == 0) {
+        if (SPIN) reinterpret_cast<double4 *>(sb)[kend - k0] = make_double4(0.0, 0.0, 0.0, 0.0);
+        else reinterpret_cast<double2 *>(sb)[kend - k0] = make_double2(0.0, 0.0);
+        reinterpret_cast<double2 *>(sb + SB::rec * kChunk)[kend - k0] = make_double2(0.0, 0.0);
+      }
+      __syncwarp();
+    }
     if (kend > kw_min) {
-      const unsigned char *sb = stage_base + (size_t)st * SB::stage;
       const double2 *uvs = reinterpret_cast<const double2 *>(sb + SB::rec * kChunk);
-      int k = max(k0, kw_min);   // even
-      for (; k < kend; k += 2) {
+      for (int k = max(k0, kw_min); k < kend; k += 2) {
         if (k <= kw_max) {
 #pragma unroll
           for (int j = 0; j < NR; ++j)
@@ -278,26 +312,22 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
             }
         }
         const int kk = k - k0;
-        const bool two = (k + 1 < kend);
         if (!SPIN) {
           const double2 *as = reinterpret_cast<const double2 *>(sb);
-          const double2 e = as[kk], ue = uvs[kk];
-          const double2 o = two ? as[kk + 1] : make_double2(0.0, 0.0);
-          const double2 uo = two ? uvs[kk + 1] : make_double2(0.0, 0.0);
+          const double2 e = as[kk], o = as[kk + 1];
+          const double ue = uvs[kk].x, uo = uvs[kk + 1].x;
 #pragma unroll
           for (int j = 0; j < NR; ++j) {
             a0r[j] = fma(e.x, pc_[j], a0r[j]); a0i[j] = fma(e.y, pc_[j], a0i[j]);
-            double n1 = fma(x[j] * ue.x, pc_[j], -pm_[j]);
+            const double n1 = fma(x[j] * ue, pc_[j], -pm_[j]);
             a1r[j] = fma(o.x, n1, a1r[j]); a1i[j] = fma(o.y, n1, a1i[j]);
-            double n2 = fma(x[j] * uo.x, n1, -pc_[j]);
-            if (two) { pm_[j] = n1; pc_[j] = n2; } else { pm_[j] = pc_[j]; pc_[j] = n1; }
+            const double n2 = fma(x[j] * uo, n1, -pc_[j]);
+            pm_[j] = n1; pc_[j] = n2;
           }
         } else {
           const double4 *hs = reinterpret_cast<const double4 *>(sb);
-          const double4 he = hs[kk];
-          const double2 ue = uvs[kk];
-          const double4 ho = two ? hs[kk + 1] : make_double4(0.0, 0.0, 0.0, 0.0);
-          const double2 uo = two ? uvs[kk + 1] : make_double2(0.0, 0.0);
+          const double4 he = hs[kk], ho = hs[kk + 1];
+          const double2 ue = uvs[kk], uo = uvs[kk + 1];
 #pragma unroll
           for (int j = 0; j < NR; ++j) {
             // even offset: sigma = +1
@@ -305,17 +335,16 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
             b1r[j] = fma(he.z, pc_[j], b1r[j]); b1i[j] = fma(he.w, pc_[j], b1i[j]);   // south A- += H- p+
             a1r[j] = fma(he.z, qc_[j], a1r[j]); a1i[j] = fma(he.w, qc_[j], a1i[j]);   // north A- += H- p-
             b0r[j] = fma(he.x, qc_[j], b0r[j]); b0i[j] = fma(he.y, qc_[j], b0i[j]);   // south A+ += H+ p-
-            double np = fma(fma(x[j], ue.x, ue.y), pc_[j], -pm_[j]);
-            double nq = fma(fma(x[j], ue.x, -ue.y), qc_[j], -qm_[j]);
+            const double np = fma(fma(x[j], ue.x, ue.y), pc_[j], -pm_[j]);
+            const double nq = fma(fma(x[j], ue.x, -ue.y), qc_[j], -qm_[j]);
             // odd offset: sigma = -1 on the southern sums
             a0r[j] = fma(ho.x, np, a0r[j]); a0i[j] = fma(ho.y, np, a0i[j]);
             b1r[j] = fma(-ho.z, np, b1r[j]); b1i[j] = fma(-ho.w, np, b1i[j]);
             a1r[j] = fma(ho.z, nq, a1r[j]); a1i[j] = fma(ho.w, nq, a1i[j]);
             b0r[j] = fma(-ho.x, nq, b0r[j]); b0i[j] = fma(-ho.y, nq, b0i[j]);
-            double np2 = fma(fma(x[j], uo.x, uo.y), np, -pc_[j]);
-            double nq2 = fma(fma(x[j], uo.x, -uo.y), nq, -qc_[j]);
-            if (two) { pm_[j] = np; pc_[j] = np2; qm_[j] = nq; qc_[j] = nq2; }
-            else { pm_[j] = pc_[j]; pc_[j] = np; qm_[j] = qc_[j]; qc_[j] = nq; }
+            const double np2 = fma(fma(x[j], uo.x, uo.y), np, -pc_[j]);
+            const double nq2 = fma(fma(x[j], uo.x, -uo.y), nq, -qc_[j]);
+            pm_[j] = np; pc_[j] = np2; qm_[j] = nq; qc_[j] = nq2;
           }
         }
       }
@@ -347,26 +376,35 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
 }
 
 // ---------------------------------------------------------------------------------------------- analysis
-// Input phase arrays X1 (, X2): X_m(ring) = sum_j map_j e^{-i m phi_j} (unweighted).
+// Input phase arrays X1 (, X2): X_m(ring) = sum_j map_j e^{-i m phi_j} (quadrature weight already applied).
 // Output partial sums part[tile][alm_idx(l,m)][NV] (NV = 2 doubles spin 0, 4 doubles spin s):
 //   spin 0:  S_l   = sum_pairs p_l (X_n + sigma_l X_s)
 //   spin s:  S+_l  = sum_pairs [p+ F+_n + sigma_l p- F+_s],  S-_l = sum_pairs [p- F-_n + sigma_l p+ F-_s],
-//            F+- = X1 +- i X2.   alpha, quadrature weight and the G/C recombination are applied by
-//            finish_alm_kernel, which also reduces over tiles (deterministic order).
-// Cross-lane reduction: 16 accumulators per lane (8 l x 2 or 4 l x 4) -> butterfly reduce-scatter
-// (8+4+2+1+1 shuffles) -> one value per lane pair -> per-warp shared slice -> summed over warps per chunk.
-template <bool SPIN>
+//            F+- = X1 +- i X2.   alpha and the G/C recombination are applied by finish_alm_kernel, which also
+//            reduces over tiles (deterministic order).
+// Cross-lane reduction: 16 accumulators per lane, index = vs * NB + b (component slot high, l offset low), then
+// a butterfly reduce-scatter (8+4+2+1+1 shuffles).  The slot -> component map is permuted per lane
+// (component = vs ^ lane bits) by permuting the ring constants once at load time, so the upper butterfly levels
+// need no selects: every lane keeps its low registers and receives the partner's high ones.
+template <int NSEL>   // number of leading select-free levels (2 for spin s, 1 for spin 0)
 PLK_D void butterfly16(double (&v)[16], int lane) {
+  // levels bit = 16, 8, 4, 2 halve the live registers; the last level (bit 1) is a plain sum
 #pragma unroll
-  for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
-    const bool up = (lane & bit) != 0;
+  for (int lev = 0; lev < 4; ++lev) {
+    const int h = 8 >> lev, bit = 16 >> lev;
+    if (lev < NSEL) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < h) {
-        double send = up ? v[j] : v[j + h];
-        double keep = up ? v[j + h] : v[j];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-      }
+      for (int j = 0; j < 8; ++j)
+        if (j < h) v[j] += __shfl_xor_sync(0xffffffffu, v[j + h], bit);
+    } else {
+      const bool up = (lane & bit) != 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < h) {
+          const double send = up ? v[j] : v[j + h];
+          const double keep = up ? v[j + h] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
     }
   }
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
@@ -395,6 +433,7 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_pairs = kNCW * 32 * NR;
   const int pair0 = blockIdx.x * tile_pairs + warp * 32 * NR + lane;
+  const int hi = SPIN ? ((lane >> 3) & 3) : ((lane >> 4) & 1);   // lane bits consumed by the select-free levels
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kNCW); }
@@ -406,15 +445,17 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
   int ks[NR];
   double x[NR];
   size_t so[NR];
-  // ring data: spin0: fe = Xn + sg0 Xs, fo = Xn - sg0 Xs ; spin: F+n, F-n, sg0 F+s, sg0 F-s
-  double f0r[NR], f0i[NR], f1r[NR], f1i[NR], f2r[NR], f2i[NR], f3r[NR], f3i[NR];
+  // lane-permuted ring constants.  spin s: fa[vs] multiplies p+, fb[vs] multiplies p-, component v = vs ^ hi of
+  //   (S+re, S+im, S-re, S-im):  A = (F+n.re, F+n.im, sF-s.re, sF-s.im), B = (sF+s.re, sF+s.im, F-n.re, F-n.im)
+  // spin 0: fa[vs] = (fe.re, fe.im)[vs ^ hi] used at even offsets, fb[vs] = (fo.re, fo.im)[vs ^ hi] at odd ones
+  double fa[NR][NV], fb[NR][NV];
   int kw_min = 1 << 30, kw_max = -1;
   const double sg0 = ((l0 + m) & 1) ? -1.0 : 1.0;
   if (warp < kNCW) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
       const int ip = pair0 + 32 * j;
-      f0r[j] = f0i[j] = f1r[j] = f1i[j] = f2r[j] = f2i[j] = f3r[j] = f3i[j] = 0.0;
+      double A[4] = {0.0, 0.0, 0.0, 0.0}, B[4] = {0.0, 0.0, 0.0, 0.0};
       if (ip < g.npair) {
         so[j] = (size_t)m * g.npair + ip;
         ks[j] = t.ks[so[j]];
@@ -424,19 +465,28 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
           const cplx n1 = X1[(size_t)rn * pitch + m];
           const cplx s1 = (rs != rn) ? X1[(size_t)rs * pitch + m] : mk(0.0, 0.0);
           if (!SPIN) {
-            f0r[j] = n1.x + sg0 * s1.x; f0i[j] = n1.y + sg0 * s1.y;
-            f1r[j] = n1.x - sg0 * s1.x; f1i[j] = n1.y - sg0 * s1.y;
+            A[0] = n1.x + sg0 * s1.x; A[1] = n1.y + sg0 * s1.y;     // fe
+            B[0] = n1.x - sg0 * s1.x; B[1] = n1.y - sg0 * s1.y;     // fo
           } else {
             const cplx n2 = X2[(size_t)rn * pitch + m];
             const cplx s2 = (rs != rn) ? X2[(size_t)rs * pitch + m] : mk(0.0, 0.0);
             // F+ = X1 + i X2 ; F- = X1 - i X2
-            f0r[j] = n1.x - n2.y; f0i[j] = n1.y + n2.x;            // F+ north
-            f1r[j] = n1.x + n2.y; f1i[j] = n1.y - n2.x;            // F- north
-            f2r[j] = sg0 * (s1.x - s2.y); f2i[j] = sg0 * (s1.y + s2.x);   // sigma0 F+ south
-            f3r[j] = sg0 * (s1.x + s2.y); f3i[j] = sg0 * (s1.y - s2.x);   // sigma0 F- south
+            A[0] = n1.x - n2.y; A[1] = n1.y + n2.x;                         // F+ north
+            B[2] = n1.x + n2.y; B[3] = n1.y - n2.x;                         // F- north
+            B[0] = sg0 * (s1.x - s2.y); B[1] = sg0 * (s1.y + s2.x);         // sigma0 F+ south
+            A[2] = sg0 * (s1.x + s2.y); A[3] = sg0 * (s1.y - s2.x);         // sigma0 F- south
           }
         }
       } else { so[j] = 0; ks[j] = 1 << 30; x[j] = 0.0; }
+#pragma unroll
+      for (int vs = 0; vs < NV; ++vs) {
+        // static-index selection of A[vs ^ hi]
+        double av = A[vs], bv = B[vs];
+#pragma unroll
+        for (int h2 = 1; h2 < NV; ++h2)
+          if (hi == h2) { av = A[vs ^ h2]; bv = B[vs ^ h2]; }
+        fa[j][vs] = av; fb[j][vs] = bv;
+      }
       if (ks[j] < K) { kw_min = min(kw_min, ks[j]); kw_max = max(kw_max, ks[j]); }
     }
 #pragma unroll
@@ -454,7 +504,7 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
   double *prow = part + (size_t)blockIdx.x * part_stride + row * NV;
 
   if (warp == kNCW) {
-    producer_loop<SPIN, false>(stage_base, full, empty, nullptr, t.UV + row, K, c0, nchunk, kNCW);
+    producer_loop<SPIN, false>(stage_base, full, empty, nullptr, t.UV + row, K, c0, nchunk);
     return;
   }
   // chunks before c0 carry no contribution from this tile: write zeros
@@ -463,6 +513,10 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
   double pc_[NR], pm_[NR], qc_[NR], qm_[NR];
 #pragma unroll
   for (int j = 0; j < NR; ++j) pc_[j] = pm_[j] = qc_[j] = qm_[j] = 0.0;
+  // value held by this lane after the butterfly: component vout at l offset bout of the batch
+  const int bout = (lane >> 1) & (NB - 1);
+  const int vout = hi;
+  const bool flip = SPIN && (bout & 1) && (vout >= 2);   // odd offsets accumulate -(S-) (see below)
 
   for (int c = c0; c < nchunk; ++c) {
     const int it = c - c0;
@@ -483,53 +537,47 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
 #pragma unroll
           for (int b = 0; b < NB; b += 2) {
             const int k = kb + b;
-            if (k < kend) {
-              if (k <= kw_max && k >= kw_min) {
+            if (k <= kw_max && k >= kw_min) {
 #pragma unroll
-                for (int j = 0; j < NR; ++j)
-                  if (k == ks[j]) {
-                    pm_[j] = t.s0[so[j]]; pc_[j] = t.s1[so[j]];
-                    if (SPIN) { qm_[j] = t.s2[so[j]]; qc_[j] = t.s3[so[j]]; }
-                  }
-              }
-              const bool two = (k + 1 < kend);
-              const double2 ue = uvs[k - k0];
-              const double2 uo = two ? uvs[k - k0 + 1] : make_double2(0.0, 0.0);
-#pragma unroll
-              for (int j = 0; j < NR; ++j) {
-                if (!SPIN) {
-                  acc[b * 2 + 0] = fma(pc_[j], f0r[j], acc[b * 2 + 0]);
-                  acc[b * 2 + 1] = fma(pc_[j], f0i[j], acc[b * 2 + 1]);
-                  double n1 = fma(x[j] * ue.x, pc_[j], -pm_[j]);
-                  acc[b * 2 + 2] = fma(n1, f1r[j], acc[b * 2 + 2]);
-                  acc[b * 2 + 3] = fma(n1, f1i[j], acc[b * 2 + 3]);
-                  double n2 = fma(x[j] * uo.x, n1, -pc_[j]);
-                  if (two) { pm_[j] = n1; pc_[j] = n2; } else { pm_[j] = pc_[j]; pc_[j] = n1; }
-                } else {
-                  // even offset (sigma = +sigma0 folded in f2,f3)
-                  acc[b * 4 + 0] = fma(pc_[j], f0r[j], fma(qc_[j], f2r[j], acc[b * 4 + 0]));   // S+ re
-                  acc[b * 4 + 1] = fma(pc_[j], f0i[j], fma(qc_[j], f2i[j], acc[b * 4 + 1]));   // S+ im
-                  acc[b * 4 + 2] = fma(qc_[j], f1r[j], fma(pc_[j], f3r[j], acc[b * 4 + 2]));   // S- re
-                  acc[b * 4 + 3] = fma(qc_[j], f1i[j], fma(pc_[j], f3i[j], acc[b * 4 + 3]));   // S- im
-                  double np = fma(fma(x[j], ue.x, ue.y), pc_[j], -pm_[j]);
-                  double nq = fma(fma(x[j], ue.x, -ue.y), qc_[j], -qm_[j]);
-                  // odd offset: southern terms change sign
-                  acc[b * 4 + 4] = fma(np, f0r[j], fma(-nq, f2r[j], acc[b * 4 + 4]));
-                  acc[b * 4 + 5] = fma(np, f0i[j], fma(-nq, f2i[j], acc[b * 4 + 5]));
-                  acc[b * 4 + 6] = fma(nq, f1r[j], fma(-np, f3r[j], acc[b * 4 + 6]));
-                  acc[b * 4 + 7] = fma(nq, f1i[j], fma(-np, f3i[j], acc[b * 4 + 7]));
-                  double np2 = fma(fma(x[j], uo.x, uo.y), np, -pc_[j]);
-                  double nq2 = fma(fma(x[j], uo.x, -uo.y), nq, -qc_[j]);
-                  if (two) { pm_[j] = np; pc_[j] = np2; qm_[j] = nq; qc_[j] = nq2; }
-                  else { pm_[j] = pc_[j]; pc_[j] = np; qm_[j] = qc_[j]; qc_[j] = nq; }
+              for (int j = 0; j < NR; ++j)
+                if (k == ks[j]) {
+                  pm_[j] = t.s0[so[j]]; pc_[j] = t.s1[so[j]];
+                  if (SPIN) { qm_[j] = t.s2[so[j]]; qc_[j] = t.s3[so[j]]; }
                 }
+            }
+            // reads past kend stay inside the stage buffer; those offsets are never written out
+            const double2 ue = uvs[k - k0], uo = uvs[k - k0 + 1];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+              if (!SPIN) {
+#pragma unroll
+                for (int vs = 0; vs < 2; ++vs) acc[vs * NB + b] = fma(pc_[j], fa[j][vs], acc[vs * NB + b]);
+                const double n1 = fma(x[j] * ue.x, pc_[j], -pm_[j]);
+#pragma unroll
+                for (int vs = 0; vs < 2; ++vs) acc[vs * NB + b + 1] = fma(n1, fb[j][vs], acc[vs * NB + b + 1]);
+                const double n2 = fma(x[j] * uo.x, n1, -pc_[j]);
+                pm_[j] = n1; pc_[j] = n2;
+              } else {
+                // even offset: component v += p+ A_v + p- B_v
+#pragma unroll
+                for (int vs = 0; vs < 4; ++vs)
+                  acc[vs * NB + b] = fma(pc_[j], fa[j][vs], fma(qc_[j], fb[j][vs], acc[vs * NB + b]));
+                const double np = fma(fma(x[j], ue.x, ue.y), pc_[j], -pm_[j]);
+                const double nq = fma(fma(x[j], ue.x, -ue.y), qc_[j], -qm_[j]);
+                // odd offset: S+ += p+ A - p- B and S- += -(p+ A - p- B); the minus on S- is applied after the
+                // butterfly (flip) so that all four slots run the same instruction
+#pragma unroll
+                for (int vs = 0; vs < 4; ++vs)
+                  acc[vs * NB + b + 1] = fma(np, fa[j][vs], fma(-nq, fb[j][vs], acc[vs * NB + b + 1]));
+                const double np2 = fma(fma(x[j], uo.x, uo.y), np, -pc_[j]);
+                const double nq2 = fma(fma(x[j], uo.x, -uo.y), nq, -qc_[j]);
+                pm_[j] = np; pc_[j] = np2; qm_[j] = nq; qc_[j] = nq2;
               }
             }
           }
-          butterfly16<SPIN>(acc, lane);
+          butterfly16<SPIN ? 2 : 1>(acc, lane);
         }
-        // lanes (2i, 2i+1) hold value i of the batch: i = b*NV + v
-        if ((lane & 1) == 0) myred[(kb - k0) * NV + (lane >> 1)] = acc[0];
+        if ((lane & 1) == 0) myred[(kb - k0 + bout) * NV + vout] = flip ? -acc[0] : acc[0];
       }
     }
     __syncwarp();

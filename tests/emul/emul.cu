@@ -49,8 +49,8 @@ void build_fft(const HostGeom &hg, HostFFT &h) {
   DevFFT &f = h.f;
   f.nside = hg.nside; f.npair = np; f.nring = hg.nring; f.Wn = Mmax; f.W = h.W.data(); f.V = h.V.data();
   f.voff = h.voff.data(); f.M = h.M.data(); f.nphi = h.nphi.data(); f.shifted = h.shifted.data();
-  f.start_n = h.sn.data(); f.start_s = h.ss.data(); f.order = h.order.data();
-  std::vector<cplx> buf(Mmax);
+  f.start_n = h.sn.data(); f.start_s = h.ss.data(); f.order = h.order.data(); f.mtop = nullptr;
+  std::vector<cplx> buf(Mmax + Mmax / 4);
   for (int ip = 0; ip < np; ++ip) bluestein_setup_body(BlockCtx(), f, ip, h.V.data(), buf.data());
 }
 }  // namespace
@@ -58,14 +58,14 @@ void build_fft(const HostGeom &hg, HostFFT &h) {
 extern "C" int emul_ring_synth(int nside, int mmax, int pitch, const cplx *X, double *map) {
   HostGeom hg = make_geom(nside);
   HostFFT h; build_fft(hg, h);
-  std::vector<cplx> buf(h.Mmax);
+  std::vector<cplx> buf(h.Mmax + h.Mmax / 4);
   for (int ip = 0; ip < hg.npair; ++ip) ring_synth_body(BlockCtx(), h.f, ip, X, pitch, mmax, map, buf.data());
   return 0;
 }
 extern "C" int emul_ring_anal(int nside, int mmax, int pitch, const double *map, cplx *X) {
   HostGeom hg = make_geom(nside);
   HostFFT h; build_fft(hg, h);
-  std::vector<cplx> buf(h.Mmax);
+  std::vector<cplx> buf(h.Mmax + h.Mmax / 4);
   const double w = 4.0 * M_PI / (double)hg.npix;
   for (int ip = 0; ip < hg.npair; ++ip) ring_anal_body(BlockCtx(), h.f, ip, map, X, pitch, mmax, w, buf.data());
   return 0;
