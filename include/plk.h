@@ -124,6 +124,12 @@ int plk_map_modes_dot_dev(plk_plan *plan, double *m, const double *w, double *su
 int plk_map_modes_sub_dev(plk_plan *plan, double *m, const double *w, const double *sums_dev,
                           const double *pinv_dev, void *stream);
 
+/* ---- measurement helpers (bench.py): per-kernel CUDA-event timing of the Legendre launches and the device's
+ *      FP64 FMA peak.  kinds: 0 synthesis spin 0, 1 synthesis spin s, 2 analysis spin 0, 3 analysis spin s. */
+int plk_profile_enable(int on);
+int plk_profile_read(int *counts4, double *total_ms4);
+int plk_fp64_peak(double *tflops, int reps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,9 @@ _SIGS = {
     'plk_alm2rlm_dev': (c_int, [c_int, vp, vp, vp]),
     'plk_rlm2alm_dev': (c_int, [c_int, vp, vp, vp]),
     'plk_dense_matvec_dev': (c_int, [c_int, vp, vp, vp, vp]),
+    'plk_profile_enable': (c_int, [c_int]),
+    'plk_profile_read': (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)]),
+    'plk_fp64_peak': (c_int, [ctypes.POINTER(c_dbl), c_int]),
     'plk_map_mul_dev': (c_int, [c_ll, vp, vp, vp]),
     'plk_map_mul2_dev': (c_int, [c_ll, vp, vp, vp, vp]),
     'plk_map_qe_pp_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -42,6 +42,22 @@ static int fail(int code, const char *fmt, ...) {
     if (e__ != cudaSuccess) return fail(PLK_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// optional per-kernel timing of the Legendre launches (CUDA events on the launching stream)
+struct ProfRec { cudaEvent_t e0, e1; int kind; };   // kind: 0 synth spin0, 1 synth spin s, 2 anal spin0, 3 anal spin s
+static bool g_prof = false;
+static std::vector<ProfRec> g_prof_recs;
+static void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof) return;
+  ProfRec r; r.kind = kind;
+  cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+static void prof_end(cudaStream_t st) {
+  if (!g_prof) return;
+  cudaEventRecord(g_prof_recs.back().e1, st);
+}
+
 extern "C" const char *plk_last_error(void) { return g_err.c_str(); }
 extern "C" int plk_version(void) { return 100; }
 extern "C" long long plk_launch_count(void) { return g_launches.load(); }
@@ -315,12 +331,14 @@ static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *a
   const int nthr = (kNCW + 1) * 32;
 #define SYN(SP, NR)                                                                                              \
   legendre_synth_kernel<SP, NR><<<grid, nthr, leg_smem<SP, true>(), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, p->morder)
+  prof_begin(spin ? 1 : 0, st);
   if (spin == 0) {
     if (nr == 4) SYN(false, 4); else if (nr == 2) SYN(false, 2); else SYN(false, 1);
   } else {
     if (nr == 4) SYN(true, 4); else if (nr == 2) SYN(true, 2); else SYN(true, 1);
   }
 #undef SYN
+  prof_end(st);
   LAUNCHED();
   return 0;
 }
@@ -339,13 +357,15 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   dim3 grid(ntile, p->mmax + 1);
   const int nthr = (kNCW + 1) * 32;
 #define ANA(SP, NR)                                                                                              \
-  legendre_anal_kernel<SP, NR><<<grid, nthr, leg_smem<SP, false>(), st>>>(p->g, d, X1, X2, p->pitch, (double *)p->part.p, stride, p->morder)
+  legendre_anal_kernel<SP, NR><<<grid, nthr, leg_smem<SP, false>(), st>>>(p->g, d, X1, X2, p->pitch, (double *)p->part.p, stride, p->morder, env_int("PLK_DBG_ANA", 0))
+  prof_begin(spin ? 3 : 2, st);
   if (spin == 0) {
     if (nr == 4) ANA(false, 4); else if (nr == 2) ANA(false, 2); else ANA(false, 1);
   } else {
     if (nr == 4) ANA(true, 4); else if (nr == 2) ANA(true, 2); else ANA(true, 1);
   }
 #undef ANA
+  prof_end(st);
   LAUNCHED();
   dim3 pg((p->lmax + 256) / 256, p->mmax + 1);
   if (spin == 0) finish_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, nullptr, (cplx *)alm1, nullptr);
@@ -613,5 +633,60 @@ extern "C" int plk_dense_matvec_dev(int n, const double *A, const double *x, dou
   if (!A || !x || !y || n < 1) return fail(PLK_EINVAL, "bad argument");
   matvec_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(n, A, x, y);
   LAUNCHED();
+  return PLK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ measurement helpers
+extern "C" int plk_profile_enable(int on) {
+  for (auto &r : g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof_recs.clear();
+  g_prof = on != 0;
+  return PLK_OK;
+}
+// sums the recorded durations per kind (4 entries each): counts[k], total_ms[k]; synchronises the device
+extern "C" int plk_profile_read(int *counts, double *total_ms) {
+  CK(cudaDeviceSynchronize());
+  for (int k = 0; k < 4; ++k) { counts[k] = 0; total_ms[k] = 0.0; }
+  for (auto &r : g_prof_recs) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    counts[r.kind] += 1; total_ms[r.kind] += ms;
+  }
+  return PLK_OK;
+}
+
+// FP64 FMA peak of the device: 8 independent dependent-chains of DFMA per thread, 1024 threads per SM resident
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+  double v0 = threadIdx.x * 1e-3, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+      v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+// returns the measured rate in TFLOP/s (2 flop per FMA), best of `reps`
+extern "C" int plk_fp64_peak(double *tflops, int reps) {
+  if (!tflops) return fail(PLK_EINVAL, "NULL");
+  int dev; CK(cudaGetDevice(&dev));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double *d; CK(cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    g_launches.fetch_add(1);
+    CK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 64.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
   return PLK_OK;
 }

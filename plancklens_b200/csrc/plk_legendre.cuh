@@ -68,16 +68,17 @@ PLK_D void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
-PLK_D bool mbar_try(uint64_t *bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~hint_ns pass
+PLK_D bool mbar_try_hint(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
       : "memory");
   return ok != 0;
 }
@@ -196,7 +197,7 @@ PLK_D void producer_loop(unsigned char *stage_base, uint64_t *full, uint64_t *em
     const int st = it % kStages;
     if (it >= kStages) {
       const uint32_t par = ((it / kStages) - 1) & 1;
-      while (!mbar_try(&empty[st], par)) __nanosleep(400);
+      while (!mbar_try_hint(&empty[st], par, 100000u)) {}
     }
     const int k0 = c * kChunk;
     const int n = min(kChunk, K - k0);
@@ -414,7 +415,7 @@ template <bool SPIN, int NR>
 __global__ void __launch_bounds__((kNCW + 1) * 32)
 legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cplx *__restrict__ X2, int pitch,
                      double *__restrict__ part, long long part_stride /* doubles per tile */,
-                     const int *__restrict__ morder) {
+                     const int *__restrict__ morder, int dbg) {
   using SB = StageBytes<SPIN, false>;
   constexpr int NV = SPIN ? 4 : 2;
   constexpr int NB = 16 / NV;   // l values per butterfly batch
@@ -575,13 +576,14 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
               }
             }
           }
-          butterfly16<SPIN ? 2 : 1>(acc, lane);
+          if (!(dbg & 1)) butterfly16<SPIN ? 2 : 1>(acc, lane);
         }
         if ((lane & 1) == 0) myred[(kb - k0 + bout) * NV + vout] = flip ? -acc[0] : acc[0];
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
+    if (dbg & 2) continue;
     named_bar_sync(1, kNCW * 32);
     // sum the per-warp slices of this chunk and write the tile partial
     const double *r0 = red + (size_t)(it & 1) * kNCW * (kChunk * NV);

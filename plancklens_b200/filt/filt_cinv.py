@@ -1,0 +1,306 @@
+"""Conjugate-gradient inverse-variance filtering libraries (reference: plancklens/filt/filt_cinv.py).
+
+`cinv_t` / `cinv_p` own a multigrid-preconditioned CG chain whose operators run on the GPU
+(`plancklens_b200.qcinv`); `library_cinv_sepTP` plugs them into the cached-library interface of
+`filt_simple.library_sepTP`.  Default chains are the reference's (filt_cinv.py:113-116, :237-239).
+"""
+import os
+import pickle as pk
+
+import numpy as np
+
+from .. import hp, utils
+from ..helpers import mpi
+from ..qcinv import cd_solve, multigrid, opfilt_pp, opfilt_tt, util, util_alm
+from . import filt_simple
+
+
+class cinv(object):
+    def __init__(self, lib_dir, lmax):
+        self.lib_dir = lib_dir
+        self.lmax = lmax
+
+    def _load(self, name, lmax):
+        lmax = self.lmax if lmax is None else lmax
+        ret = np.loadtxt(os.path.join(self.lib_dir, name))
+        assert len(ret) > lmax, (len(ret), lmax)
+        return ret[:lmax + 1]
+
+    def get_tal(self, a, lmax=None):
+        assert a.lower() in ['t', 'e', 'b'], a
+        return self._load("tal.dat", lmax)
+
+    def get_fmask(self):
+        return hp.read_map(os.path.join(self.lib_dir, "fmask.fits.gz"))
+
+    def get_ftl(self, lmax=None):
+        return self._load("ftl.dat", lmax)
+
+    def get_fel(self, lmax=None):
+        return self._load("fel.dat", lmax)
+
+    def get_fbl(self, lmax=None):
+        return self._load("fbl.dat", lmax)
+
+
+def _ninv_hash(comps):
+    return [utils.clhash(c) if isinstance(c, np.ndarray) and c.size > 1 else c for c in comps]
+
+
+class cinv_t(cinv):
+    r"""Temperature-only inverse-variance (Wiener) filter (reference: filt_cinv.py:56-203).
+
+        Args:
+            lib_dir: mask and isotropic approximations are cached there
+            lmax: filtered alm's are reconstructed up to lmax
+            nside: resolution of the maps to filter
+            cl: fiducial CMB spectra (dict with 'tt')
+            transf: transfer function
+            ninv: list of maps / paths whose product is the inverse pixel variance
+            rescal_cl: isotropic rescaling of the unknowns before the CG (default: :math:`\sqrt{\ell(\ell+1)/2\pi}`),
+                       which changes the convergence criterion only
+    """
+
+    def __init__(self, lib_dir, lmax, nside, cl, transf, ninv, rescal_cl='default', marge_monopole=True,
+                 marge_dipole=True, marge_maps=(), pcf='default', chain_descr=None):
+        assert lib_dir is not None and lmax >= 1024 and nside >= 512, (lib_dir, lmax, nside)
+        assert isinstance(ninv, list)
+        super(cinv_t, self).__init__(lib_dir, lmax)
+        if rescal_cl in ['default', None]:
+            default_rescal = True
+            rescal_cl = np.sqrt(np.arange(lmax + 1, dtype=float) * np.arange(1, lmax + 2, dtype=float) / 2. / np.pi)
+        else:
+            default_rescal = False
+            assert len(rescal_cl) >= lmax + 1, [rescal_cl.shape, lmax]
+        dl = {k: rescal_cl[:lmax + 1] ** 2 * cl[k][:lmax + 1] for k in cl.keys()}
+        transf_dl = transf[:lmax + 1] * utils.cli(rescal_cl)
+        self.nside = nside
+        self.cl = cl
+        self.dl = dl
+        self.transf = transf[:lmax + 1]
+        self.rescaled_transf = transf_dl
+        self.rescal_cl = rescal_cl
+        self.default_rescal = default_rescal
+        self.ninv = ninv
+        self.marge_monopole = marge_monopole
+        self.marge_dipole = marge_dipole
+        self.marge_maps = marge_maps
+
+        pcf = os.path.join(lib_dir, "dense.pk") if pcf == 'default' else ''
+        if chain_descr is None:
+            chain_descr = \
+                [[3, ["split(dense(" + pcf + "), 64, diag_cl)"], 256, 128, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [2, ["split(stage(3),  256, diag_cl)"], 512, 256, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [1, ["split(stage(2),  512, diag_cl)"], 1024, 512, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [0, ["split(stage(1), 1024, diag_cl)"], lmax, nside, np.inf, 1.0e-5, cd_solve.tr_cg, cd_solve.cache_mem()]]
+        n_inv_filt = util.jit(opfilt_tt.alm_filter_ninv, ninv, transf_dl, marge_monopole=marge_monopole,
+                              marge_dipole=marge_dipole, marge_maps=marge_maps)
+        self.chain_descr = chain_descr
+        self.chain = util.jit(multigrid.multigrid_chain, opfilt_tt, self.chain_descr, dl, n_inv_filt)
+        if mpi.rank == 0:
+            if not os.path.exists(lib_dir):
+                os.makedirs(lib_dir)
+            fn = os.path.join(lib_dir, "filt_hash.pk")
+            if not os.path.exists(fn):
+                with open(fn, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+            if not os.path.exists(os.path.join(lib_dir, "ftl.dat")):
+                np.savetxt(os.path.join(lib_dir, "ftl.dat"), self._calc_ftl())
+            if not os.path.exists(os.path.join(lib_dir, "tal.dat")):
+                np.savetxt(os.path.join(lib_dir, "tal.dat"), self._calc_tal())
+            if not os.path.exists(os.path.join(lib_dir, "fmask.fits.gz")):
+                hp.write_map(os.path.join(lib_dir, "fmask.fits.gz"), self._calc_mask())
+        mpi.barrier()
+        fn = os.path.join(lib_dir, "filt_hash.pk")
+        with open(fn, 'rb') as f:
+            utils.hash_check(pk.load(f), self.hashdict(), fn=fn)
+
+    def _calc_ftl(self):
+        ninv = self.chain.n_inv_filt.n_inv
+        npix = len(ninv)
+        NlevT_uKamin = np.sqrt(4. * np.pi / npix / np.sum(ninv) * len(np.where(ninv != 0.0)[0])) * 180. * 60. / np.pi
+        print("cinv_t::noiseT_uk_arcmin = %.3f" % NlevT_uKamin)
+        s_cls = self.cl
+        if s_cls['tt'][0] == 0.:
+            assert self.chain.n_inv_filt.marge_monopole
+        if s_cls['tt'][1] == 0.:
+            assert self.chain.n_inv_filt.marge_dipole
+        ftl = utils.cli(s_cls['tt'][0:self.lmax + 1]
+                        + (NlevT_uKamin * np.pi / 180. / 60.) ** 2 * utils.cli(self.transf[0:self.lmax + 1] ** 2))
+        if self.chain.n_inv_filt.marge_monopole:
+            ftl[0] = 0.0
+        if self.chain.n_inv_filt.marge_dipole:
+            ftl[1] = 0.0
+        return ftl
+
+    def _calc_tal(self):
+        return utils.cli(self.transf)
+
+    def _calc_mask(self):
+        ninv = self.chain.n_inv_filt.n_inv
+        assert hp.npix2nside(len(ninv)) == self.nside
+        return np.where(ninv > 0, 1., 0.)
+
+    def hashdict(self):
+        hd = {'lmax': self.lmax, 'nside': self.nside, 'cltt': utils.clhash(self.cl['tt'][:self.lmax + 1]),
+              'transf': utils.clhash(self.transf[:self.lmax + 1]), 'ninv': _ninv_hash(self.ninv),
+              'marge_monopole': self.marge_monopole, 'marge_dipole': self.marge_dipole,
+              'marge_maps': self.marge_maps}
+        if self.default_rescal is False:
+            hd['rescal_cl'] = utils.clhash(self.rescal_cl)
+        return hd
+
+    def apply_ivf(self, tmap, soltn=None):
+        """Inverse-variance filtered alm of a temperature map (numpy in, numpy out; the solve runs on the GPU)."""
+        if soltn is None:
+            talm = util_alm.dalm.zeros(self.lmax)
+        else:
+            talm = util_alm.dalm.from_numpy(soltn)
+        self.chain.solve(talm, tmap)
+        return hp.almxfl(talm.numpy(), self.rescal_cl)
+
+
+class cinv_p(cinv):
+    r"""Polarization-only inverse-variance (Wiener) filter (reference: filt_cinv.py:206-338).
+
+        ninv: list of 1 (QQ = UU) or 3 (QQ, QU, UU) lists of maps / paths.
+    """
+
+    def __init__(self, lib_dir, lmax, nside, cl, transf, ninv, pcf='default', chain_descr=None, transf_blm=None,
+                 marge_qmaps=(), marge_umaps=()):
+        assert lib_dir is not None and lmax >= 1024 and nside >= 512, (lib_dir, lmax, nside)
+        super(cinv_p, self).__init__(lib_dir, lmax)
+        self.nside = nside
+        self.cl = cl
+        self.transf_e = transf
+        self.transf_b = transf if transf_blm is None else transf_blm
+        self.transf = transf if transf_blm is None else 0.5 * self.transf_e + 0.5 * self.transf_b
+        self.ninv = ninv
+        pcf = os.path.join(lib_dir, "dense.pk") if pcf == 'default' else ''
+        if chain_descr is None:
+            chain_descr = \
+                [[2, ["split(dense(" + pcf + "), 32, diag_cl)"], 512, 256, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [1, ["split(stage(2),  512, diag_cl)"], 1024, 512, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [0, ["split(stage(1), 1024, diag_cl)"], lmax, nside, np.inf, 1.0e-5, cd_solve.tr_cg, cd_solve.cache_mem()]]
+        n_inv_filt = util.jit(opfilt_pp.alm_filter_ninv, ninv, transf[0:lmax + 1], b_transf_b=transf_blm,
+                              marge_umaps=marge_umaps, marge_qmaps=marge_qmaps)
+        self.chain_descr = chain_descr
+        self.chain = util.jit(multigrid.multigrid_chain, opfilt_pp, chain_descr, cl, n_inv_filt)
+        if mpi.rank == 0:
+            if not os.path.exists(lib_dir):
+                os.makedirs(lib_dir)
+            fn = os.path.join(lib_dir, "filt_hash.pk")
+            if not os.path.exists(fn):
+                with open(fn, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+            if not os.path.exists(os.path.join(lib_dir, "fbl.dat")):
+                fel, fbl = self._calc_febl()
+                np.savetxt(os.path.join(lib_dir, "fel.dat"), fel)
+                np.savetxt(os.path.join(lib_dir, "fbl.dat"), fbl)
+            if not os.path.exists(os.path.join(lib_dir, "tal.dat")):
+                np.savetxt(os.path.join(lib_dir, "tal.dat"), self._calc_tal())
+            if not os.path.exists(os.path.join(lib_dir, "fmask.fits.gz")):
+                hp.write_map(os.path.join(lib_dir, "fmask.fits.gz"), self._calc_mask())
+        mpi.barrier()
+        fn = os.path.join(lib_dir, "filt_hash.pk")
+        with open(fn, 'rb') as f:
+            utils.hash_check(pk.load(f), self.hashdict(), fn=fn)
+
+    def hashdict(self):
+        return {'lmax': self.lmax, 'nside': self.nside,
+                'clee': utils.clhash(self.cl.get('ee', np.array([0.]))),
+                'cleb': utils.clhash(self.cl.get('eb', np.array([0.]))),
+                'clbb': utils.clhash(self.cl.get('bb', np.array([0.]))),
+                'transf': utils.clhash(self.transf), 'ninv': [_ninv_hash(self.ninv[0])]}
+
+    def apply_ivf(self, tmap, soltn=None):
+        """Inverse-variance filtered (E, B) alms of a (Q, U) map pair."""
+        if soltn is not None:
+            assert len(soltn) == 2
+            assert hp.Alm.getlmax(soltn[0].size) == self.lmax and hp.Alm.getlmax(soltn[1].size) == self.lmax
+            talm = util_alm.eblm([util_alm.dalm.from_numpy(soltn[0]), util_alm.dalm.from_numpy(soltn[1])])
+        else:
+            talm = util_alm.eblm([util_alm.dalm.zeros(self.lmax), util_alm.dalm.zeros(self.lmax)])
+        assert len(tmap) == 2
+        self.chain.solve(talm, [tmap[0], tmap[1]])
+        return talm.numpy()
+
+    def _calc_febl(self):
+        assert 'eb' not in self.chain.s_cls.keys()
+        ninv = self.chain.n_inv_filt.get_ninv()
+        lev = lambda n: np.sqrt(4. * np.pi / len(n) / np.sum(n) * len(np.where(n != 0.0)[0])) * 180. * 60. / np.pi
+        if len(ninv) == 1:
+            NlevP_uKamin = lev(ninv[0])
+        else:
+            assert len(ninv) == 3
+            NlevP_uKamin = 0.5 * lev(ninv[0]) + 0.5 * lev(ninv[2])
+        print("cinv_p::noiseP_uk_arcmin = %.3f" % NlevP_uKamin)
+        s_cls = self.chain.s_cls
+        b_e = self.chain.n_inv_filt.b_transf_e
+        b_b = self.chain.n_inv_filt.b_transf_b
+        fel = utils.cli(s_cls['ee'][:self.lmax + 1] + (NlevP_uKamin * np.pi / 180. / 60.) ** 2 * utils.cli(b_e[0:self.lmax + 1] ** 2))
+        fbl = utils.cli(s_cls['bb'][:self.lmax + 1] + (NlevP_uKamin * np.pi / 180. / 60.) ** 2 * utils.cli(b_b[0:self.lmax + 1] ** 2))
+        fel[0:2] *= 0.0
+        fbl[0:2] *= 0.0
+        return fel, fbl
+
+    def _calc_tal(self):
+        return utils.cli(self.transf)
+
+    def _calc_mask(self):
+        mask = np.ones(hp.nside2npix(self.nside), dtype=float)
+        for ninv in self.chain.n_inv_filt.get_ninv():
+            assert hp.npix2nside(len(ninv)) == self.nside
+            mask *= (ninv > 0.)
+        return mask
+
+
+class library_cinv_sepTP(filt_simple.library_sepTP):
+    """CG inverse-variance filtering of a simulation library, T and P filtered separately
+    (reference: filt_cinv.py:515-587)."""
+
+    def __init__(self, lib_dir, sim_lib, cinvt, cinvp, cl_weights, soltn_lib=None):
+        self.cinv_t = cinvt
+        self.cinv_p = cinvp
+        super(library_cinv_sepTP, self).__init__(lib_dir, sim_lib, cl_weights, soltn_lib=soltn_lib)
+        if mpi.rank == 0:
+            fname_mask = os.path.join(self.lib_dir, "fmask.fits.gz")
+            if not os.path.exists(fname_mask):
+                fmask = self.cinv_t.get_fmask()
+                assert np.all(fmask == self.cinv_p.get_fmask())
+                hp.write_map(fname_mask, fmask)
+        mpi.barrier()
+
+    def hashdict(self):
+        return {'cinv_t': self.cinv_t.hashdict(), 'cinv_p': self.cinv_p.hashdict(), 'sim_lib': self.sim_lib.hashdict()}
+
+    def get_fmask(self):
+        return hp.read_map(os.path.join(self.lib_dir, "fmask.fits.gz"))
+
+    def get_tal(self, a, lmax=None):
+        assert a.lower() in ['t', 'e', 'b'], a
+        return (self.cinv_t if a.lower() == 't' else self.cinv_p).get_tal(a, lmax=lmax)
+
+    def get_ftl(self, lmax=None):
+        return self.cinv_t.get_ftl(lmax=lmax)
+
+    def get_fel(self, lmax=None):
+        return self.cinv_p.get_fel(lmax=lmax)
+
+    def get_fbl(self, lmax=None):
+        return self.cinv_p.get_fbl(lmax=lmax)
+
+    def _apply_ivf_t(self, tmap, soltn=None):
+        return self.cinv_t.apply_ivf(tmap, soltn=soltn)
+
+    def _apply_ivf_p(self, pmap, soltn=None):
+        return self.cinv_p.apply_ivf(pmap, soltn=soltn)
+
+    def get_tmliklm(self, idx):
+        return hp.almxfl(self.get_sim_tlm(idx), self.cinv_t.cl['tt'])
+
+    def get_emliklm(self, idx):
+        return hp.almxfl(self.get_sim_elm(idx), self.cinv_p.cl['ee'])
+
+    def get_bmliklm(self, idx):
+        return hp.almxfl(self.get_sim_blm(idx), self.cinv_p.cl['bb'])

@@ -1,0 +1,215 @@
+"""Non-iterative CMB filtering libraries (reference: plancklens/filt/filt_simple.py).
+
+`library_sepTP` is the template class every separately-filtered (T and P) library derives from: it caches the
+inverse-variance filtered alms on disk and derives the Wiener-filtered ones.  `library_fullsky_sepTP` is the
+isotropic full-sky filter of params/idealized_example.py; its transforms run on the GPU.
+"""
+import os
+import pickle as pk
+
+import numpy as np
+
+from .. import hp, utils
+from ..helpers import mpi
+
+
+class library_sepTP(object):
+    """Inverse-variance and Wiener filtering of a simulation library, T and P filtered independently
+    (reference: filt_simple.py:16-183).
+
+    Args:
+        lib_dir: hashes and filtered alms are cached there
+        sim_lib: simulation library with `get_sim_tmap`, `get_sim_pmap`
+        cl_weights: CMB spectra turning inverse-variance filtered alms into Wiener-filtered ones
+    """
+
+    def __init__(self, lib_dir, sim_lib, cl_weights, soltn_lib=None, cache=True):
+        self.lib_dir = lib_dir
+        self.sim_lib = sim_lib
+        self.cl = cl_weights
+        self.soltn_lib = soltn_lib
+        self.cache = cache
+        fn_hash = os.path.join(lib_dir, 'filt_hash.pk')
+        if mpi.rank == 0:
+            if not os.path.exists(lib_dir):
+                os.makedirs(lib_dir)
+            if not os.path.exists(fn_hash):
+                with open(fn_hash, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+        mpi.barrier()
+        with open(fn_hash, 'rb') as f:
+            utils.hash_check(pk.load(f), self.hashdict(), fn=fn_hash)
+
+    # -- to be provided by the concrete filter
+    def hashdict(self):
+        assert 0, 'override this'
+
+    def get_fmask(self):
+        assert 0, 'override this'
+
+    def _apply_ivf_t(self, tmap, soltn=None):
+        assert 0, 'override this'
+
+    def _apply_ivf_p(self, pmap, soltn=None):
+        assert 0, 'override this'
+
+    def get_ftl(self):
+        r"""Isotropic approximation :math:`F^{T}_\ell = (C_\ell^{TT} + N^{T}_\ell / b_\ell^2)^{-1}`."""
+        assert 0, 'override this'
+
+    def get_fel(self):
+        assert 0, 'override this'
+
+    def get_fbl(self):
+        assert 0, 'override this'
+
+    def get_tal(self, a):
+        assert 0, 'override this'
+
+    # -- cached products
+    def _fname(self, idx, a):
+        return os.path.join(self.lib_dir, ('sim_%04d_%slm.fits' % (idx, a)) if idx >= 0 else 'dat_%slm.fits' % a)
+
+    def get_sim_tlm(self, idx):
+        """Inverse-variance filtered temperature alm of simulation idx (idx = -1: data)."""
+        fn = self._fname(idx, 't')
+        if os.path.exists(fn):
+            return hp.read_alm(fn)
+        soltn = None if self.soltn_lib is None else self.soltn_lib.get_sim_tmliklm(idx)
+        tlm = self._apply_ivf_t(self.sim_lib.get_sim_tmap(idx), soltn=soltn)
+        if self.cache:
+            hp.write_alm(fn, tlm, overwrite=True)
+        return tlm
+
+    def _get_sim_eblm(self, idx, which):
+        fn_e, fn_b = self._fname(idx, 'e'), self._fname(idx, 'b')
+        fn = fn_e if which == 'e' else fn_b
+        if os.path.exists(fn):
+            return hp.read_alm(fn)
+        soltn = None
+        if self.soltn_lib is not None:
+            soltn = np.array([self.soltn_lib.get_sim_emliklm(idx), self.soltn_lib.get_sim_bmliklm(idx)])
+        elm, blm = self._apply_ivf_p(self.sim_lib.get_sim_pmap(idx), soltn=soltn)
+        if self.cache:
+            hp.write_alm(fn_e, elm, overwrite=True)
+            hp.write_alm(fn_b, blm, overwrite=True)
+        return elm if which == 'e' else blm
+
+    def get_sim_elm(self, idx):
+        """Inverse-variance filtered E-mode alm."""
+        return self._get_sim_eblm(idx, 'e')
+
+    def get_sim_blm(self, idx):
+        """Inverse-variance filtered B-mode alm."""
+        return self._get_sim_eblm(idx, 'b')
+
+    def get_sim_tmliklm(self, idx):
+        """Wiener-filtered temperature alm."""
+        return hp.almxfl(self.get_sim_tlm(idx), self.cl['tt'])
+
+    def get_sim_emliklm(self, idx):
+        return hp.almxfl(self.get_sim_elm(idx), self.cl['ee'])
+
+    def get_sim_bmliklm(self, idx):
+        return hp.almxfl(self.get_sim_blm(idx), self.cl['bb'])
+
+
+class library_fullsky_sepTP(library_sepTP):
+    """Full-sky isotropic filter: filtered alm = f_l / transf_l * map2alm(map) (reference: filt_simple.py:346-407).
+
+    Args:
+        lib_dir, sim_lib: as above
+        nside: resolution of the simulation library
+        transf: transfer function (array, or dict with 't', 'e', 'b')
+        cl_len: spectra for the Wiener-filtered alms
+        ftl, fel, fbl: isotropic filters
+    """
+
+    def __init__(self, lib_dir, sim_lib, nside, transf, cl_len, ftl, fel, fbl, cache=False):
+        transfd = transf if isinstance(transf, dict) else {'t': transf, 'e': transf, 'b': transf}
+        assert all(k in transfd for k in 'teb')
+        self.sim_lib = sim_lib
+        self.ftl, self.fel, self.fbl = ftl, fel, fbl
+        self.lmax_fl = max(len(ftl), len(fel), len(fbl)) - 1
+        self.nside = nside
+        self.transf = transfd
+        super(library_fullsky_sepTP, self).__init__(lib_dir, sim_lib, cl_len, cache=cache)
+
+    def hashdict(self):
+        return {'sim_lib': self.sim_lib.hashdict(), 'transf': utils.clhash(self.transf['t']),
+                'cl_len': {k: utils.clhash(self.cl[k]) for k in ['tt', 'ee', 'bb']},
+                'ftl': utils.clhash(self.ftl), 'fel': utils.clhash(self.fel), 'fbl': utils.clhash(self.fbl)}
+
+    def get_fmask(self):
+        return np.ones(hp.nside2npix(self.nside), dtype=float)
+
+    def get_tal(self, a):
+        assert a.lower() in ['t', 'e', 'b']
+        return utils.cli(self.transf[a.lower()])
+
+    def get_ftl(self):
+        return np.copy(self.ftl)
+
+    def get_fel(self):
+        return np.copy(self.fel)
+
+    def get_fbl(self):
+        return np.copy(self.fbl)
+
+    def _apply_ivf_t(self, tmap, soltn=None):
+        assert len(tmap) == hp.nside2npix(self.nside), (hp.npix2nside(tmap.size), self.nside)
+        alm = hp.map2alm(tmap, lmax=self.lmax_fl, iter=0)
+        return hp.almxfl(alm, self.get_ftl() * utils.cli(self.transf['t'][:len(self.ftl)]))
+
+    def _apply_ivf_p(self, pmap, soltn=None):
+        assert len(pmap[0]) == hp.nside2npix(self.nside) and len(pmap[0]) == len(pmap[1])
+        elm, blm = hp.map2alm_spin([m for m in pmap], 2, lmax=self.lmax_fl)
+        elm = hp.almxfl(elm, self.get_fel() * utils.cli(self.transf['e'][:len(self.fel)]))
+        blm = hp.almxfl(blm, self.get_fbl() * utils.cli(self.transf['b'][:len(self.fbl)]))
+        return elm, blm
+
+
+class library_apo_sepTP(library_sepTP):
+    """Apodised-mask + isotropic filter (reference: filt_simple.py:473-534)."""
+
+    def __init__(self, lib_dir, sim_lib, apomask_path, cl_len, transf, ftl, fel, fbl, cache=False):
+        assert len(transf) >= max(len(ftl), len(fel), len(fbl))
+        assert os.path.exists(apomask_path)
+        self.ftl, self.fel, self.fbl = ftl, fel, fbl
+        self.transf = transf
+        self.lmax_fl = max(len(ftl), len(fel), len(fbl)) - 1
+        self.apomask_path = apomask_path
+        self.nside = hp.npix2nside(hp.read_map(apomask_path).size)
+        super(library_apo_sepTP, self).__init__(lib_dir, sim_lib, cl_len, cache=cache)
+
+    def hashdict(self):
+        return {'sim_lib': self.sim_lib.hashdict(), 'apomask': self.apomask_path, 'transf': utils.clhash(self.transf),
+                'cl_len': {k: utils.clhash(self.cl[k]) for k in ['tt', 'ee', 'bb']},
+                'ftl': utils.clhash(self.ftl), 'fel': utils.clhash(self.fel), 'fbl': utils.clhash(self.fbl)}
+
+    def get_fmask(self):
+        return hp.read_map(self.apomask_path)
+
+    def get_tal(self, a):
+        assert a.lower() in ['t', 'e', 'b']
+        return utils.cli(self.transf)
+
+    def get_ftl(self):
+        return np.copy(self.ftl)
+
+    def get_fel(self):
+        return np.copy(self.fel)
+
+    def get_fbl(self):
+        return np.copy(self.fbl)
+
+    def _apply_ivf_t(self, tmap, soltn=None):
+        alm = hp.map2alm(tmap * self.get_fmask(), lmax=self.lmax_fl, iter=0)
+        return hp.almxfl(alm, self.get_ftl() * utils.cli(self.transf[:len(self.ftl)]))
+
+    def _apply_ivf_p(self, pmap, soltn=None):
+        mask = self.get_fmask()
+        elm, blm = hp.map2alm_spin([m * mask for m in pmap], 2, lmax=self.lmax_fl)
+        elm = hp.almxfl(elm, self.get_fel() * utils.cli(self.transf[:len(self.fel)]))
+        blm = hp.almxfl(blm, self.get_fbl() * utils.cli(self.transf[:len(self.fbl)]))
+        return elm, blm

@@ -1,0 +1,276 @@
+r"""Polarization-only Wiener / inverse-variance filter operators on the GPU (reference: plancklens/qcinv/opfilt_pp.py).
+
+ :math:`S^{-1} (S^{-1} + Y^t N^{-1} Y)^{-1} Y^t N^{-1}`
+
+Plug-in surface of the reference module (`calc_prep`, `apply_fini`, `dot_op`, `fwd_op`, `pre_op_diag`,
+`pre_op_dense`, `alm_filter_sinv`, `alm_filter_ninv`).  Vectors are `util_alm.eblm` of GPU-resident `dalm`s.
+One `fwd_op`: spin-2 synthesis with the E/B transfer functions fused, the N^{-1} per-pixel kernel
+(scalar, or the symmetric QQ/QU/UU form), spin-2 analysis with b_l npix/4pi fused, and one four-term per-l
+combination kernel per component for S^{-1} x + N x.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import hp, sht
+from ..utils import clhash
+from . import dense, util
+from .util_alm import dalm, eblm
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+
+
+def _as_eblm_dev(alm):
+    """(eblm of dalm, converted?)"""
+    if isinstance(alm.elm, dalm):
+        return alm, False
+    return eblm([dalm.from_numpy(alm.elm), dalm.from_numpy(alm.blm)]), True
+
+
+def _combine(lmax, terms):
+    """sum_j fl_j[l] a_j[l,m] for up to four (device alm tensor, device fl tensor) terms."""
+    n = len(terms)
+    out = torch.empty_like(terms[0][0])
+    ins = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in terms])
+    fls = (ctypes.c_void_p * n)(*[t[1].data_ptr() for t in terms])
+    nfl = (ctypes.c_int * n)(*[int(t[1].numel()) for t in terms])
+    sht.check(sht._lib.load().plk_alm_combine_dev(lmax, n, ins, fls, nfl, sht._ptr(out), sht._stream()))
+    return out
+
+
+class dot_op:
+    """sum over E and B of sum_{l>=2} (2l+1) C_l^{ab}  (reference: opfilt_pp.py:27-34)."""
+
+    def __init__(self):
+        pass
+
+    def __call__(self, alm1, alm2):
+        assert alm1.lmax == alm2.lmax
+        e = sht.alm_dot(alm1.elm.t, alm2.elm.t, lmin=2)
+        b = sht.alm_dot(alm1.blm.t, alm2.blm.t, lmin=2)
+        return float(e.item()) + float(b.item())
+
+
+class _lmat2:
+    """Per-l symmetric 2x2 matrix applied to an (E, B) pair: one four-term combine per component."""
+
+    def __init__(self, mat):
+        self.mat = mat
+        self._d = [[_dev(mat[:, i, j]) for j in range(2)] for i in range(2)]
+
+    def apply(self, alm):
+        lmax = alm.lmax
+        e, b = alm.elm.t, alm.blm.t
+        re = _combine(lmax, [(e, self._d[0][0]), (b, self._d[0][1])])
+        rb = _combine(lmax, [(e, self._d[1][0]), (b, self._d[1][1])])
+        z = alm.is_zero()
+        return eblm([dalm(re, lmax, z), dalm(rb, lmax, z)])
+
+
+class alm_filter_sinv:
+    """Per-l pseudo-inverse of the (EE, EB; EB, BB) signal matrix (reference: opfilt_pp.py:87-107)."""
+
+    def __init__(self, s_cls, lmax):
+        slmat = np.zeros((lmax + 1, 2, 2), dtype=float)
+        slmat[:, 0, 0] = s_cls.get('ee', np.zeros(lmax + 1))[:lmax + 1]
+        slmat[:, 0, 1] = s_cls.get('eb', np.zeros(lmax + 1))[:lmax + 1]
+        slmat[:, 1, 0] = s_cls.get('eb', np.zeros(lmax + 1))[:lmax + 1]
+        slmat[:, 1, 1] = s_cls.get('bb', np.zeros(lmax + 1))[:lmax + 1]
+        slinv = np.zeros((lmax + 1, 2, 2))
+        for l in range(lmax + 1):
+            slinv[l] = np.linalg.pinv(slmat[l])
+        self.lmax = lmax
+        self.slinv = slinv
+        self._op = None
+
+    def calc(self, alm):
+        if self._op is None:
+            self._op = _lmat2(self.slinv)
+        a, host = _as_eblm_dev(alm)
+        r = self._op.apply(a)
+        return eblm(list(r.numpy())) if host else r
+
+    def hashdict(self):
+        return {'slinv': clhash(self.slinv.flatten())}
+
+
+class fwd_op:
+    """A x = S^{-1} x + B^t N^{-1} B x  (reference: opfilt_pp.py:37-55; no zero short-circuit there either)."""
+
+    def __init__(self, s_cls, n_inv_filt):
+        lmax = len(n_inv_filt.b_transf) - 1
+        self.s_inv_filt = alm_filter_sinv(s_cls, lmax)
+        self.n_inv_filt = n_inv_filt
+
+    def hashdict(self):
+        return {'s_inv_filt': self.s_inv_filt.hashdict(), 'n_inv_filt': self.n_inv_filt.hashdict()}
+
+    def __call__(self, alm):
+        return self.calc(alm)
+
+    def calc(self, alm):
+        nlm = alm * 1.0
+        self.n_inv_filt.apply_alm(nlm)
+        slm = self.s_inv_filt.calc(alm)
+        return nlm + slm
+
+
+class pre_op_diag:
+    """Per-l 2x2 preconditioner pinv(S^{-1} + diag(b_e^2, b_b^2)/N_l)  (reference: opfilt_pp.py:57-80)."""
+
+    def __init__(self, s_cls, n_inv_filt):
+        lmax = len(n_inv_filt.b_transf) - 1
+        s_inv_filt = alm_filter_sinv(s_cls, lmax)
+        assert (s_inv_filt.lmax + 1) >= len(n_inv_filt.b_transf)
+        ninv_fel, ninv_fbl = n_inv_filt.get_febl()
+        flmat = s_inv_filt.slinv
+        flmat[:, 0, 0] += ninv_fel[:lmax + 1]
+        flmat[:, 1, 1] += ninv_fbl[:lmax + 1]
+        self.flmat = np.linalg.pinv(flmat)
+        self._op = _lmat2(self.flmat)
+
+    def __call__(self, talm):
+        return self.calc(talm)
+
+    def calc(self, alm):
+        return self._op.apply(alm)
+
+
+def pre_op_dense(lmax, fwd_op, cache_fname=None):
+    return dense.pre_op_dense_pp(lmax, fwd_op, cache_fname=cache_fname)
+
+
+class alm_filter_ninv(object):
+    """Pixel-space polarization inverse noise: one map (QQ = UU) or three (QQ, QU, UU)
+    (reference: opfilt_pp.py:110-303).  Template projection in polarization (marge_qmaps / marge_umaps)
+    is not on the GPU path yet."""
+
+    def __init__(self, n_inv, b_transf, nlev_febl=None, b_transf_b=None, marge_qmaps=(), marge_umaps=()):
+        self.b_transf_e = np.asarray(b_transf, dtype=float)
+        self.b_transf_b = np.asarray(b_transf_b, dtype=float) if b_transf_b is not None else self.b_transf_e
+        self.b_transf = 0.5 * (self.b_transf_e + self.b_transf_b)
+        self.nside = None
+        self.n_inv = None
+        self.nlev_febl = nlev_febl
+        self._n_inv = n_inv   # maps, paths or lists of those
+        if len(marge_qmaps) > 0 or len(marge_umaps) > 0:
+            raise NotImplementedError("Q/U template marginalisation is not on the GPU path yet")
+        self.marge_qmaps = marge_qmaps
+        self.marge_umaps = marge_umaps
+        self.wmarg = False
+        self.templates_p = []
+        self._ninv_d = None
+        self._fl_cache = {}
+
+    def _load_ninv(self):
+        if self.n_inv is None:
+            self.n_inv = []
+            for tn in self._n_inv:
+                self.n_inv.append(np.asarray(util.read_map(tn), dtype=float))
+            assert len(self.n_inv) in [1, 3], len(self.n_inv)
+            self.nside = hp.npix2nside(len(self.n_inv[0]))
+            self._ninv_d = [_dev(n) for n in self.n_inv]
+
+    def _calc_febl(self):
+        self._load_ninv()
+        if len(self.n_inv) == 1:
+            nlev_febl = 10800. / np.sqrt(np.sum(self.n_inv[0]) / (4.0 * np.pi)) / np.pi
+        else:
+            nlev_febl = 10800. / np.sqrt(np.sum(0.5 * (self.n_inv[0] + self.n_inv[2])) / (4.0 * np.pi)) / np.pi
+        print("ninv_febl: using %.2f uK-amin noise Cl" % nlev_febl)
+        return nlev_febl
+
+    def get_ninv(self):
+        self._load_ninv()
+        return self.n_inv
+
+    def get_mask(self):
+        ninv = self.get_ninv()
+        mask = np.where(ninv[0] > 0, 1., 0)
+        for ni in ninv[1:]:
+            mask *= (ni > 0)
+        return mask
+
+    def get_febl(self):
+        if self.nlev_febl is None:
+            self.nlev_febl = self._calc_febl()
+        n_inv_cl_e = self.b_transf_e ** 2 / (self.nlev_febl / 180. / 60. * np.pi) ** 2
+        n_inv_cl_b = self.b_transf_b ** 2 / (self.nlev_febl / 180. / 60. * np.pi) ** 2
+        return n_inv_cl_e, n_inv_cl_b
+
+    def hashdict(self):
+        return {'n_inv': [util.mask_hash(n, dtype=np.float16) for n in self._n_inv],
+                'b_transf': clhash(self.b_transf), 'templates_p': []}
+
+    def degrade(self, nside):
+        self._load_ninv()
+        if nside == self.nside:
+            return self
+        return alm_filter_ninv([hp.ud_grade(n, nside, power=-2) for n in self.n_inv], self.b_transf_e,
+                               b_transf_b=self.b_transf_b)
+
+    def _fl(self, which, lmax):
+        k = (which, lmax)
+        if k not in self._fl_cache:
+            npix = len(self.n_inv[0])
+            b = self.b_transf_e if which[0] == 'e' else self.b_transf_b
+            self._fl_cache[k] = sht.dev_fl(b * (npix / (4. * np.pi)) if which[1:] == 'out' else b, lmax)
+        return self._fl_cache[k]
+
+    def apply_alm(self, alm):
+        """alm <- B^t N^{-1} B alm in place (reference: opfilt_pp.py:253-270)."""
+        self._load_ninv()
+        a, host = _as_eblm_dev(alm)
+        lmax = a.lmax
+        plan = sht.get_plan(self.nside, lmax)
+        qmap, umap = plan.alm2map_spin(a.elm.t, a.blm.t, 2, flg=self._fl('ein', lmax), flc=self._fl('bin', lmax))
+        self.apply_map([qmap, umap])
+        plan.map2alm_spin(qmap, umap, 2, flg=self._fl('eout', lmax), flc=self._fl('bout', lmax),
+                          out=(a.elm.t, a.blm.t))
+        a.elm.zero = a.blm.zero = False
+        if host:
+            e, b = a.numpy()
+            alm.elm[:] = e
+            alm.blm[:] = b
+
+    def apply_map(self, amap):
+        """(Q, U) <- N^{-1} (Q, U) in place (reference: opfilt_pp.py:272-303)."""
+        self._load_ninv()
+        qmap, umap = amap
+        host = not isinstance(qmap, torch.Tensor)
+        q = sht.dev_map(qmap) if host else qmap
+        u = sht.dev_map(umap) if host else umap
+        if len(self.n_inv) == 1:
+            sht.map_mul2(q, u, self._ninv_d[0])
+        else:
+            sht.map_ninv3(q, u, self._ninv_d[0], self._ninv_d[1], self._ninv_d[2])
+        if host:
+            qmap[:] = q.cpu().numpy()
+            umap[:] = u.cpu().numpy()
+
+
+def calc_prep(maps, s_cls, n_inv_filt):
+    """b = B^t N^{-1} d for d = (Q, U)  (reference: opfilt_pp.py:306-317)."""
+    qmap = sht.dev_map(np.array(util.read_map(maps[0]), dtype=float)) if not isinstance(maps[0], torch.Tensor) else maps[0].clone()
+    umap = sht.dev_map(np.array(util.read_map(maps[1]), dtype=float)) if not isinstance(maps[1], torch.Tensor) else maps[1].clone()
+    assert qmap.numel() == umap.numel()
+    lmax = len(n_inv_filt.b_transf) - 1
+    n_inv_filt.apply_map([qmap, umap])
+    plan = sht.get_plan(n_inv_filt.nside, lmax)
+    elm, blm = plan.map2alm_spin(qmap, umap, 2, flg=n_inv_filt._fl('eout', lmax), flc=n_inv_filt._fl('bout', lmax))
+    return eblm([dalm(elm, lmax), dalm(blm, lmax)])
+
+
+def apply_fini(alm, s_cls, n_inv_filt):
+    """Wiener solution -> inverse-variance filtered (E, B), in place (reference: opfilt_pp.py:320-324)."""
+    sfilt = alm_filter_sinv(s_cls, alm.lmax)
+    ret = sfilt.calc(alm)
+    if isinstance(alm.elm, dalm):
+        alm.elm.t.copy_(ret.elm.t)
+        alm.blm.t.copy_(ret.blm.t)
+    else:
+        alm.elm[:] = ret.elm
+        alm.blm[:] = ret.blm

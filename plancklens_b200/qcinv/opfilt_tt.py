@@ -1,0 +1,255 @@
+r"""Temperature-only Wiener / inverse-variance filter operators on the GPU (reference: plancklens/qcinv/opfilt_tt.py).
+
+ :math:`S^{-1} (S^{-1} + Y^t N^{-1} Y)^{-1} Y^t N^{-1}`
+
+Same plug-in surface as the reference module -- `calc_prep`, `apply_fini`, `dot_op`, `fwd_op`, `pre_op_diag`,
+`pre_op_dense`, `alm_filter_ninv` -- so `multigrid.multigrid_chain(opfilt_tt, ...)` works unchanged.  Vectors are
+`util_alm.dalm` (GPU resident); one `fwd_op` is: b_l scaling fused into the synthesis, N^{-1} and the
+monopole/dipole projection as two per-pixel kernels, analysis with the b_l npix/4pi scaling fused, and a
+two-term per-l combination for the C_l^{-1} term.  No host round trip inside the operator.
+"""
+import hashlib
+
+import numpy as np
+import torch
+
+from .. import hp, sht
+from ..utils import clhash
+from . import dense, template_removal, util
+from .util_alm import dalm
+
+
+def _cli(cl):
+    cl = np.asarray(cl, dtype=float)
+    ret = np.zeros_like(cl)
+    nz = cl != 0.
+    ret[nz] = 1. / cl[nz]
+    return ret
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+
+
+def _as_dalm(alm):
+    return alm if isinstance(alm, dalm) else dalm.from_numpy(alm)
+
+
+def calc_prep(m, s_cls, n_inv_filt):
+    """b = B^t N^{-1} d  (reference: opfilt_tt.py:30-36)."""
+    tmap = sht.dev_map(m).clone() if isinstance(m, torch.Tensor) else sht.dev_map(np.array(m, dtype=float))
+    n_inv_filt.apply_map(tmap)
+    lmax = len(n_inv_filt.b_transf) - 1
+    plan = sht.get_plan(n_inv_filt.nside, lmax)
+    return dalm(plan.map2alm(tmap, fl=n_inv_filt.fl_out(lmax)), lmax)
+
+
+def apply_fini(alm, s_cls, n_inv_filt):
+    """Wiener-filtered solution -> inverse-variance filtered alm, in place (reference: opfilt_tt.py:39-41)."""
+    fl = _dev(_cli(s_cls['tt']))
+    if isinstance(alm, dalm):
+        alm.almxfl(fl, inplace=True)
+    else:
+        alm[:] = hp.almxfl(alm, _cli(s_cls['tt']))
+
+
+class dot_op:
+    """sum_l (2l+1) C_l^{ab}  (reference: opfilt_tt.py:43-51)."""
+
+    def __init__(self):
+        pass
+
+    def __call__(self, alm1, alm2):
+        assert alm1.lmax == alm2.lmax
+        return float(sht.alm_dot(alm1.t, alm2.t, lmin=0).item())
+
+
+class fwd_op:
+    """A x = C_l^{-1} x + B^t N^{-1} B x  (reference: opfilt_tt.py:54-73)."""
+
+    def __init__(self, s_cls, n_inv_filt):
+        self.cltt_inv = _cli(s_cls['tt'])
+        self.n_inv_filt = n_inv_filt
+        self._cltt_inv_d = _dev(self.cltt_inv)
+        self._ones_d = None
+
+    def hashdict(self):
+        return {'cltt_inv': clhash(self.cltt_inv), 'n_inv_filt': self.n_inv_filt.hashdict()}
+
+    def __call__(self, talm):
+        return self.calc(talm)
+
+    def calc(self, talm):
+        if talm.is_zero():   # do nothing if zero (reference: opfilt_tt.py:68)
+            return talm
+        alm = talm.copy()
+        self.n_inv_filt.apply_alm(alm)
+        alm.t = _combine2(alm.t, None, talm.t, self._cltt_inv_d)
+        return alm
+
+
+def _combine2(a, fla, b, flb):
+    """fla[l] a + flb[l] b on device alms (fl None = 1) via plk_alm_combine_dev."""
+    import ctypes
+    lib = sht._lib.load()
+    lmax = sht.alm_lmax(a.numel())
+    ones = _ones(lmax)
+    fla = ones if fla is None else fla
+    flb = ones if flb is None else flb
+    out = torch.empty_like(a)
+    ins = (ctypes.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+    fls = (ctypes.c_void_p * 2)(fla.data_ptr(), flb.data_ptr())
+    nfl = (ctypes.c_int * 2)(int(fla.numel()), int(flb.numel()))
+    sht.check(lib.plk_alm_combine_dev(lmax, 2, ins, fls, nfl, sht._ptr(out), sht._stream()))
+    return out
+
+
+_ONES = {}
+
+
+def _ones(lmax):
+    if lmax not in _ONES:
+        _ONES[lmax] = torch.ones(lmax + 1, dtype=torch.float64, device='cuda')
+    return _ONES[lmax]
+
+
+class pre_op_diag:
+    """Harmonic-space diagonal preconditioner (reference: opfilt_tt.py:76-93)."""
+
+    def __init__(self, s_cls, n_inv_filt):
+        cltt = s_cls['tt']
+        assert len(cltt) >= len(n_inv_filt.b_transf)
+        n_inv_cl = np.sum(n_inv_filt.n_inv) / (4.0 * np.pi)
+        lmax = len(n_inv_filt.b_transf) - 1
+        assert lmax <= (len(cltt) - 1)
+        filt = _cli(cltt[:lmax + 1])
+        filt += n_inv_cl * n_inv_filt.b_transf[:lmax + 1] ** 2
+        self.filt = _cli(filt)
+        self._filt_d = _dev(self.filt)
+
+    def __call__(self, talm):
+        return self.calc(talm)
+
+    def calc(self, talm):
+        return talm.almxfl(self._filt_d)
+
+
+def pre_op_dense(lmax, fwd_op, cache_fname=None):
+    return dense.pre_op_dense_tt(lmax, fwd_op, cache_fname=cache_fname)
+
+
+class alm_filter_ninv(object):
+    """Pixel-space inverse noise with monopole / dipole marginalisation (reference: opfilt_tt.py:99-205)."""
+
+    def __init__(self, n_inv, b_transf, marge_monopole=False, marge_dipole=False, marge_uptolmin=-1, marge_maps=(),
+                 nlev_ftl=None):
+        if isinstance(n_inv, list):
+            n_inv_prod = util.load_map(n_inv[0])
+            for n in n_inv[1:]:
+                n_inv_prod = n_inv_prod * util.load_map(n)
+            n_inv = n_inv_prod
+        else:
+            n_inv = util.load_map(n_inv)
+        n_inv = np.asarray(n_inv, dtype=float)
+        if len(marge_maps) > 0 or marge_uptolmin >= 0:
+            raise NotImplementedError("template maps / marge_uptolmin are not on the GPU path yet; "
+                                      "monopole and dipole marginalisation are (SURVEY.md section 8a)")
+        nz = n_inv != 0.0
+        print("opfilt_tt: inverse noise map std dev / av = %.3e" % (np.std(n_inv[nz]) / np.average(n_inv[nz])))
+
+        self.n_inv = n_inv
+        self.b_transf = np.asarray(b_transf, dtype=float)
+        self.npix = len(n_inv)
+        self.nside = hp.npix2nside(self.npix)
+        self.marge_monopole = marge_monopole
+        self.marge_dipole = marge_dipole
+        self.marge_uptolmin = marge_uptolmin
+        self.templates = []
+        self.templates_hash = []
+        if marge_monopole:
+            self.templates.append(template_removal.template_monopole())
+        if marge_dipole:
+            self.templates.append(template_removal.template_dipole())
+
+        self._ninv_d = _dev(n_inv)
+        self._fl_cache = {}
+        self._plan0 = sht.get_plan(self.nside, max(len(self.b_transf) - 1, 1))
+        self._sums = torch.zeros(4, dtype=torch.float64, device='cuda')
+        if len(self.templates) != 0:
+            modes = [i for t in self.templates for i in t.modes]
+            # P^t N^{-1} P on the active modes: row a = sum_p n_inv mode_a {1, x, y, z}
+            full = np.zeros((4, 4))
+            minus_eye = -torch.eye(4, dtype=torch.float64, device='cuda')
+            for a in modes:
+                ea = torch.zeros(4, dtype=torch.float64, device='cuda')
+                ea[a] = 1.0
+                tmp = torch.zeros(self.npix, dtype=torch.float64, device='cuda')
+                self._plan0.modes_sub(tmp, self._ninv_d, ea, minus_eye.reshape(-1))   # tmp = n_inv * mode_a
+                full[a] = self._plan0.modes_dot(tmp).cpu().numpy()
+            sub = full[np.ix_(modes, modes)]
+            sub = 0.5 * (sub + sub.T)
+            eigv, eigw = np.linalg.eigh(sub)
+            self.Pt_Nn1_P_inv = np.dot(np.dot(eigw, np.diag(1.0 / eigv)), np.transpose(eigw))
+            pinv4 = np.zeros((4, 4))
+            pinv4[np.ix_(modes, modes)] = self.Pt_Nn1_P_inv
+            self._pinv_d = _dev(pinv4.reshape(-1))
+
+        if nlev_ftl is None:
+            nlev_ftl = 10800. / np.sqrt(np.sum(self.n_inv) / (4.0 * np.pi)) / np.pi
+        self.nlev_ftl = nlev_ftl
+        print("ninv_ftl: using %.2f uK-amin noise Cl" % self.nlev_ftl)
+
+    def hashdict(self):
+        return {'n_inv': clhash(self.n_inv), 'b_transf': clhash(self.b_transf),
+                'marge_monopole': self.marge_monopole, 'marge_dipole': self.marge_dipole,
+                'templates_hash': self.templates_hash, 'marge_uptolmin': self.marge_uptolmin}
+
+    def get_ftl(self):
+        return self.b_transf ** 2 / (self.nlev_ftl / 60. / 180. * np.pi) ** 2
+
+    def degrade(self, nside):
+        """Same filter on a coarser grid: n_inv summed over children (reference: opfilt_tt.py:172-181)."""
+        if nside == self.nside:
+            return self
+        print("DEGRADING WITH NO MARGE MAPS")
+        return alm_filter_ninv(hp.ud_grade(self.n_inv, nside, power=-2), self.b_transf,
+                               marge_monopole=self.marge_monopole, marge_dipole=self.marge_dipole,
+                               marge_uptolmin=self.marge_uptolmin, marge_maps=[])
+
+    # per-l factors on the device, padded to the lmax of the vector they multiply
+    def fl_in(self, lmax):
+        k = ('in', lmax)
+        if k not in self._fl_cache:
+            self._fl_cache[k] = sht.dev_fl(self.b_transf, lmax)
+        return self._fl_cache[k]
+
+    def fl_out(self, lmax):
+        k = ('out', lmax)
+        if k not in self._fl_cache:
+            self._fl_cache[k] = sht.dev_fl(self.b_transf * (self.npix / (4. * np.pi)), lmax)
+        return self._fl_cache[k]
+
+    def apply_alm(self, alm):
+        """alm <- B^t N^{-1} B alm, in place (reference: opfilt_tt.py:183-190)."""
+        host = not isinstance(alm, dalm)
+        v = _as_dalm(alm)
+        plan = sht.get_plan(self.nside, v.lmax)
+        tmap = plan.alm2map(v.t, fl=self.fl_in(v.lmax))
+        self.apply_map(tmap)
+        plan.map2alm(tmap, fl=self.fl_out(v.lmax), out=v.t)
+        v.zero = False
+        if host:
+            alm[:] = v.numpy()
+
+    def apply_map(self, tmap):
+        """tmap <- N^{-1} tmap with the templates projected out, in place (reference: opfilt_tt.py:193-205)."""
+        host = not isinstance(tmap, torch.Tensor)
+        t = sht.dev_map(tmap) if host else tmap
+        plan = sht.get_plan(self.nside, self._plan0.lmax)
+        if len(self.templates) != 0:
+            plan.modes_dot(t, w=self._ninv_d, out=self._sums)          # t *= n_inv ; sums = P^t t
+            plan.modes_sub(t, self._ninv_d, self._sums, self._pinv_d)    # t -= n_inv P (P^t N^-1 P)^-1 sums
+        else:
+            sht.map_mul(t, self._ninv_d)
+        if host:
+            tmap[:] = t.cpu().numpy()

@@ -1,0 +1,393 @@
+"""Quadratic-estimator evaluation (reference: plancklens/qest.py), GPU resident.
+
+`library.get_sim_qlm(k, idx)` keeps the reference's behaviour (keys, caching under lib_dir, symmetrisation when
+the two legs come from different filtering libraries).  For the lensing keys 'ptt'/'xtt', 'p_p'/'x_p', 'p'/'x'
+the legs are synthesised, multiplied pixel by pixel and analysed back entirely on the GPU:
+
+  T estimator (qest.py:248-263):   alm2map(T_bar)                       ->  t
+                                   alm2map_spin(-sqrt(l(l+1)) T^WF, 1)  ->  (G, C);   (G t, C t)
+  P estimator (qest.py:265-285):   alm2map_spin(1/2 E_bar, 1/2 B_bar, 2) ->  (Q, U)
+                                   alm2map_spin(sqrt((l-2)(l+3)) (E,B)^WF, 3) -> (G3, C3)
+                                   alm2map_spin(sqrt((l+2)(l-1)) (E,B)^WF, 1) -> (G1, C1)
+                                   (Q - iU)(G3 + iC3) - (Q + iU)(G1 - iC1)
+  then map2alm_spin(., 1, lmax_qlm) x -sqrt(L(L+1)).
+
+All per-l factors are fused into the transforms (`fl` arguments of libplk_b200).  For the MV key 'p' the T and P
+real-space products are summed BEFORE one spin-1 analysis (the analysis is linear, so this equals the reference's
+sum of two analyses to round-off and saves one of seven transforms); `merge_analysis=False` restores the
+reference's order of operations.
+"""
+import collections
+import os
+import pickle as pk
+
+import numpy as np
+import torch
+
+from . import hp, sht
+from . import utils as ut
+from .helpers import mpi
+
+_write_alm = lambda fn, alm: hp.write_alm(fn, alm, overwrite=True)
+
+
+def library_jtTP(lib_dir, ivfs1, ivfs2, nside, lmax_qlm=None, resplib=None):
+    return library(lib_dir, ivfs1, ivfs2, nside, lmax_qlm=lmax_qlm, resplib=resplib)
+
+
+def library_sepTP(lib_dir, ivfs1, ivfs2, clte, nside, lmax_qlm=None, resplib=None):
+    return library(lib_dir, ivfs1, ivfs2, nside, clte=clte, lmax_qlm=lmax_qlm, resplib=resplib)
+
+
+def _dfl(fl):
+    return torch.from_numpy(np.ascontiguousarray(fl, dtype=np.float64)).cuda()
+
+
+def _grad_fl(lmax, spin, kind):
+    """per-l factors of the gradient legs (reference: qest.py:463, 494-503)."""
+    l = np.arange(lmax + 1, dtype=float)
+    if kind == 't':
+        return -np.sqrt(l * (l + 1))
+    fl = (l + 2) * (l - 1) if spin == 1 else (l - 2) * (l + 3)
+    fl[:spin] = 0.
+    return np.sqrt(np.maximum(fl, 0.))
+
+
+class qe_device:
+    """The GPU evaluation of the lensing estimators from device-resident filtered alms.
+
+    tbar, ebar, bbar: inverse-variance filtered alms; twf, ewf, bwf: Wiener-filtered alms entering the gradient
+    legs (already including the C^TE cross terms when relevant).  All are complex128 CUDA tensors of lmax_ivf.
+    """
+
+    def __init__(self, nside, lmax_ivf, lmax_qlm):
+        self.nside, self.lmax_ivf, self.lmax_qlm = nside, lmax_ivf, lmax_qlm
+        self.plan_ivf = sht.get_plan(nside, lmax_ivf)
+        self.plan_qlm = sht.get_plan(nside, lmax_qlm)
+        self.fl_t1 = _dfl(_grad_fl(lmax_ivf, 1, 't'))
+        self.fl_p1 = _dfl(_grad_fl(lmax_ivf, 1, 'p'))
+        self.fl_p3 = _dfl(_grad_fl(lmax_ivf, 3, 'p'))
+        self.fl_half = _dfl(0.5 * np.ones(lmax_ivf + 1))
+        L = np.arange(lmax_qlm + 1, dtype=float)
+        self.fl_out = _dfl(-np.sqrt(L * (L + 1)))
+        npix = 12 * nside ** 2
+        self._buf = [torch.empty(npix, dtype=torch.float64, device='cuda') for _ in range(10)]
+
+    def t_products(self, tbar, twf, out=None):
+        """(G t, C t) maps of the temperature estimator."""
+        b = self._buf
+        t = self.plan_ivf.alm2map(tbar, out=b[0])
+        G, C = self.plan_ivf.alm2map_spin(twf, None, 1, flg=self.fl_t1, out=(b[1], b[2]) if out is None else out)
+        sht.map_mul2(G, C, t)
+        return G, C
+
+    def p_products(self, ebar, bbar, ewf, bwf, out=None):
+        """(Re, Im) maps of the polarization estimator."""
+        b = self._buf
+        Q, U = self.plan_ivf.alm2map_spin(ebar, bbar, 2, flg=self.fl_half, flc=self.fl_half, out=(b[0], b[3]))
+        G3, C3 = self.plan_ivf.alm2map_spin(ewf, bwf, 3, flg=self.fl_p3, flc=self.fl_p3, out=(b[4], b[5]))
+        G1, C1 = self.plan_ivf.alm2map_spin(ewf, bwf, 1, flg=self.fl_p1, flc=self.fl_p1, out=(b[6], b[7]))
+        re, im = (b[8], b[9]) if out is None else out
+        sht.map_qe_pp(Q, U, G3, C3, G1, C1, re, im)
+        return re, im
+
+    def analyse(self, re, im):
+        return self.plan_qlm.map2alm_spin(re, im, 1, flg=self.fl_out, flc=self.fl_out)
+
+    def ptt(self, tbar, twf):
+        return self.analyse(*self.t_products(tbar, twf))
+
+    def p_p(self, ebar, bbar, ewf, bwf):
+        return self.analyse(*self.p_products(ebar, bbar, ewf, bwf))
+
+    def p(self, tbar, ebar, bbar, twf, ewf, bwf, merge_analysis=True):
+        b = self._buf
+        re, im = self.p_products(ebar, bbar, ewf, bwf)             # in b[8], b[9]
+        if merge_analysis:
+            G, C = self.t_products(tbar, twf)                       # in b[1], b[2]
+            sht.map_axpy(re, G, 1.0)
+            sht.map_axpy(im, C, 1.0)
+            return self.analyse(re, im)
+        GP, CP = self.analyse(re, im)
+        GT, CT = self.analyse(*self.t_products(tbar, twf))
+        sht.alm_axpy(GP, GT, 1.0)
+        sht.alm_axpy(CP, CT, 1.0)
+        return GP, CP
+
+
+class library:
+    r"""QE evaluation library built on two inverse-variance filtered simulation libraries
+    (reference: qest.py:50-438).
+
+        Args:
+            lib_dir: estimates are cached there
+            ivfs1, ivfs2: filtering libraries of the first and second leg
+            nside: resolution of the real-space products
+            clte (optional): TE spectrum used to build the Wiener-filtered legs from separately filtered T and P
+            lmax_qlm (optional): maximum multipole of the estimates (default 3 nside - 1)
+    """
+
+    def __init__(self, lib_dir, ivfs1, ivfs2, nside, clte=None, lmax_qlm=None, resplib=None, merge_analysis=True):
+        if lmax_qlm is None:
+            lmax_qlm = 3 * nside - 1
+        self.lib_dir = lib_dir
+        self.prefix = lib_dir
+        self.nside = nside
+        self.lmax_qlm = {'T': lmax_qlm, 'P': lmax_qlm, 'PS': lmax_qlm}
+        self.merge_analysis = merge_analysis
+        if clte is None:
+            self.f2map1 = lib_filt2map(ivfs1, nside)
+            self.f2map2 = lib_filt2map(ivfs2, nside)
+        else:
+            self.f2map1 = lib_filt2map_sepTP(ivfs1, nside, clte)
+            self.f2map2 = lib_filt2map_sepTP(ivfs2, nside, clte)
+        fnhash = os.path.join(self.lib_dir, "qe_sim_hash.pk")
+        if mpi.rank == 0 and not os.path.exists(fnhash):
+            if not os.path.exists(self.lib_dir):
+                os.makedirs(self.lib_dir)
+            with open(fnhash, 'wb') as f:
+                pk.dump(self.hashdict(), f, protocol=2)
+        mpi.barrier()
+        with open(fnhash, 'rb') as f:
+            ut.hash_check(pk.load(f), self.hashdict(), fn=fnhash)
+        fn_fsky = os.path.join(lib_dir, 'fskies.dat')
+        if mpi.rank == 0 and not os.path.exists(fn_fsky):
+            ms = {1: self.get_mask(1), 2: self.get_mask(2)}
+            with open(fn_fsky, 'w') as f:
+                for i in [1, 2]:
+                    for j in [1, 2][i - 1:]:
+                        f.write('%4s %.5f \n' % (10 * i + j, np.mean(ms[i] * ms[j])))
+        mpi.barrier()
+        self.fskies = {}
+        with open(fn_fsky) as f:
+            for line in f:
+                key, val = line.split()
+                self.fskies[int(key)] = float(val)
+        self.fsky11, self.fsky12, self.fsky22 = self.fskies[11], self.fskies[12], self.fskies[22]
+        self.resplib = resplib
+        self.keys_fund = ['ptt', 'xtt', 'p_p', 'x_p', 'p', 'x']
+        self.keys = self.keys_fund + ['p_tp', 'x_tp']
+        self.keys_remaps = {}
+        self._qe = None
+
+    def hashdict(self):
+        return {'f2map1': self.f2map1.hashdict(), 'f2map2': self.f2map2.hashdict()}
+
+    def get_fundkeys(self, k_list):
+        klist = k_list if isinstance(k_list, list) else [k_list]
+        ret = []
+        for k in klist:
+            if k in self.keys_fund:
+                ret.append(k)
+            elif '_tp' in k:
+                ret += [k[0] + 'tt', k[0] + '_p']
+        return list(collections.OrderedDict.fromkeys(ret))
+
+    def get_fsky(self, id):
+        assert id in [11, 22, 12], id
+        return self.fskies[id]
+
+    def get_lmax_qlm(self, k):
+        assert self.lmax_qlm['T'] == self.lmax_qlm['P']
+        return self.lmax_qlm['T']
+
+    def get_mask(self, leg):
+        assert leg in [1, 2]
+        return self.f2map1.ivfs.get_fmask() if leg == 1 else self.f2map2.ivfs.get_fmask()
+
+    def get_sim_qlm(self, k, idx, lmax=None):
+        """QE estimate for key k and simulation idx (computed on the GPU and cached on first call)."""
+        k = self.keys_remaps.get(k, k)
+        if lmax is None:
+            lmax = self.get_lmax_qlm(k)
+        assert lmax <= self.get_lmax_qlm(k)
+        if k in ['p_tp', 'x_tp']:
+            return self.get_sim_qlm('%stt' % k[0], idx, lmax=lmax) + self.get_sim_qlm('%s_p' % k[0], idx, lmax=lmax)
+        assert k in self.keys_fund, (k, self.keys_fund)
+        fname = os.path.join(self.lib_dir, 'sim_%s_%04d.fits' % (k, idx) if idx != -1 else 'dat_%s.fits' % k)
+        if not os.path.exists(fname):
+            if k in ['ptt', 'xtt']:
+                self._build_sim_Tgclm(idx)
+            elif k in ['p_p', 'x_p']:
+                self._build_sim_Pgclm(idx)
+            elif k in ['p', 'x']:
+                self._build_sim_MVgclm(idx)
+        return ut.alm_copy(hp.read_alm(fname), lmax=lmax)
+
+    def get_dat_qlm(self, k, **kwargs):
+        return self.get_sim_qlm(k, -1, **kwargs)
+
+    def get_sim_qlm_mf(self, k, mc_sims, lmax=None):
+        """Mean-field estimate: average of the QE over mc_sims (reference: qest.py:206-246)."""
+        if lmax is None:
+            lmax = self.get_lmax_qlm(k)
+        assert lmax <= self.get_lmax_qlm(k)
+        if k in ['p_tp', 'x_tp']:
+            return self.get_sim_qlm_mf('%stt' % k[0], mc_sims, lmax=lmax) + self.get_sim_qlm_mf('%s_p' % k[0], mc_sims, lmax=lmax)
+        assert k in self.keys_fund, (k, self.keys_fund)
+        fname = os.path.join(self.lib_dir, 'simMF_k1%s_%s.fits' % (k, ut.mchash(mc_sims)))
+        if not os.path.exists(fname):
+            this_mcs = np.unique(mc_sims)
+            MF = np.zeros(hp.Alm.getsize(lmax), dtype=complex)
+            if len(this_mcs) == 0:
+                return MF
+            for i, idx in ut.enumerate_progress(this_mcs, label='calculating %s MF' % k):
+                MF += self.get_sim_qlm(k, idx, lmax=lmax)
+            MF /= len(this_mcs)
+            _write_alm(fname, MF)
+        return ut.alm_copy(hp.read_alm(fname), lmax=lmax)
+
+    # ---- GPU evaluation
+    def _engine(self, lmax_ivf):
+        if self._qe is None or self._qe.lmax_ivf != lmax_ivf:
+            self._qe = qe_device(self.nside, lmax_ivf, self.lmax_qlm['T'])
+        return self._qe
+
+    def _legs(self, idx, k, swapped):
+        f1 = self.f2map2 if swapped else self.f2map1
+        f2 = self.f2map1 if swapped else self.f2map2
+        return f1, f2
+
+    def _get_sim_Tgclm(self, idx, k, swapped=False):
+        """T-only estimator, gradient and curl (reference: qest.py:248-263)."""
+        f1, f2 = self._legs(idx, k, swapped)
+        tbar = f1.ivfs.get_sim_tlm(idx)
+        twf = f2.wf_tlm(idx, k)
+        qe = self._engine(hp.Alm.getlmax(tbar.size))
+        G, C = qe.ptt(sht.dev_alm(tbar), sht.dev_alm(twf))
+        return G.cpu().numpy(), C.cpu().numpy()
+
+    def _get_sim_Pgclm(self, idx, k, swapped=False):
+        """P-only estimator (reference: qest.py:265-285)."""
+        f1, f2 = self._legs(idx, k, swapped)
+        ebar, bbar = f1.ivfs.get_sim_elm(idx), f1.ivfs.get_sim_blm(idx)
+        ewf, bwf = f2.wf_eblm(idx, k)
+        qe = self._engine(hp.Alm.getlmax(ebar.size))
+        G, C = qe.p_p(sht.dev_alm(ebar), sht.dev_alm(bbar), sht.dev_alm(ewf), sht.dev_alm(bwf))
+        return G.cpu().numpy(), C.cpu().numpy()
+
+    def _get_sim_MVgclm(self, idx, k, swapped=False):
+        """MV estimator = P + T pieces with the C^TE cross terms in the Wiener legs (reference: qest.py:318-322)."""
+        assert k == 'p'
+        f1, f2 = self._legs(idx, k, swapped)
+        tbar, ebar, bbar = f1.ivfs.get_sim_tlm(idx), f1.ivfs.get_sim_elm(idx), f1.ivfs.get_sim_blm(idx)
+        twf = f2.wf_tlm(idx, 'p')
+        ewf, bwf = f2.wf_eblm(idx, 'p')
+        qe = self._engine(hp.Alm.getlmax(tbar.size))
+        G, C = qe.p(sht.dev_alm(tbar), sht.dev_alm(ebar), sht.dev_alm(bbar), sht.dev_alm(twf), sht.dev_alm(ewf),
+                    sht.dev_alm(bwf), merge_analysis=self.merge_analysis)
+        return G.cpu().numpy(), C.cpu().numpy()
+
+    def _symmetrised(self, fun, idx, k):
+        G, C = fun(idx, k)
+        if not self.f2map1.ivfs == self.f2map2.ivfs:
+            _G, _C = fun(idx, k, swapped=True)
+            G = 0.5 * (G + _G)
+            C = 0.5 * (C + _C)
+        return G, C
+
+    def _save(self, kg, kc, idx, G, C):
+        _write_alm(os.path.join(self.lib_dir, 'sim_%s_%04d.fits' % (kg, idx) if idx != -1 else 'dat_%s.fits' % kg), G)
+        _write_alm(os.path.join(self.lib_dir, 'sim_%s_%04d.fits' % (kc, idx) if idx != -1 else 'dat_%s.fits' % kc), C)
+
+    def _build_sim_Tgclm(self, idx):
+        self._save('ptt', 'xtt', idx, *self._symmetrised(self._get_sim_Tgclm, idx, 'ptt'))
+
+    def _build_sim_Pgclm(self, idx):
+        self._save('p_p', 'x_p', idx, *self._symmetrised(self._get_sim_Pgclm, idx, 'p_p'))
+
+    def _build_sim_MVgclm(self, idx):
+        self._save('p', 'x', idx, *self._symmetrised(self._get_sim_MVgclm, idx, 'p'))
+
+
+class lib_filt2map(object):
+    """Filtered alms -> real-space legs, jointly filtered T and P (reference: qest.py:441-530).
+
+    The `get_*map` methods return numpy maps as in the reference; `wf_tlm` / `wf_eblm` return the Wiener-filtered
+    alms that enter the gradient legs (what the GPU path consumes)."""
+
+    def __init__(self, ivfs, nside):
+        self.ivfs = ivfs
+        self.nside = nside
+
+    def hashdict(self):
+        return {'ivfs': self.ivfs.hashdict(), 'nside': self.nside}
+
+    def wf_tlm(self, idx, k=None):
+        return self.ivfs.get_sim_tmliklm(idx)
+
+    def wf_eblm(self, idx, k=None):
+        return self.ivfs.get_sim_emliklm(idx), self.ivfs.get_sim_bmliklm(idx)
+
+    def get_gtmap(self, idx, k=None, xfilt=None):
+        r"""\sum_{lm} MAP_talm sqrt(l (l + 1)) _1 Ylm(n): spin-1 transform with zero curl (reference: qest.py:453-464)."""
+        assert xfilt is None, 'not implemented'
+        tlm = self.wf_tlm(idx, k)
+        lmax = hp.Alm.getlmax(tlm.size)
+        Glm = hp.almxfl(tlm, _grad_fl(lmax, 1, 't'))
+        return hp.alm2map_spin([Glm, np.zeros_like(Glm)], self.nside, 1, lmax)
+
+    def get_tmap(self, idx):
+        return hp.alm2map(self.ivfs.get_sim_tmliklm(idx), self.nside)
+
+    def get_pmap(self, idx):
+        Glm, Clm = self.ivfs.get_sim_emliklm(idx), self.ivfs.get_sim_bmliklm(idx)
+        return hp.alm2map_spin([Glm, Clm], self.nside, 2, hp.Alm.getlmax(Glm.size))
+
+    def get_gpmap(self, idx, spin, k=None, xfilt=None):
+        r"""\sum_{lm} (Elm +- iBlm) sqrt((l+2)(l-1)) _1 Ylm(n) or sqrt((l-2)(l+3)) _3 Ylm(n) (reference: qest.py:481-504)."""
+        assert spin in [1, 3]
+        assert xfilt is None, 'not implemented'
+        Glm, Clm = self.wf_eblm(idx, k)
+        lmax = hp.Alm.getlmax(Glm.size)
+        fl = _grad_fl(lmax, spin, 'p')
+        return hp.alm2map_spin([hp.almxfl(Glm, fl), hp.almxfl(Clm, fl)], self.nside, spin, lmax)
+
+    def get_irestmap(self, idx, xfilt=None):
+        assert xfilt is None, 'not implemented'
+        reslm = self.ivfs.get_sim_tlm(idx)
+        return hp.alm2map(reslm, self.nside, lmax=hp.Alm.getlmax(reslm.size))
+
+    def get_irespmap(self, idx, xfilt=None):
+        assert xfilt is None, 'not implemented'
+        reselm, resblm = self.ivfs.get_sim_elm(idx), self.ivfs.get_sim_blm(idx)
+        assert hp.Alm.getlmax(reselm.size) == hp.Alm.getlmax(resblm.size)
+        return hp.alm2map_spin([reselm * 0.5, resblm * 0.5], self.nside, 2, hp.Alm.getlmax(reselm.size))
+
+
+class lib_filt2map_sepTP(lib_filt2map):
+    """Same for separately filtered T and P: the C^TE cross terms are added to the Wiener legs of the MV
+    estimator (reference: qest.py:533-638)."""
+
+    def __init__(self, ivfs, nside, clte):
+        super(lib_filt2map_sepTP, self).__init__(ivfs, nside)
+        self.clte = clte
+
+    def hashdict(self):
+        return {'ivfs': self.ivfs.hashdict(), 'nside': self.nside, 'clte': ut.clhash(self.clte)}
+
+    def wf_tlm(self, idx, k=None):
+        assert k in ['ptt', 'p'], k
+        tlm = self.ivfs.get_sim_tmliklm(idx)
+        if k == 'p':
+            tlm = tlm + hp.almxfl(self.ivfs.get_sim_elm(idx), self.clte)      # qest.py:582-588
+        return tlm
+
+    def wf_eblm(self, idx, k=None):
+        assert k in ['p_p', 'p'], k
+        elm, blm = self.ivfs.get_sim_emliklm(idx), self.ivfs.get_sim_bmliklm(idx)
+        if k == 'p':
+            elm = elm + hp.almxfl(self.ivfs.get_sim_tlm(idx), self.clte)      # qest.py:613-618
+        return elm, blm
+
+    def get_tmap(self, idx, joint=False):
+        tlm = self.ivfs.get_sim_tmliklm(idx)
+        if joint:
+            tlm = tlm + hp.almxfl(self.ivfs.get_sim_elm(idx), self.clte)
+        return hp.alm2map(tlm, self.nside)
+
+    def get_pmap(self, idx, joint=False):
+        Glm, Clm = self.ivfs.get_sim_emliklm(idx), self.ivfs.get_sim_bmliklm(idx)
+        if joint:
+            Glm = Glm + hp.almxfl(self.ivfs.get_sim_tlm(idx), self.clte)
+        return hp.alm2map_spin([Glm, Clm], self.nside, 2, hp.Alm.getlmax(Glm.size))

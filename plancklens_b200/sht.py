@@ -236,6 +236,32 @@ def alm_splice(lo, hi, lsplit):
     return out
 
 
+def map_axpy(y, x, a):
+    """y += a x on real maps (even number of pixels)"""
+    assert y.numel() % 2 == 0
+    check(_lib.load().plk_alm_axpy_dev(y.numel() // 2, float(a), None, _ptr(x), _ptr(y), _stream()))
+    return y
+
+
+def profile_enable(on=True):
+    check(_lib.load().plk_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """-> {kind: (count, total_ms)} for kinds synth0, synths, anal0, anals"""
+    c = (ctypes.c_int * 4)()
+    t = (ctypes.c_double * 4)()
+    check(_lib.load().plk_profile_read(c, t))
+    names = ['synth_spin0', 'synth_spins', 'anal_spin0', 'anal_spins']
+    return {n: (int(c[i]), float(t[i])) for i, n in enumerate(names)}
+
+
+def fp64_peak_tflops(reps=3):
+    v = ctypes.c_double()
+    check(_lib.load().plk_fp64_peak(ctypes.byref(v), reps))
+    return float(v.value)
+
+
 def map_mul(y, a):
     check(_lib.load().plk_map_mul_dev(y.numel(), _ptr(y), _ptr(a), _stream()))
     return y

@@ -1,0 +1,61 @@
+"""Gaussian CMB alm simulations from fiducial spectra (reference: plancklens/sims/cmbs.py:25-102)."""
+import numpy as np
+
+from .. import hp, utils
+
+
+def _get_fields(cls):
+    order = ['p', 't', 'e', 'b', 'o']
+    ret = [f for f in order if (f + f) in cls.keys()]
+    for k in cls.keys():
+        for f in k:
+            if f not in ret:
+                ret.append(f)
+    return ret
+
+
+class sims_cmb_unl:
+    """Correlated Gaussian alms: phases coloured by the per-l matrix square root of the spectra."""
+
+    def __init__(self, cls_unl, lib_pha):
+        lmax = lib_pha.lmax
+        fields = _get_fields(cls_unl)
+        nf = len(fields)
+        rmat = np.zeros((lmax + 1, nf, nf))
+        for i, a in enumerate(fields):
+            for j, b in enumerate(fields):
+                if j >= i and (a + b) in cls_unl:
+                    rmat[:, i, j] = cls_unl[a + b][:lmax + 1]
+                    rmat[:, j, i] = rmat[:, i, j]
+        t, v = np.linalg.eigh(rmat)
+        assert np.all(t >= -1e-14 * np.max(np.abs(t))), 'spectra not positive semi-definite'
+        t = np.maximum(t, 0.)
+        self.rmat = np.einsum('lij,lj,lkj->lik', v, np.sqrt(t), v)
+        self._cl_hash = {k: utils.clhash(cls_unl[k]) for k in cls_unl.keys()}
+        self.lmax = lmax
+        self.lib_pha = lib_pha
+        self.fields = fields
+
+    def hashdict(self):
+        ret = dict(self._cl_hash)
+        ret['phas'] = self.lib_pha.hashdict()
+        return ret
+
+    def _get_sim_alm(self, idx, idf):
+        ret = hp.almxfl(self.lib_pha.get_sim(idx, idf=0), self.rmat[:, idf, 0])
+        for i in range(1, len(self.fields)):
+            ret += hp.almxfl(self.lib_pha.get_sim(idx, idf=i), self.rmat[:, idf, i])
+        return ret
+
+    def get_sim_alm(self, idx, field):
+        assert field in self.fields, self.fields
+        return self._get_sim_alm(idx, self.fields.index(field))
+
+    def get_sim_tlm(self, idx):
+        return self.get_sim_alm(idx, 't')
+
+    def get_sim_elm(self, idx):
+        return self.get_sim_alm(idx, 'e')
+
+    def get_sim_blm(self, idx):
+        return self.get_sim_alm(idx, 'b')

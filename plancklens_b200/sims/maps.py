@@ -1,0 +1,80 @@
+"""CMB + noise map simulations (reference: plancklens/sims/maps.py:10-173); the synthesis runs on the GPU."""
+import numpy as np
+
+from .. import hp
+from ..utils import clhash
+from . import phas
+
+
+class cmb_maps(object):
+    """Lensed-CMB alm library x transfer function -> maps (reference: maps.py:10-91)."""
+
+    def __init__(self, sims_cmb_len, cl_transf, nside=2048, cl_transf_P=None, lib_dir=None):
+        self.sims_cmb_len = sims_cmb_len
+        self.cl_transf_T = cl_transf
+        self.cl_transf_P = np.copy(cl_transf) if cl_transf_P is None else cl_transf_P
+        self.nside = nside
+
+    def hashdict(self):
+        ret = {'sims_cmb_len': self.sims_cmb_len.hashdict(), 'nside': self.nside, 'cl_transf': clhash(self.cl_transf_T)}
+        if not np.all(self.cl_transf_P == self.cl_transf_T):
+            ret['cl_transf_P'] = clhash(self.cl_transf_P)
+        return ret
+
+    def get_sim_tmap(self, idx):
+        tlm = hp.almxfl(self.sims_cmb_len.get_sim_tlm(idx), self.cl_transf_T)
+        return hp.alm2map(tlm, self.nside) + self.get_sim_tnoise(idx)
+
+    def get_sim_pmap(self, idx):
+        elm = hp.almxfl(self.sims_cmb_len.get_sim_elm(idx), self.cl_transf_P)
+        blm = hp.almxfl(self.sims_cmb_len.get_sim_blm(idx), self.cl_transf_P)
+        Q, U = hp.alm2map_spin([elm, blm], self.nside, 2, hp.Alm.getlmax(elm.size))
+        return Q + self.get_sim_qnoise(idx), U + self.get_sim_unoise(idx)
+
+    def get_sim_tnoise(self, idx):
+        assert 0, 'subclass this'
+
+    def get_sim_qnoise(self, idx):
+        assert 0, 'subclass this'
+
+    def get_sim_unoise(self, idx):
+        assert 0, 'subclass this'
+
+
+class cmb_maps_noisefree(cmb_maps):
+    def get_sim_tnoise(self, idx):
+        return np.zeros(hp.nside2npix(self.nside))
+
+    get_sim_qnoise = get_sim_tnoise
+    get_sim_unoise = get_sim_tnoise
+
+
+class cmb_maps_nlev(cmb_maps):
+    """Homogeneous white noise of nlev_t / nlev_p uK-arcmin on top (reference: maps.py:116-173)."""
+
+    def __init__(self, sims_cmb_len, cl_transf, nlev_t, nlev_p, nside, lib_dir=None, pix_lib_phas=None):
+        if pix_lib_phas is None:
+            assert lib_dir is not None
+            pix_lib_phas = phas.pix_lib_phas(lib_dir, 3, (hp.nside2npix(nside),))
+        assert pix_lib_phas.shape == (hp.nside2npix(nside),), (pix_lib_phas.shape, (hp.nside2npix(nside),))
+        self.pix_lib_phas = pix_lib_phas
+        self.nlev_t = nlev_t
+        self.nlev_p = nlev_p
+        super(cmb_maps_nlev, self).__init__(sims_cmb_len, cl_transf, nside=nside, lib_dir=lib_dir)
+
+    def hashdict(self):
+        ret = super(cmb_maps_nlev, self).hashdict()
+        ret.update({'nlev_t': self.nlev_t, 'nlev_p': self.nlev_p, 'pixphas': self.pix_lib_phas.hashdict()})
+        return ret
+
+    def _vamin(self):
+        return np.sqrt(hp.nside2pixarea(self.nside, degrees=True)) * 60
+
+    def get_sim_tnoise(self, idx):
+        return self.nlev_t / self._vamin() * self.pix_lib_phas.get_sim(idx, idf=0)
+
+    def get_sim_qnoise(self, idx):
+        return self.nlev_p / self._vamin() * self.pix_lib_phas.get_sim(idx, idf=1)
+
+    def get_sim_unoise(self, idx):
+        return self.nlev_p / self._vamin() * self.pix_lib_phas.get_sim(idx, idf=2)

@@ -1,0 +1,90 @@
+"""Seeded small inputs shared by tests/golden/make_golden.py (reference side) and the parity tests (CUDA side)."""
+import numpy as np
+
+
+def alm_size(lmax):
+    return (lmax + 1) * (lmax + 2) // 2
+
+
+def alm_ls(lmax):
+    return np.concatenate([np.arange(m, lmax + 1) for m in range(lmax + 1)])
+
+
+def rand_alm(rng, lmax, lmin=0):
+    n = alm_size(lmax)
+    a = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    a[:lmax + 1] = a[:lmax + 1].real
+    a[alm_ls(lmax) < lmin] = 0
+    return a
+
+
+def toy_cls(lmax):
+    l = np.arange(lmax + 1, dtype=float)
+    lp = np.maximum(l, 2.0)
+    tt = 1e3 / (lp * (lp + 1)) * np.exp(-(lp / 60.0) ** 2) + 1e-4
+    ee = 30.0 / (lp * (lp + 1)) * np.exp(-(lp / 70.0) ** 2) + 1e-5
+    bb = 0.1 * ee
+    te = 0.4 * np.sqrt(tt * ee) * np.cos(lp / 9.0)
+    for c in (tt, ee, bb, te):
+        c[:2] = 0.0
+    return {'tt': tt, 'ee': ee, 'bb': bb, 'te': te}
+
+
+def pix_z(nside):
+    """z = cos(theta) of every RING pixel (ring geometry only)."""
+    N = nside
+    z = np.empty(12 * N * N)
+    p = 0
+    for i in range(1, 4 * N):
+        if i < N:
+            n, zz = 4 * i, 1 - i * i / (3.0 * N * N)
+        elif i <= 3 * N:
+            n, zz = 4 * N, (2 * N - i) * 2.0 / (3.0 * N)
+        else:
+            ip = 4 * N - i
+            n, zz = 4 * ip, -(1 - ip * ip / (3.0 * N * N))
+        z[p:p + n] = zz
+        p += n
+    return z
+
+
+def cg_case(nside=32, lmax=64, seed=1234):
+    rng = np.random.default_rng(seed)
+    npix = 12 * nside ** 2
+    z = pix_z(nside)
+    mask = (np.abs(z) > np.sin(np.deg2rad(15.0))).astype(float)
+    holes = rng.choice(npix, 40, replace=False)
+    mask[holes] = 0.0
+    cls = toy_cls(lmax)
+    transf = np.exp(-0.5 * np.arange(lmax + 1) * (np.arange(lmax + 1) + 1.0) * (0.03 ** 2))
+    pixarea = 4 * np.pi / npix
+    # pixel noise chosen so that S/N crosses one near l ~ 40 (a few tens of CG iterations, as in production)
+    ninv_t = mask * (1.0 + 0.5 * z ** 2) / 300.0 * (pixarea / (4 * np.pi / (12 * 32 ** 2)))
+    ninv_p = mask * (1.0 + 0.3 * z ** 2) / 10.0
+    return {'nside': nside, 'lmax': lmax, 'cls': cls, 'transf': transf,
+            'ninv_t': [ninv_t], 'ninv_p1': [[ninv_p]],
+            'ninv_p3': [[ninv_p], [0.2 * ninv_p * z], [ninv_p * (1.0 + 0.1 * z)]],
+            'tmap': rng.standard_normal(npix) * 3.0, 'qmap': rng.standard_normal(npix), 'umap': rng.standard_normal(npix),
+            'x_t': rand_alm(rng, lmax), 'x_e': rand_alm(rng, lmax, 2), 'x_b': rand_alm(rng, lmax, 2)}
+
+
+def chain_descr_t(cd_solve):
+    """Two-level version of the reference's default T chain (filt_cinv.py:113-116), sized for nside 32."""
+    return [[1, ["split(dense, 8, diag_cl)"], 32, 16, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+            [0, ["split(stage(1), 32, diag_cl)"], 64, 32, np.inf, 1.0e-6, cd_solve.tr_cg, cd_solve.cache_mem()]]
+
+
+def chain_descr_p(cd_solve):
+    return [[1, ["split(dense, 8, diag_cl)"], 32, 16, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+            [0, ["split(stage(1), 32, diag_cl)"], 64, 32, np.inf, 1.0e-6, cd_solve.tr_cg, cd_solve.cache_mem()]]
+
+
+def qe_case(nside=32, lmax=48, lmax_qlm=64, seed=4321):
+    rng = np.random.default_rng(seed)
+    cls = toy_cls(lmax)
+    q = {'nside': nside, 'lmax': lmax, 'lmax_qlm': lmax_qlm, 'cls': cls}
+    for tag in ('1', '2'):
+        q['tlm' + tag] = rand_alm(rng, lmax, 2) * 1e-2
+        q['elm' + tag] = rand_alm(rng, lmax, 2) * 1e-1
+        q['blm' + tag] = rand_alm(rng, lmax, 2) * 1e-1
+    return q

@@ -1,0 +1,142 @@
+"""CPU: host-side helpers of the product (no GPU, no compute calls into the library)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+from helpers import alm_size, rand_alm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """The C-ABI library loads on a GPU-less host and exports every function include/plk.h declares."""
+    from plancklens_b200 import _build, _lib
+    if not os.path.exists(_build.SO):
+        _build.build()
+    lib = ctypes.CDLL(_build.SO)
+    hdr = open(os.path.join(ROOT, 'include', 'plk.h')).read()
+    declared = set(re.findall(r'\b(plk_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.plk_version() == 100
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from plancklens_b200 import _lib, sht
+    with pytest.raises(_lib.PlkError):
+        sht.Plan(8, 16)
+    from plancklens_b200 import hp
+    with pytest.raises(_lib.PlkError):
+        hp.alm2map(np.zeros(alm_size(4), dtype=complex), 2)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (tier framing, section 3)."""
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, 'plancklens_b200')):
+        for f in fs:
+            if f.endswith('.py'):
+                src = open(os.path.join(dp, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle\b', src, re.M):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_hp_helpers_against_oracle_geometry():
+    from oracle import ref_geom as rg
+    from oracle.healpy_shim import healpy as shim
+    from plancklens_b200 import hp
+    rng = np.random.default_rng(0)
+    lmax = 37
+    a, b = rand_alm(rng, lmax), rand_alm(rng, lmax)
+    fl = rng.standard_normal(20)       # shorter than lmax+1: higher l must be zeroed
+    assert np.array_equal(hp.almxfl(a, fl), shim.almxfl(a, fl))
+    assert np.allclose(hp.alm2cl(a, b), shim.alm2cl(a, b), rtol=1e-14, atol=0)
+    assert hp.Alm.getsize(lmax) == a.size and hp.Alm.getlmax(a.size) == lmax
+    assert hp.Alm.getidx(lmax, 5, 3) == rg.alm_getidx(lmax, 5, 3)
+    for nside in (1, 2, 8, 64):
+        idx = np.arange(12 * nside * nside)
+        assert np.array_equal(hp.ring2nest(nside, idx), rg.ring2nest(nside, idx))
+        assert np.array_equal(np.sort(hp.ring2nest(nside, idx)), idx)
+    m = rng.standard_normal(12 * 16 * 16)
+    assert np.allclose(hp.ud_grade(m, 4, power=-2), rg.ud_grade_sum(m, 4))
+    assert abs(hp.ud_grade(m, 4, power=-2).sum() - m.sum()) < 1e-10
+
+
+def test_ring2nest_children_are_neighbours():
+    """Independent check of the RING->NEST map: the four children of a NEST parent lie within ~1 pixel of each other."""
+    from oracle import ref_geom as rg
+    from plancklens_b200 import hp
+    nside = 16
+    theta, phi = rg.pix2ang(nside)
+    vec = np.stack([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)], 1)
+    nest = hp.ring2nest(nside, np.arange(12 * nside ** 2))
+    order = np.argsort(nest)
+    v = vec[order].reshape(-1, 4, 3)
+    c = v.mean(1, keepdims=True)
+    c /= np.linalg.norm(c, axis=2, keepdims=True)
+    ang = np.arccos(np.clip((v * c).sum(2), -1, 1))
+    assert ang.max() < 1.2 * np.sqrt(4 * np.pi / (12 * nside ** 2))
+
+
+def test_utils_and_containers():
+    from plancklens_b200 import utils
+    from plancklens_b200.qcinv import util_alm
+    rng = np.random.default_rng(1)
+    a = rand_alm(rng, 20)
+    lo = utils.alm_copy(a, lmax=9)
+    assert lo.size == alm_size(9)
+    hi = rand_alm(rng, 20)
+    sp = util_alm.alm_splice(lo, hi, 7)
+    ls = gi.alm_ls(20)
+    assert np.array_equal(sp[ls > 7], hi[ls > 7])
+    assert np.array_equal(sp[ls <= 7], a[ls <= 7])
+    e = util_alm.eblm([a.copy(), hi.copy()])
+    f = e + e * 2.0
+    assert np.allclose(f.elm, 3 * a) and np.allclose(f.blm, 3 * hi)
+    e -= e
+    assert e.is_zero()
+    assert np.array_equal(utils.cli(np.array([0., 2., -1.])), np.array([0., 0.5, 0.]))
+    cls = utils.camb_clfile(os.path.join(ROOT, 'plancklens_b200', 'data', 'cls', 'FFP10_wdipole_lensedCls.dat'), lmax=100)
+    assert set(cls) == {'tt', 'ee', 'bb', 'te'} and cls['tt'].size == 101 and cls['tt'][0] == 0 and cls['tt'][2] > 0
+
+
+def test_cd_solve_on_numpy_vectors():
+    """The solver is generic over vector types: plain numpy SPD system, exact in n steps."""
+    from plancklens_b200.qcinv import cd_monitors, cd_solve
+    rng = np.random.default_rng(2)
+    n = 30
+    A = rng.standard_normal((n, n))
+    A = A @ A.T + n * np.eye(n)
+    b = rng.standard_normal(n)
+    x = np.zeros(n)
+    dot = lambda u, v: float(np.dot(u, v))
+    mon = cd_monitors.monitor_basic(dot, iter_max=200, eps_min=1e-12, logger=None)
+    it = cd_solve.cd_solve(x, b, lambda v: A @ v, [lambda r: r / np.diag(A)], dot, mon, cd_solve.tr_cg, cd_solve.cache_mem())
+    assert it <= n + 2
+    assert np.allclose(A @ x, b, atol=1e-9)
+
+
+def test_multigrid_descr_parser_rejects_unknown():
+    from plancklens_b200.qcinv import multigrid
+    with pytest.raises(AssertionError):
+        multigrid.parse_pre_op_descr("bogus(1)", opfilt=None, s_cls=None, n_inv_filt=None, stages={}, lmax=8, nside=4, chain=None)
+
+
+def test_sim_phases_follow_reference_recipe():
+    from plancklens_b200.sims import phas
+    lib = phas.lib_phas(None, 3, 30)
+    a = lib.get_sim(4, idf=1)
+    assert np.all(a[:31].imag == 0) and np.any(a[31:].imag != 0)
+    assert np.array_equal(a, lib.get_sim(4, idf=1)) and not np.array_equal(a, lib.get_sim(5, idf=1))
+    big = phas.lib_phas(None, 1, 300).get_sim(0, idf=0)
+    assert abs(np.mean(np.abs(big[301:]) ** 2) - 1.0) < 0.02 and abs(np.var(big[:301].real) - 1.0) < 0.2

@@ -1,0 +1,74 @@
+"""CPU: the C oracle against the brute-force definition, closed forms and adjointness."""
+import numpy as np
+import pytest
+
+from helpers import alm_dot, alm_size, rand_alm, rel_l2
+
+
+@pytest.mark.parametrize("spin", [0, 1, 2, 3])
+def test_oracle_matches_bruteforce(oracle_sht, spin):
+    from oracle import bruteforce as bf
+    nside, lmax = 4, 11
+    rng = np.random.default_rng(spin)
+    npix = 12 * nside ** 2
+    if spin == 0:
+        a = rand_alm(rng, lmax)
+        assert rel_l2(oracle_sht.alm2map(a, nside, lmax=lmax), bf.alm2map_spin([a], nside, 0, lmax)[0]) < 1e-13
+        m = rng.standard_normal(npix)
+        assert rel_l2(oracle_sht.map2alm(m, lmax=lmax), bf.map2alm_spin([m], 0, lmax)[0]) < 1e-13
+    else:
+        g, c = rand_alm(rng, lmax, spin), rand_alm(rng, lmax, spin)
+        ref = bf.alm2map_spin([g, c], nside, spin, lmax)
+        got = oracle_sht.alm2map_spin([g, c], nside, spin, lmax)
+        assert rel_l2(got[0], ref[0]) < 1e-13 and rel_l2(got[1], ref[1]) < 1e-13
+        m = [rng.standard_normal(npix), rng.standard_normal(npix)]
+        ref = bf.map2alm_spin(m, spin, lmax)
+        got = oracle_sht.map2alm_spin(m, spin, lmax=lmax)
+        assert rel_l2(got[0], ref[0]) < 1e-13 and rel_l2(got[1], ref[1]) < 1e-13
+
+
+def test_spin_harmonic_closed_forms():
+    """1Y_11 = -sqrt(3/16pi)(1 - cos) and 2Y_22 = 1/8 sqrt(5/pi)(1 - cos)^2."""
+    from oracle.bruteforce import slam
+    th = np.linspace(0.05, 3.0, 17)
+    assert np.max(np.abs(slam(1, 1, 1, th) + np.sqrt(3 / (16 * np.pi)) * (1 - np.cos(th)))) < 1e-15
+    assert np.max(np.abs(slam(2, 2, 2, th) - np.sqrt(5 / np.pi) / 8 * (1 - np.cos(th)) ** 2)) < 1e-15
+
+
+@pytest.mark.parametrize("spin", [0, 2])
+def test_oracle_adjointness(oracle_sht, spin):
+    nside, lmax = 32, 64
+    rng = np.random.default_rng(5)
+    npix = 12 * nside ** 2
+    w = 4 * np.pi / npix
+    if spin == 0:
+        a, m = rand_alm(rng, lmax), rng.standard_normal(npix)
+        lhs = alm_dot(oracle_sht.map2alm(m, lmax=lmax), a, lmax)
+        rhs = w * np.dot(m, oracle_sht.alm2map(a, nside, lmax=lmax))
+    else:
+        g, c = rand_alm(rng, lmax, spin), rand_alm(rng, lmax, spin)
+        m = [rng.standard_normal(npix), rng.standard_normal(npix)]
+        gm, cm = oracle_sht.map2alm_spin(m, spin, lmax=lmax)
+        y = oracle_sht.alm2map_spin([g, c], nside, spin, lmax)
+        lhs = alm_dot(gm, g, lmax) + alm_dot(cm, c, lmax)
+        rhs = w * (np.dot(m[0], y[0]) + np.dot(m[1], y[1]))
+    assert abs(lhs - rhs) < 1e-12 * abs(lhs)
+
+
+def test_oracle_deep_underflow_against_mpmath(oracle_sht):
+    """lambda_lm at l = m = 300 on a polar ring (value ~1e-470 at the pole side, ~1 at the equator)."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    nside, lmax, l, m = 128, 300, 300, 300
+    a = np.zeros(alm_size(lmax), dtype=complex)
+    a[m * (2 * lmax + 1 - m) // 2 + l] = 1.0
+    X, _ = oracle_sht.legendre_synth(nside, 0, lmax, lmax, a)
+    for r in (60, 127, 255):
+        i = r + 1
+        z = mp.mpf(1) - mp.mpf(i * i) / (3 * nside * nside) if i < nside else mp.mpf(2 * (2 * nside - i)) / (3 * nside)
+        s = mp.sqrt(1 - z * z)
+        v = mp.sqrt(1 / (4 * mp.pi))
+        for k in range(1, m + 1):
+            v *= -mp.sqrt(mp.mpf(2 * k + 1) / (2 * k)) * s
+        if abs(v) > mp.mpf(10) ** -250:
+            assert abs(X[r, m].real - float(v)) < 1e-13 * abs(float(v))
