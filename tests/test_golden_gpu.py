@@ -1,0 +1,190 @@
+"""GPU parity of the product's reference-API layer (qcinv operators, CG chains, qest) against golden vectors
+produced by the unmodified reference (tests/golden/make_golden.py) and against the CPU oracle.
+
+Tolerances: operators 1e-10 relative L2 (north_star), CG: identical top-level iteration count and the same eps
+trace, solution within 1e-7 (the stop test is eps <= 1e-6)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden.npz')
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope='module')
+def mods():
+    from plancklens_b200.qcinv import cd_solve, multigrid, opfilt_pp, opfilt_tt, util_alm
+    return dict(cd_solve=cd_solve, multigrid=multigrid, opfilt_pp=opfilt_pp, opfilt_tt=opfilt_tt, util_alm=util_alm)
+
+
+def test_opfilt_tt_operators(gold, mods):
+    ot, ua = mods['opfilt_tt'], mods['util_alm']
+    c = gi.cg_case()
+    nf = ot.alm_filter_ninv(c['ninv_t'], c['transf'], marge_monopole=True, marge_dipole=True)
+    x = ua.dalm.from_numpy(c['x_t'])
+    fwd = ot.fwd_op(c['cls'], nf)
+    y = fwd(x)
+    assert rel_l2(y.numpy(), gold['tt_fwd']) < 1e-10
+    assert rel_l2(x.numpy(), c['x_t']) == 0.0          # fwd_op must not modify its argument
+    assert rel_l2(ot.calc_prep(c['tmap'], c['cls'], nf).numpy(), gold['tt_prep']) < 1e-10
+    assert rel_l2(ot.pre_op_diag(c['cls'], nf)(x).numpy(), gold['tt_prediag']) < 1e-12
+    d = ot.dot_op()(x, y)
+    assert abs(d - gold['tt_dot'][0]) < 1e-10 * abs(gold['tt_dot'][0])
+    a = c['x_t'].copy()
+    nf.apply_alm(a)                                     # numpy in-place form of the reference
+    assert rel_l2(a, gold['tt_apply_alm']) < 1e-10
+    z = ua.dalm.zeros(c['lmax'])
+    assert fwd(z) is z                                  # zero short-circuit (opfilt_tt.py:68)
+
+
+def test_opfilt_pp_operators(gold, mods):
+    op, ua = mods['opfilt_pp'], mods['util_alm']
+    c = gi.cg_case()
+    for tag, ninv in (('pp', c['ninv_p1']), ('pp3', c['ninv_p3'])):
+        nf = op.alm_filter_ninv(ninv, c['transf'])
+        x = ua.eblm([ua.dalm.from_numpy(c['x_e']), ua.dalm.from_numpy(c['x_b'])])
+        fwd = op.fwd_op(c['cls'], nf)
+        y = fwd(x)
+        e, b = y.numpy()
+        assert rel_l2(e, gold[tag + '_fwd_e']) < 1e-10 and rel_l2(b, gold[tag + '_fwd_b']) < 1e-10
+        pe, pb = op.calc_prep([c['qmap'], c['umap']], c['cls'], nf).numpy()
+        assert rel_l2(pe, gold[tag + '_prep_e']) < 1e-10 and rel_l2(pb, gold[tag + '_prep_b']) < 1e-10
+        d = op.dot_op()(x, y)
+        assert abs(d - gold[tag + '_dot'][0]) < 1e-10 * abs(gold[tag + '_dot'][0])
+        if tag == 'pp':
+            e, b = op.pre_op_diag(c['cls'], nf)(x).numpy()
+            assert rel_l2(e, gold['pp_prediag_e']) < 1e-12 and rel_l2(b, gold['pp_prediag_b']) < 1e-12
+
+
+def _solve(mods, opfilt, descr, cls, nf, sol, data):
+    chain = mods['multigrid'].multigrid_chain(opfilt, descr, cls, nf)
+    chain.solve(sol, data)
+    return chain
+
+
+def test_cg_tt_same_iterations_as_reference(gold, mods):
+    """Two-level multigrid chain with a dense coarse preconditioner: same iteration count, same eps trace."""
+    c = gi.cg_case()
+    nf = mods['opfilt_tt'].alm_filter_ninv(c['ninv_t'], c['transf'], marge_monopole=True, marge_dipole=True)
+    sol = np.zeros(gold['tt_soltn'].size, dtype=complex)
+    chain = _solve(mods, mods['opfilt_tt'], gi.chain_descr_t(mods['cd_solve']), c['cls'], nf, sol, c['tmap'])
+    ref = gold['tt_trace']
+    assert chain.niter == int(ref[-1][1])
+    eps = np.array([t[1] for t in chain.last_monitor.trace])
+    assert np.allclose(eps, ref[:, 2], rtol=1e-5)
+    assert rel_l2(sol, gold['tt_soltn']) < 1e-7
+
+
+def test_cg_tt_diag_only(gold, mods):
+    c = gi.cg_case()
+    cd = mods['cd_solve']
+    nf = mods['opfilt_tt'].alm_filter_ninv(c['ninv_t'], c['transf'], marge_monopole=True, marge_dipole=True)
+    descr = [[0, ["diag_cl"], c['lmax'], c['nside'], np.inf, 1.0e-6, cd.tr_cg, cd.cache_mem()]]
+    sol = np.zeros(gold['tt_diag_soltn'].size, dtype=complex)
+    chain = _solve(mods, mods['opfilt_tt'], descr, c['cls'], nf, sol, c['tmap'])
+    ref = gold['tt_diag_trace']
+    assert chain.niter == int(ref[-1][1])
+    assert np.allclose(np.array([t[1] for t in chain.last_monitor.trace]), ref[:, 2], rtol=1e-5)
+    assert rel_l2(sol, gold['tt_diag_soltn']) < 1e-7
+
+
+def test_cg_pp_same_iterations_as_reference(gold, mods):
+    c = gi.cg_case()
+    ua = mods['util_alm']
+    nf = mods['opfilt_pp'].alm_filter_ninv(c['ninv_p1'], c['transf'])
+    n = gold['pp_soltn_e'].size
+    sol = ua.eblm([np.zeros(n, dtype=complex), np.zeros(n, dtype=complex)])
+    chain = _solve(mods, mods['opfilt_pp'], gi.chain_descr_p(mods['cd_solve']), c['cls'], nf, sol, [c['qmap'], c['umap']])
+    ref = gold['pp_trace']
+    assert chain.niter == int(ref[-1][1])
+    assert np.allclose(np.array([t[1] for t in chain.last_monitor.trace]), ref[:, 2], rtol=1e-5)
+    assert rel_l2(sol.elm, gold['pp_soltn_e']) < 1e-7 and rel_l2(sol.blm, gold['pp_soltn_b']) < 1e-7
+
+
+class _mem_ivfs:
+    lib_dir = None
+
+    def __init__(self, q, tag):
+        self.q, self.tag = q, tag
+
+    def hashdict(self):
+        return {'tag': self.tag}
+
+    def get_fmask(self):
+        return np.ones(12 * self.q['nside'] ** 2)
+
+    def get_sim_tlm(self, idx): return self.q['tlm' + self.tag].copy()
+    def get_sim_elm(self, idx): return self.q['elm' + self.tag].copy()
+    def get_sim_blm(self, idx): return self.q['blm' + self.tag].copy()
+
+    def get_sim_tmliklm(self, idx):
+        from plancklens_b200 import hp
+        return hp.almxfl(self.get_sim_tlm(idx), self.q['cls']['tt'])
+
+    def get_sim_emliklm(self, idx):
+        from plancklens_b200 import hp
+        return hp.almxfl(self.get_sim_elm(idx), self.q['cls']['ee'])
+
+    def get_sim_bmliklm(self, idx):
+        from plancklens_b200 import hp
+        return hp.almxfl(self.get_sim_blm(idx), self.q['cls']['bb'])
+
+
+@pytest.mark.parametrize("merge", [True, False])
+def test_qest_library_matches_reference(gold, merge):
+    """qest.library_sepTP.get_sim_qlm for 'ptt', 'p_p', 'p' (same-leg and two-leg symmetrised) vs the reference."""
+    from plancklens_b200 import qest
+    q = gi.qe_case()
+    with tempfile.TemporaryDirectory() as tmp:
+        iv1, iv2 = _mem_ivfs(q, '1'), _mem_ivfs(q, '2')
+        dd = qest.library_sepTP(os.path.join(tmp, 'dd'), iv1, iv1, q['cls']['te'], q['nside'], lmax_qlm=q['lmax_qlm'])
+        ds = qest.library_sepTP(os.path.join(tmp, 'ds'), iv1, iv2, q['cls']['te'], q['nside'], lmax_qlm=q['lmax_qlm'])
+        dd.merge_analysis = ds.merge_analysis = merge
+        for k in ['ptt', 'p_p', 'p']:
+            assert rel_l2(dd.get_sim_qlm(k, 0), gold['qe_dd_' + k]) < 1e-10
+            xk = 'x' + k[1:]
+            ref = gold['qe_dd_' + xk]
+            got = dd.get_sim_qlm(xk, 0)
+            assert np.linalg.norm(got - ref) < 1e-10 * max(np.linalg.norm(ref), np.linalg.norm(gold['qe_dd_' + k]))
+            assert rel_l2(ds.get_sim_qlm(k, 0), gold['qe_ds_' + k]) < 1e-10
+        # qlm auto-spectra within 1e-8 (north_star)
+        from plancklens_b200 import hp
+        for k in ['ptt', 'p_p', 'p']:
+            cl, ref = hp.alm2cl(dd.get_sim_qlm(k, 0)), hp.alm2cl(gold['qe_dd_' + k])
+            assert np.max(np.abs(cl[2:] - ref[2:]) / ref[2:]) < 1e-8
+        # mean field over two "sims" = plain average (reference: qest.py:239-243)
+        mf = dd.get_sim_qlm_mf('ptt', np.array([0, 1]))
+        assert rel_l2(mf, gold['qe_dd_ptt']) < 1e-10    # both indices map to the same in-memory sim
+
+
+def test_shts_seam_signatures(oracle_sht):
+    """plancklens_b200.shts exposes the four functions of the reference seam with its signatures."""
+    from plancklens_b200 import shts, utils_spin
+    rng = np.random.default_rng(0)
+    nside, lmax = 16, 32
+    from helpers import rand_alm
+    a = rand_alm(rng, lmax)
+    m = shts.alm2map(a, nside)
+    assert rel_l2(m, oracle_sht.alm2map(a, nside, lmax=lmax)) < 1e-11
+    assert rel_l2(shts.map2alm(m, lmax, iter=0), oracle_sht.map2alm(m, lmax=lmax)) < 1e-11
+    g, c = rand_alm(rng, lmax, 2), rand_alm(rng, lmax, 2)
+    q, u = shts.alm2map_spin([g, c], nside, 2, lmax)
+    rq, ru = oracle_sht.alm2map_spin([g, c], nside, 2, lmax)
+    assert rel_l2(q, rq) < 1e-11 and rel_l2(u, ru) < 1e-11
+    e, b = shts.map2alm_spin([q, u], 2, lmax)
+    re, rb = oracle_sht.map2alm_spin([rq, ru], 2, lmax=lmax)
+    assert rel_l2(e, re) < 1e-11 and rel_l2(b, rb) < 1e-11
+    t0, zero = utils_spin.alm2map_spin([a, a * 0], nside, 0, lmax)       # spin 0: G^0 = -T
+    assert rel_l2(t0, -m) < 1e-13 and zero == 0.
+    with pytest.raises(TypeError):
+        shts.alm2map(a[:-1], nside)
