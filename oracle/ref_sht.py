@@ -119,18 +119,25 @@ def phase2map(nside, X):
     mmax = X.shape[1] - 1
     out = np.empty(12 * nside * nside)
     m = np.arange(mmax + 1)
-    # group rings of equal length (equatorial belt is one batch)
     for n in np.unique(g.nphi):
         rows = np.where(g.nphi == n)[0]
         Xs = X[rows] * np.exp(1j * m[None, :] * g.phi0[rows][:, None])
-        d = np.zeros((rows.size, n), dtype=complex)       # full-length spectrum, Hermitian-completed
-        k = m % n
-        np.add.at(d, (slice(None), k), Xs)
-        kc = (-m[1:]) % n
-        np.add.at(d, (slice(None), kc), np.conj(Xs[:, 1:]))
-        x = np.fft.ifft(d, axis=1) * n
+        if 2 * mmax < n:
+            # no aliasing: Hermitian half spectrum straight into a complex-to-real FFT
+            h = np.zeros((rows.size, n // 2 + 1), dtype=complex)
+            h[:, :mmax + 1] = Xs
+            x = np.fft.irfft(h, n=n, axis=1) * n
+        else:
+            full = np.zeros((rows.size, n), dtype=complex)       # spectrum of the m >= 0 part, wrapped mod n
+            for j0 in range(0, mmax + 1, n):
+                blk = Xs[:, j0:j0 + n]
+                full[:, :blk.shape[1]] += blk
+            d = full.copy()                                        # add the conjugate (m < 0) images
+            d[:, 0] += np.conj(full[:, 0]) - np.conj(Xs[:, 0])    # m = 0 itself has no mirror term
+            d[:, 1:] += np.conj(full[:, :0:-1])
+            x = (np.fft.ifft(d, axis=1) * n).real
         for a, r in enumerate(rows):
-            out[g.start[r]:g.start[r] + n] = x[a].real
+            out[g.start[r]:g.start[r] + n] = x[a]
     return out
 
 
@@ -142,8 +149,13 @@ def map2phase(nside, mp, mmax):
     for n in np.unique(g.nphi):
         rows = np.where(g.nphi == n)[0]
         x = np.stack([mp[g.start[r]:g.start[r] + n] for r in rows])
-        d = np.fft.fft(x, axis=1)
-        X[rows] = d[:, m % n] * np.exp(-1j * m[None, :] * g.phi0[rows][:, None])
+        h = np.fft.rfft(x, axis=1)
+        if mmax <= n // 2:
+            d = h[:, :mmax + 1]
+        else:
+            k = m % n
+            d = np.where((k <= n // 2)[None, :], h[:, np.minimum(k, n // 2)], np.conj(h[:, np.minimum(n - k, n // 2)]))
+        X[rows] = d * np.exp(-1j * m[None, :] * g.phi0[rows][:, None])
     return X
 
 

@@ -43,6 +43,18 @@ def _dfl(fl):
     return torch.from_numpy(np.ascontiguousarray(fl, dtype=np.float64)).cuda()
 
 
+def _combine(lmax, terms):
+    """sum_j fl_j[l] a_j[l,m] on the device (plk_alm_combine_dev)."""
+    import ctypes
+    n = len(terms)
+    out = torch.empty_like(terms[0][0])
+    ins = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in terms])
+    fls = (ctypes.c_void_p * n)(*[t[1].data_ptr() for t in terms])
+    nfl = (ctypes.c_int * n)(*[int(t[1].numel()) for t in terms])
+    sht.check(sht._lib.load().plk_alm_combine_dev(lmax, n, ins, fls, nfl, sht._ptr(out), sht._stream()))
+    return out
+
+
 def _grad_fl(lmax, spin, kind):
     """per-l factors of the gradient legs (reference: qest.py:463, 494-503)."""
     l = np.arange(lmax + 1, dtype=float)
@@ -93,6 +105,15 @@ class qe_device:
 
     def analyse(self, re, im):
         return self.plan_qlm.map2alm_spin(re, im, 1, flg=self.fl_out, flc=self.fl_out)
+
+    def to_host(self, G, C):
+        """device qlm pair -> numpy, through pinned staging buffers"""
+        if not hasattr(self, '_pin'):
+            self._pin = [torch.empty(G.numel(), dtype=torch.complex128, pin_memory=True) for _ in range(2)]
+        self._pin[0].copy_(G, non_blocking=True)
+        self._pin[1].copy_(C, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pin[0].numpy().copy(), self._pin[1].numpy().copy()
 
     def ptt(self, tbar, twf):
         return self.analyse(*self.t_products(tbar, twf))
@@ -237,6 +258,12 @@ class library:
             _write_alm(fname, MF)
         return ut.alm_copy(hp.read_alm(fname), lmax=lmax)
 
+    def eval_qlm(self, k, idx, swapped=False):
+        """Gradient and curl estimate for a fundamental key, computed on the GPU, not cached (numpy out)."""
+        assert k in ['ptt', 'p_p', 'p'], k
+        fun = {'ptt': self._get_sim_Tgclm, 'p_p': self._get_sim_Pgclm, 'p': self._get_sim_MVgclm}[k]
+        return fun(idx, k, swapped=swapped)
+
     # ---- GPU evaluation
     def _engine(self, lmax_ivf):
         if self._qe is None or self._qe.lmax_ivf != lmax_ivf:
@@ -271,12 +298,16 @@ class library:
         assert k == 'p'
         f1, f2 = self._legs(idx, k, swapped)
         tbar, ebar, bbar = f1.ivfs.get_sim_tlm(idx), f1.ivfs.get_sim_elm(idx), f1.ivfs.get_sim_blm(idx)
-        twf = f2.wf_tlm(idx, 'p')
-        ewf, bwf = f2.wf_eblm(idx, 'p')
         qe = self._engine(hp.Alm.getlmax(tbar.size))
-        G, C = qe.p(sht.dev_alm(tbar), sht.dev_alm(ebar), sht.dev_alm(bbar), sht.dev_alm(twf), sht.dev_alm(ewf),
-                    sht.dev_alm(bwf), merge_analysis=self.merge_analysis)
-        return G.cpu().numpy(), C.cpu().numpy()
+        dt, de, db = sht.dev_alm(tbar), sht.dev_alm(ebar), sht.dev_alm(bbar)
+        wf = f2.wf_device(idx, 'p', (dt, de, db) if f2 is f1 or f2.ivfs is f1.ivfs else None)
+        if wf is None:
+            twf = sht.dev_alm(f2.wf_tlm(idx, 'p'))
+            ewf, bwf = [sht.dev_alm(a) for a in f2.wf_eblm(idx, 'p')]
+        else:
+            twf, ewf, bwf = wf
+        G, C = qe.p(dt, de, db, twf, ewf, bwf, merge_analysis=self.merge_analysis)
+        return qe.to_host(G, C)
 
     def _symmetrised(self, fun, idx, k):
         G, C = fun(idx, k)
@@ -318,6 +349,11 @@ class lib_filt2map(object):
 
     def wf_eblm(self, idx, k=None):
         return self.ivfs.get_sim_emliklm(idx), self.ivfs.get_sim_bmliklm(idx)
+
+    def wf_device(self, idx, k, dev_bars=None):
+        """Wiener legs built on the GPU from the inverse-variance filtered alms, when the filtering library exposes
+        its weights as `cl` (every `library_sepTP` does); None otherwise (host path through get_sim_*mliklm)."""
+        return None
 
     def get_gtmap(self, idx, k=None, xfilt=None):
         r"""\sum_{lm} MAP_talm sqrt(l (l + 1)) _1 Ylm(n): spin-1 transform with zero curl (reference: qest.py:453-464)."""
@@ -379,6 +415,27 @@ class lib_filt2map_sepTP(lib_filt2map):
         if k == 'p':
             elm = elm + hp.almxfl(self.ivfs.get_sim_tlm(idx), self.clte)      # qest.py:613-618
         return elm, blm
+
+    def wf_device(self, idx, k, dev_bars=None):
+        cl = getattr(self.ivfs, 'cl', None)
+        if not isinstance(cl, dict) or not all(x in cl for x in ('tt', 'ee', 'bb')) or type(self.ivfs).__name__ in ('library_ftl', 'library_shuffle'):
+            return None
+        if dev_bars is None:
+            dev_bars = [sht.dev_alm(a) for a in (self.ivfs.get_sim_tlm(idx), self.ivfs.get_sim_elm(idx), self.ivfs.get_sim_blm(idx))]
+        dt, de, db = dev_bars
+        if not hasattr(self, '_cl_d'):
+            self._cl_d = {x: _dfl(cl[x]) for x in ('tt', 'ee', 'bb')}
+            self._cl_d['te'] = _dfl(self.clte)
+        c = self._cl_d
+        lmax = sht.alm_lmax(dt.numel())
+        if k == 'p':
+            twf = _combine(lmax, [(dt, c['tt']), (de, c['te'])])       # qest.py:582-588
+            ewf = _combine(lmax, [(de, c['ee']), (dt, c['te'])])       # qest.py:613-618
+        else:
+            twf = sht.almxfl(dt, c['tt'])
+            ewf = sht.almxfl(de, c['ee'])
+        bwf = sht.almxfl(db, c['bb'])
+        return twf, ewf, bwf
 
     def get_tmap(self, idx, joint=False):
         tlm = self.ivfs.get_sim_tmliklm(idx)
