@@ -83,6 +83,9 @@ struct plk_plan {
   DevFFT f{};
   DevRings rings{};
   int fft_smem = 0;
+  struct FftClass { int M, nbatch, offset, count, smem, threads; };
+  std::vector<FftClass> fft_classes;
+  int *fft_list = nullptr;      // ring pairs grouped by FFT size class
   int *fft_order = nullptr;
   int *morder = nullptr;
   std::vector<void *> owned;
@@ -111,6 +114,10 @@ static int ensure(DevBuf &b, size_t bytes) {
 }
 
 static int nextpow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 
 extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
   if (!out) return fail(PLK_EINVAL, "plan pointer is NULL");
@@ -179,14 +186,34 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
     std::iota(mo.begin(), mo.end(), 0);
     rc = upload(p, mo, &di); if (rc) { plk_plan_destroy(p); return rc; } p->morder = di;
   }
-  p->fft_smem = (Mmax + Mmax / 4) * (int)sizeof(cplx);   // work buffer + quarter-wave twiddles
+  // size classes: one launch per distinct FFT size so that every block of a launch needs the same shared memory
+  {
+    std::map<int, std::vector<int>> by_m;
+    for (int ip = 0; ip < hg.npair; ++ip) by_m[M[ip]].push_back(ip);
+    std::vector<int> list;
+    const int nb4_maxm = env_int("PLK_FFT_NB4_MAXM", 1024);
+    for (auto it = by_m.rbegin(); it != by_m.rend(); ++it) {     // largest transforms first
+      plk_plan::FftClass c;
+      c.M = it->first; c.offset = (int)list.size(); c.count = (int)it->second.size();
+      c.nbatch = c.M == 0 ? 0 : (c.M <= nb4_maxm ? 4 : 2);
+      c.smem = c.M == 0 ? 0 : (c.nbatch * c.M + c.M / 4) * (int)sizeof(cplx);
+      c.threads = (c.nbatch * c.M / 16 >= 512) ? 512 : 256;   // one radix-16 butterfly per thread and pass
+      p->fft_smem = std::max(p->fft_smem, c.smem);
+      list.insert(list.end(), it->second.begin(), it->second.end());
+      p->fft_classes.push_back(c);
+    }
+    int *di; int rc = upload(p, list, &di); if (rc) { plk_plan_destroy(p); return rc; } p->fft_list = di;
+  }
   if (p->fft_smem > 227 * 1024) { plk_plan_destroy(p); return fail(PLK_EINVAL, "ring FFT needs %d bytes of shared memory", p->fft_smem); }
   {
     static int attr_smem = 0;   // the attribute is per function, not per plan: only ever raise it
     if (p->fft_smem > attr_smem) {
-      cudaError_t e1 = cudaFuncSetAttribute(ring_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
-      cudaError_t e2 = cudaFuncSetAttribute(ring_anal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
+      cudaError_t e1 = cudaFuncSetAttribute(ring_synth_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
+      cudaError_t e2 = cudaFuncSetAttribute(ring_anal_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
       cudaError_t e3 = cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
+      cudaError_t e4 = cudaFuncSetAttribute(ring_synth_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
+      cudaError_t e5 = cudaFuncSetAttribute(ring_anal_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->fft_smem);
+      if (e4 != cudaSuccess || e5 != cudaSuccess) e1 = e4 != cudaSuccess ? e4 : e5;
       if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { plk_plan_destroy(p); return fail(PLK_ECUDA, "cudaFuncSetAttribute(smem=%d) failed", p->fft_smem); }
       attr_smem = p->fft_smem;
     }
@@ -300,10 +327,6 @@ static size_t leg_smem() {
   if (!SYNTH) s += (size_t)2 * kNCW * kChunk * (SPIN ? 4 : 2) * sizeof(double);
   return s;
 }
-static int env_int(const char *name, int dflt) {
-  const char *v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 static int pick_nr(const plk_plan *p, int nrmax) {
   // enough blocks to cover the SMs a few times over; small grids get fewer pairs per thread
   int nr = nrmax;
@@ -377,16 +400,22 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
 static int ring_synth(plk_plan *p, const cplx *X, double *map, cudaStream_t st, const int *mtop = nullptr) {
   DevFFT f = p->f;
   f.mtop = mtop;
-  ring_synth_kernel<<<p->npair, kFftThreads, p->fft_smem, st>>>(f, X, p->pitch, p->mmax, map);
-  LAUNCHED();
+  for (const auto &c : p->fft_classes) {
+    if (c.threads == 512) ring_synth_kernel<512, 1><<<c.count, 512, c.smem, st>>>(f, p->fft_list + c.offset, c.nbatch, X, p->pitch, p->mmax, map);
+    else ring_synth_kernel<256, 3><<<c.count, 256, c.smem, st>>>(f, p->fft_list + c.offset, c.nbatch, X, p->pitch, p->mmax, map);
+    LAUNCHED();
+  }
   return 0;
 }
 static int ring_anal(plk_plan *p, const double *map, cplx *X, cudaStream_t st, const int *mtop = nullptr) {
   const double w = 4.0 * M_PI / (double)p->npix;
   DevFFT f = p->f;
   f.mtop = mtop;
-  ring_anal_kernel<<<p->npair, kFftThreads, p->fft_smem, st>>>(f, map, X, p->pitch, p->mmax, w);
-  LAUNCHED();
+  for (const auto &c : p->fft_classes) {
+    if (c.threads == 512) ring_anal_kernel<512, 1><<<c.count, 512, c.smem, st>>>(f, p->fft_list + c.offset, c.nbatch, map, X, p->pitch, p->mmax, w);
+    else ring_anal_kernel<256, 3><<<c.count, 256, c.smem, st>>>(f, p->fft_list + c.offset, c.nbatch, map, X, p->pitch, p->mmax, w);
+    LAUNCHED();
+  }
   return 0;
 }
 static int ensure_phase(plk_plan *p, int ncomp) {

@@ -6,10 +6,14 @@
 //   packed   y^{(a)}_t = x_{4t+2a} + i x_{4t+2a+1},  a = 0, 1,
 // where d_k is the length-n Hermitian spectrum obtained by folding (aliasing) all m <= mmax onto the ring's
 // band, including the e^{i m phi0} shift.  The length-q DFT runs entirely in shared memory:
-//   q = 2^j        : in-place radix-4 DIF, output read in bit-reversed order;
+//   q = 2^j        : in-place DIF, output read in bit-reversed order;
 //   otherwise      : Bluestein chirp-z with M = nextpow2(2q-1): DIF forward, pointwise multiply by the
 //                    precomputed kernel spectrum (stored in DIF output order), DIT inverse -- no bit reversal;
 //   q <= kTinyQ    : direct evaluation of the defining sum.
+// FFT passes are radix 16 / 8 / 4 in REGISTERS (a thread loads R strided elements, runs log2 R radix-2 levels,
+// stores back in place), so a 4096-point transform is 3 shared-memory round trips; the element index is XOR
+// swizzled (i ^ ((i >> 4) & 15)) which makes every pass of a radix-16 schedule bank-conflict free.  The 2 or 4
+// DFTs of a ring (pair) run as one batch through the same passes.
 // Analysis uses the same inverse-DFT machinery on conjugated data (DFT(y) = conj(IDFT(conj y))).
 // No cuFFT: 2047 distinct cap-ring lengths per nside would mean thousands of plans and launches per transform.
 #pragma once
@@ -37,12 +41,6 @@ struct DevFFT {
 };
 
 PLK_HD int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
-PLK_HD int bitrev(int v, int bits) {
-  unsigned r = 0;
-  for (int i = 0; i < bits; ++i) { r = (r << 1) | ((unsigned)v & 1u); v >>= 1; }
-  return (int)r;
-}
-
 PLK_HD int lg2(int v) {   // exact log2 of a power of two
 #if defined(__CUDA_ARCH__)
   return 31 - __clz(v);
@@ -50,6 +48,17 @@ PLK_HD int lg2(int v) {   // exact log2 of a power of two
   return 31 - __builtin_clz((unsigned)v);
 #endif
 }
+PLK_HD int bitrev(int v, int bits) {
+#if defined(__CUDA_ARCH__)
+  return (int)(__brev((unsigned)v) >> (32 - bits));
+#else
+  unsigned r = 0;
+  for (int i = 0; i < bits; ++i) { r = (r << 1) | ((unsigned)v & 1u); v >>= 1; }
+  return (int)r;
+#endif
+}
+// shared-memory element swizzle (bijective on every aligned block of 16 elements)
+PLK_HD int SW(int i) { return i ^ ((i >> 4) & 15); }
 
 // twiddle e^{sign * 2 pi i * num / L}, 0 <= num < L, from a QUARTER-wave table W[k] = e^{-2 pi i k / Wn}, k < Wn/4
 // (kept in shared memory by the kernels): the other quadrants follow from W[k + Wn/4] = -i W[k].
@@ -64,67 +73,68 @@ PLK_HD cplx tw(const cplx *W, int lgWn, int num, int lgL) {
   return SIGN < 0 ? w : conj(w);
 }
 
-// ------------------------------------------------------------------ in-place shared-memory FFT stages
-// "tid/nthr" explicit so the very same code can be driven from a host loop in tests.
+// z * e^{SIGN 2 pi i k / 16}, k = 0..7 known at compile time after unrolling
 template <int SIGN>
-PLK_HD void dif_r2_stage(cplx *u, int M, const cplx *W, int lgWn, int tid, int nthr) {
-  const int H = M >> 1, lgM = lg2(M);
-  for (int i = tid; i < H; i += nthr) {
-    cplx a = u[i], b = u[i + H];
-    u[i] = a + b;
-    u[i + H] = (a - b) * tw<SIGN>(W, lgWn, i, lgM);
+PLK_HD cplx mul_root16(cplx z, int k) {
+  const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, r2 = 0.70710678118654752440;
+  const double sg = SIGN < 0 ? -1.0 : 1.0;   // e^{SIGN i phi} = cos phi + i sg sin phi
+  switch (k) {
+    case 0: return z;
+    case 4: return SIGN < 0 ? mul_mi(z) : mul_i(z);
+    case 2: return mk(r2 * (z.x - sg * z.y), r2 * (z.y + sg * z.x));
+    case 6: return mk(-r2 * (z.x + sg * z.y), r2 * (sg * z.x - z.y));
+    case 1: return mk(c1 * z.x - sg * s1 * z.y, c1 * z.y + sg * s1 * z.x);
+    case 3: return mk(s1 * z.x - sg * c1 * z.y, s1 * z.y + sg * c1 * z.x);
+    case 5: return mk(-s1 * z.x - sg * c1 * z.y, -s1 * z.y + sg * c1 * z.x);
+    default: return mk(-c1 * z.x - sg * s1 * z.y, -c1 * z.y + sg * s1 * z.x);   // 7
   }
 }
-// fused pair of radix-2 DIF stages on sub-transforms of length L (bit-reversal compatible ordering)
-template <int SIGN>
-PLK_HD void dif_r4_stage(cplx *u, int M, int L, const cplx *W, int lgWn, int tid, int nthr) {
-  const int Q = L >> 2, lgL = lg2(L), lgQ = lgL - 2;
-  for (int b = tid; b < (M >> 2); b += nthr) {
-    const int grp = b >> lgQ, j = b & (Q - 1);
-    cplx *p = u + ((size_t)grp << lgL) + j;
-    cplx a0 = p[0], a1 = p[Q], a2 = p[2 * Q], a3 = p[3 * Q];
-    cplx t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = a1 - a3;
-    t3 = SIGN < 0 ? mul_mi(t3) : mul_i(t3);
-    p[0] = t0 + t2;
-    p[Q] = (t0 - t2) * tw<SIGN>(W, lgWn, 2 * j, lgL);
-    p[2 * Q] = (t1 + t3) * tw<SIGN>(W, lgWn, j, lgL);
-    p[3 * Q] = (t1 - t3) * tw<SIGN>(W, lgWn, 3 * j, lgL);
+
+// log2(R) fused radix-2 DIF levels on v[k] = x[base + k * L/R] (j = index inside the stride block): results go back
+// to the same places and the overall transform stays in bit-reversed order whatever the radix schedule.
+// Level t pairs (k, k+h), h = R >> (t+1), with twiddle W_L^{2^t j} * e^{SIGN 2 pi i kk / (2h)}.
+template <int R, int SIGN>
+PLK_HD void radix_dif_regs(cplx (&v)[R], const cplx *W, int lgWn, int j, int lgL) {
+  constexpr int lgR = R == 16 ? 4 : (R == 8 ? 3 : 2);
+#pragma unroll
+  for (int t = 0; t < lgR; ++t) {
+    const int h = R >> (t + 1);
+    const cplx wt = tw<SIGN>(W, lgWn, j << t, lgL);
+#pragma unroll
+    for (int g = 0; g < R; g += 2 * h) {
+#pragma unroll
+      for (int kk = 0; kk < h; ++kk) {
+        const cplx a = v[g + kk], b = v[g + kk + h];
+        v[g + kk] = a + b;
+        v[g + kk + h] = mul_root16<SIGN>(a - b, kk * (8 / h)) * wt;
+      }
+    }
   }
 }
-// fused pair of radix-2 DIT stages producing sub-transforms of length L (input: two levels of bit reversal below)
-template <int SIGN>
-PLK_HD void dit_r4_stage(cplx *u, int M, int L, const cplx *W, int lgWn, int tid, int nthr) {
-  const int Q = L >> 2, lgL = lg2(L), lgQ = lgL - 2;
-  for (int b = tid; b < (M >> 2); b += nthr) {
-    const int grp = b >> lgQ, j = b & (Q - 1);
-    cplx *p = u + ((size_t)grp << lgL) + j;
-    cplx e0 = p[0], e1 = p[Q], e2 = p[2 * Q], e3 = p[3 * Q];
-    const cplx w2 = tw<SIGN>(W, lgWn, 2 * j, lgL);
-    cplx e1w = e1 * w2, e3w = e3 * w2;
-    cplx f0 = e0 + e1w, f1 = e0 - e1w, f2 = e2 + e3w, f3 = e2 - e3w;
-    const cplx w1 = tw<SIGN>(W, lgWn, j, lgL);
-    cplx f2w = f2 * w1;
-    cplx f3w = f3 * w1;
-    f3w = SIGN < 0 ? mul_mi(f3w) : mul_i(f3w);   // w^{j + L/4}
-    p[0] = f0 + f2w;
-    p[2 * Q] = f0 - f2w;
-    p[Q] = f1 + f3w;
-    p[3 * Q] = f1 - f3w;
-  }
-}
-template <int SIGN>
-PLK_HD void dit_r2_stage(cplx *u, int M, const cplx *W, int lgWn, int tid, int nthr) {
-  const int H = M >> 1, lgM = lg2(M);
-  for (int i = tid; i < H; i += nthr) {
-    cplx a = u[i], b = u[i + H] * tw<SIGN>(W, lgWn, i, lgM);
-    u[i] = a + b;
-    u[i + H] = a - b;
+// the transpose: DIT levels in the opposite order
+template <int R, int SIGN>
+PLK_HD void radix_dit_regs(cplx (&v)[R], const cplx *W, int lgWn, int j, int lgL) {
+  constexpr int lgR = R == 16 ? 4 : (R == 8 ? 3 : 2);
+#pragma unroll
+  for (int t = lgR - 1; t >= 0; --t) {
+    const int h = R >> (t + 1);
+    const cplx wt = tw<SIGN>(W, lgWn, j << t, lgL);
+#pragma unroll
+    for (int g = 0; g < R; g += 2 * h) {
+#pragma unroll
+      for (int kk = 0; kk < h; ++kk) {
+        const cplx a = v[g + kk];
+        const cplx b = mul_root16<SIGN>(v[g + kk + h] * wt, kk * (8 / h));
+        v[g + kk] = a + b;
+        v[g + kk + h] = a - b;
+      }
+    }
   }
 }
 
 // Execution context: on the device a thread block; on the host (tests/emul) a single "thread" that walks
-// every strided loop serially -- all cross-thread traffic goes through `buf` between sync() points, so the
-// very same body code is valid for both.
+// every strided loop serially -- all cross-thread traffic goes through shared buffers between sync() points, so
+// the very same body code is valid for both.
 struct BlockCtx {
   PLK_HD int tid() const {
 #if defined(__CUDA_ARCH__)
@@ -147,22 +157,59 @@ struct BlockCtx {
   }
 };
 
-// natural order in -> bit-reversed order out
-template <int SIGN, class Ctx>
-PLK_HD void fft_dif(Ctx ctx, cplx *u, int M, const cplx *W, int Wn) {
-  int L = M;
-  const int lgWn = lg2(Wn);
-  if (lg2(M) & 1) { dif_r2_stage<SIGN>(u, M, W, lgWn, ctx.tid(), ctx.nthr()); ctx.sync(); L >>= 1; }
-  for (; L >= 4; L >>= 2) { dif_r4_stage<SIGN>(u, M, L, W, lgWn, ctx.tid(), ctx.nthr()); ctx.sync(); }
+// one pass over nb transforms of M points stored at buf + f * M (swizzled): sub-transform length L = 2^lgL
+template <int R, int SIGN, bool DIT, class Ctx>
+PLK_HD void fft_pass(Ctx ctx, cplx *buf, int nb, int M, int lgL, const cplx *W, int lgWn) {
+  constexpr int lgR = R == 16 ? 4 : (R == 8 ? 3 : 2);
+  const int lgM = lg2(M), lgS = lgL - lgR, lgB = lgM - lgR;
+  for (int w = ctx.tid(); w < (nb << lgB); w += ctx.nthr()) {
+    const int f = w >> lgB, b = w & ((1 << lgB) - 1);
+    const int grp = b >> lgS, j = b & ((1 << lgS) - 1);
+    cplx *p = buf + ((size_t)f << lgM);
+    const int base = (grp << lgL) + j;
+    cplx v[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) v[k] = p[SW(base + (k << lgS))];
+    if (DIT) radix_dit_regs<R, SIGN>(v, W, lgWn, j, lgL);
+    else radix_dif_regs<R, SIGN>(v, W, lgWn, j, lgL);
+#pragma unroll
+    for (int k = 0; k < R; ++k) p[SW(base + (k << lgS))] = v[k];
+  }
 }
-// bit-reversed order in -> natural order out
+template <int SIGN, bool DIT, class Ctx>
+PLK_HD void fft_pass_r(Ctx ctx, int r, cplx *buf, int nb, int M, int lgL, const cplx *W, int lgWn) {
+  if (r == 4) fft_pass<16, SIGN, DIT>(ctx, buf, nb, M, lgL, W, lgWn);
+  else if (r == 3) fft_pass<8, SIGN, DIT>(ctx, buf, nb, M, lgL, W, lgWn);
+  else fft_pass<4, SIGN, DIT>(ctx, buf, nb, M, lgL, W, lgWn);
+  ctx.sync();
+}
+// radix schedule: ceil(bits/4) passes of 2..4 bits each, larger ones first (bits >= 4)
+PLK_HD int pass_bits(int bits, int ipass) {
+  const int np = (bits + 3) >> 2;
+  const int base = bits / np, extra = bits - base * np;
+  return base + (ipass < extra ? 1 : 0);
+}
+// natural order in -> bit-reversed order out (batched, in place)
 template <int SIGN, class Ctx>
-PLK_HD void fft_dit(Ctx ctx, cplx *u, int M, const cplx *W, int Wn) {
-  const bool odd = lg2(M) & 1;
-  const int Ltop = odd ? (M >> 1) : M;
-  const int lgWn = lg2(Wn);
-  for (int L = 4; L <= Ltop; L <<= 2) { dit_r4_stage<SIGN>(u, M, L, W, lgWn, ctx.tid(), ctx.nthr()); ctx.sync(); }
-  if (odd) { dit_r2_stage<SIGN>(u, M, W, lgWn, ctx.tid(), ctx.nthr()); ctx.sync(); }
+PLK_HD void fft_dif(Ctx ctx, cplx *buf, int nb, int M, const cplx *W) {
+  const int bits = lg2(M), np = (bits + 3) >> 2;
+  int lgL = bits;
+  for (int ip = 0; ip < np; ++ip) {
+    const int r = pass_bits(bits, ip);
+    fft_pass_r<SIGN, false>(ctx, r, buf, nb, M, lgL, W, bits);
+    lgL -= r;
+  }
+}
+// bit-reversed order in -> natural order out: the same passes backwards
+template <int SIGN, class Ctx>
+PLK_HD void fft_dit(Ctx ctx, cplx *buf, int nb, int M, const cplx *W) {
+  const int bits = lg2(M), np = (bits + 3) >> 2;
+  int lgL = 0;
+  for (int ip = np - 1; ip >= 0; --ip) {
+    const int r = pass_bits(bits, ip);
+    lgL += r;
+    fft_pass_r<SIGN, true>(ctx, r, buf, nb, M, lgL, W, bits);
+  }
 }
 
 // ------------------------------------------------------------------ fold / unfold helpers
@@ -180,8 +227,8 @@ PLK_HD cplx fold_bin(const cplx *X, int mmax, int n, int k, int shifted) {
 }
 
 // E^{(a)}_{k'} = e^{(2a)}_{k'} + i e^{(2a+1)}_{k'},  e^{(r)} = w_n^{r k'} sum_c i^{rc} d_{k'+qc},
-// d_k = e^{i pi k/n * shifted} D(k)
-PLK_HD cplx synth_input(const cplx *X, int mmax, int n, int q, int kp, int shifted, int a) {
+// d_k = e^{i pi k/n * shifted} D(k);  both a = 0 and a = 1 from one gather
+PLK_HD void synth_input2(const cplx *X, int mmax, int n, int q, int kp, int shifted, cplx &E0, cplx &E1) {
   const cplx g = expipi32(kp, n);             // e^{i pi k'/n}
   const cplx g2 = g * g;                      // w_n^{k'}
   cplx d[4];
@@ -193,96 +240,100 @@ PLK_HD cplx synth_input(const cplx *X, int mmax, int n, int q, int kp, int shift
     cplx D = fold_bin(X, mmax, n, kp + q * c, shifted);
     d[c] = shifted ? (g * c8[c]) * D : D;
   }
-  // r = 2a (even): i^{rc} = (-1)^{a c};  r = 2a+1: i^{rc} = i^{(2a+1)c}
-  cplx wr = mk(1.0, 0.0);
-  for (int i = 0; i < 2 * a; ++i) wr = wr * g2;      // w_n^{2a k'}
-  cplx e0, e1;
-  if (a == 0) {
-    e0 = d[0] + d[1] + d[2] + d[3];
-    e1 = (d[0] - d[2]) + mul_i(d[1] - d[3]);          // i^c
-  } else {
-    e0 = (d[0] + d[2]) - (d[1] + d[3]);               // (-1)^c
-    e1 = (d[0] - d[2]) - mul_i(d[1] - d[3]);          // i^{3c} = (-i)^c
-  }
-  e0 = wr * e0;
-  e1 = (wr * g2) * e1;
-  return e0 + mul_i(e1);
+  const cplx s02 = d[0] + d[2], s13 = d[1] + d[3], m02 = d[0] - d[2], m13 = mul_i(d[1] - d[3]);
+  const cplx g4 = g2 * g2, g6 = g4 * g2;
+  // r = 0: sum_c d_c ; r = 1: i^c ; r = 2: (-1)^c ; r = 3: (-i)^c, times w_n^{r k'}
+  const cplx e0 = s02 + s13, e1 = g2 * (m02 + m13), e2 = g4 * (s02 - s13), e3 = g6 * (m02 - m13);
+  E0 = e0 + mul_i(e1);
+  E1 = e2 + mul_i(e3);
 }
 
 PLK_HD cplx chirp(int t, int q) { return expipi32(t * t, q); }   // b_t = e^{i pi t^2/q}, t < 2^15
 
-// In-place inverse-sign length-q DFT of buf[0..q): Z_k = sum_t z_t e^{+2 pi i t k/q}.
-// On return Z_k = fetchZ(buf, k, ...).
+// In-place inverse-sign length-q DFTs of nb buffers: Z_k = sum_t z_t e^{+2 pi i t k/q}; Z_k = fetchZ(buf, k, ...)
 template <class Ctx>
-PLK_HD void idft_q(Ctx ctx, cplx *buf, int q, int M, const cplx *W, int Wn, const cplx *Vq) {
+PLK_HD void idft_q(Ctx ctx, cplx *buf, int nb, int q, int M, const cplx *W, const cplx *Vq) {
   if (M == q) {
-    fft_dif<+1>(ctx, buf, M, W, Wn);
+    fft_dif<+1>(ctx, buf, nb, M, W);
   } else {
-    fft_dif<-1>(ctx, buf, M, W, Wn);
-    for (int i = ctx.tid(); i < M; i += ctx.nthr()) buf[i] = buf[i] * Vq[i];
+    fft_dif<-1>(ctx, buf, nb, M, W);
+    const int lgM = lg2(M);
+    for (int w = ctx.tid(); w < (nb << lgM); w += ctx.nthr()) {
+      const int f = w >> lgM, i = w & (M - 1);
+      cplx *p = buf + ((size_t)f << lgM);
+      p[SW(i)] = p[SW(i)] * Vq[i];
+    }
     ctx.sync();
-    fft_dit<+1>(ctx, buf, M, W, Wn);
+    fft_dit<+1>(ctx, buf, nb, M, W);
   }
 }
-// copies the quarter-wave twiddles of an M-point transform next to the work buffer: tws[k] = e^{-2 pi i k/M}, k < M/4
+PLK_HD cplx fetchZ(const cplx *buf, int k, int q, int M, int bits) {
+  if (M == q) return buf[SW(bitrev(k, bits))];
+  return (1.0 / (double)M) * (chirp(k, q) * buf[SW(k)]);
+}
+// copies the quarter-wave twiddles of an M-point transform into shared memory: tws[k] = e^{-2 pi i k/M}, k < M/4
 template <class Ctx>
 PLK_HD void load_twiddles(Ctx ctx, cplx *tws, int M, const cplx *Wg, int Wng) {
   const int st = Wng / M;
   for (int k = ctx.tid(); k < (M >> 2); k += ctx.nthr()) tws[k] = Wg[(size_t)k * st];
   ctx.sync();
 }
-PLK_HD cplx fetchZ(const cplx *buf, int k, int q, int M, int bits) {
-  if (M == q) return buf[bitrev(k, bits)];
-  return (1.0 / (double)M) * (chirp(k, q) * buf[k]);
-}
 
 // ------------------------------------------------------------------ synthesis: X[ring][m] -> pixels
+// smem: [M/4 twiddles][nbatch buffers of M]; nbatch = 2 (one ring: a = 0, 1) or 4 (both rings of the pair)
 template <class Ctx>
 PLK_HD void ring_synth_body(Ctx ctx, const DevFFT &f, int ip, const cplx *X, int pitch, int mmax_in, double *map,
-                            cplx *buf) {
+                            cplx *smem, int nbatch) {
   const int n = f.nphi[ip], q = n >> 2, M = f.M[ip], shifted = f.shifted[ip];
-  const int bits = ilog2(M > 0 ? M : 1);
-  const cplx *Vq = (f.voff[ip] >= 0) ? f.V + f.voff[ip] : nullptr;
   // rows of X are exactly zero above mtop (pairs the Legendre stage skips): do not fold them
   const int mmax = f.mtop ? (f.mtop[ip] < mmax_in ? f.mtop[ip] : mmax_in) : mmax_in;
-  cplx *tws = buf + M;
-  if (M > 0) load_twiddles(ctx, tws, M, f.W, f.Wn);
-  for (int half = 0; half < 2; ++half) {
-    const long long start = half == 0 ? f.start_n[ip] : f.start_s[ip];
-    if (start < 0) continue;
-    const int ring = half == 0 ? ip : f.nring - 1 - ip;
-    const cplx *Xr = X + (size_t)ring * pitch;
-    double *out = map + start;
-    if (M == 0) {
-      // tiny ring: x_j = X_0 + 2 Re sum_{m>0} X_m e^{i m phi_j}, phi_j = pi (shifted + 2j)/n
-      for (int j = ctx.tid(); j < n; j += ctx.nthr()) {
-        double acc = Xr[0].x;
-        for (int m = 1; m <= mmax; ++m) {
-          cplx e = expipi32(m * (shifted + 2 * j), n);
-          acc += 2.0 * (Xr[m].x * e.x - Xr[m].y * e.y);
-        }
-        out[j] = acc;
+  const int nhalf = f.start_s[ip] >= 0 ? 2 : 1;
+  if (M == 0) {
+    // tiny ring: x_j = X_0 + 2 Re sum_{m>0} X_m e^{i m phi_j}, phi_j = pi (shifted + 2j)/n
+    for (int w = ctx.tid(); w < nhalf * n; w += ctx.nthr()) {
+      const int half = w / n, j = w - half * n;
+      const cplx *Xr = X + (size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch;
+      double acc = Xr[0].x;
+      for (int m = 1; m <= mmax; ++m) {
+        const cplx e = expipi32(m * (shifted + 2 * j), n);
+        acc += 2.0 * (Xr[m].x * e.x - Xr[m].y * e.y);
       }
-      continue;
+      map[(half == 0 ? f.start_n[ip] : f.start_s[ip]) + j] = acc;
     }
-    for (int a = 0; a < 2; ++a) {
-      for (int i = ctx.tid(); i < M; i += ctx.nthr()) {
-        cplx v = mk(0.0, 0.0);
-        if (i < q) {
-          v = synth_input(Xr, mmax, n, q, i, shifted, a);
-          if (M != q) v = v * chirp(i, q);
-        }
-        buf[i] = v;
+    return;
+  }
+  const int bits = lg2(M);
+  const cplx *Vq = (f.voff[ip] >= 0) ? f.V + f.voff[ip] : nullptr;
+  cplx *tws = smem, *buf = smem + (M >> 2);
+  load_twiddles(ctx, tws, M, f.W, f.Wn);
+  const int hstep = nbatch >= 4 ? 2 : 1;
+  for (int h0 = 0; h0 < nhalf; h0 += hstep) {
+    const int nh = (nhalf - h0) < hstep ? (nhalf - h0) : hstep;
+    for (int w = ctx.tid(); w < (nh << bits); w += ctx.nthr()) {
+      const int hh = w >> bits, i = w & (M - 1), half = h0 + hh;
+      cplx e0 = mk(0.0, 0.0), e1 = mk(0.0, 0.0);
+      if (i < q) {
+        const cplx *Xr = X + (size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch;
+        synth_input2(Xr, mmax, n, q, i, shifted, e0, e1);
+        if (M != q) { const cplx c = chirp(i, q); e0 = e0 * c; e1 = e1 * c; }
       }
-      ctx.sync();
-      idft_q(ctx, buf, q, M, tws, M, Vq);
-      for (int t = ctx.tid(); t < q; t += ctx.nthr()) {
-        cplx y = fetchZ(buf, t, q, M, bits);
-        out[4 * t + 2 * a] = y.x;
-        out[4 * t + 2 * a + 1] = y.y;
-      }
-      ctx.sync();
+      buf[((size_t)(2 * hh) << bits) + SW(i)] = e0;
+      buf[((size_t)(2 * hh + 1) << bits) + SW(i)] = e1;
     }
+    ctx.sync();
+    idft_q(ctx, buf, 2 * nh, q, M, tws, Vq);
+    for (int w = ctx.tid(); w < nh * q; w += ctx.nthr()) {
+      const int hh = w / q, t = w - hh * q, half = h0 + hh;
+      const cplx y0 = fetchZ(buf + ((size_t)(2 * hh) << bits), t, q, M, bits);
+      const cplx y1 = fetchZ(buf + ((size_t)(2 * hh + 1) << bits), t, q, M, bits);
+      double *out = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]) + 4 * t;   // 32-byte aligned
+#if defined(__CUDA_ARCH__)
+      *reinterpret_cast<double4 *>(out) = make_double4(y0.x, y0.y, y1.x, y1.y);
+#else
+      out[0] = y0.x; out[1] = y0.y; out[2] = y1.x; out[3] = y1.y;
+#endif
+    }
+    ctx.sync();
   }
 }
 
@@ -290,95 +341,98 @@ PLK_HD void ring_synth_body(Ctx ctx, const DevFFT &f, int ip, const cplx *X, int
 // X_m = wgt * sum_j map_j e^{-i m phi_j}
 template <class Ctx>
 PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, cplx *X, int pitch, int mmax_in,
-                           double wgt, cplx *buf) {
+                           double wgt, cplx *smem, int nbatch) {
   const int n = f.nphi[ip], q = n >> 2, M = f.M[ip], shifted = f.shifted[ip];
-  const int bits = ilog2(M > 0 ? M : 1);
-  const cplx *Vq = (f.voff[ip] >= 0) ? f.V + f.voff[ip] : nullptr;
   // the Legendre stage never reads X above mtop on this pair
   const int mmax = f.mtop ? (f.mtop[ip] < mmax_in ? f.mtop[ip] : mmax_in) : mmax_in;
-  cplx *tws = buf + M;
-  if (M > 0) load_twiddles(ctx, tws, M, f.W, f.Wn);
-  for (int half = 0; half < 2; ++half) {
-    const long long start = half == 0 ? f.start_n[ip] : f.start_s[ip];
-    if (start < 0) continue;
-    const int ring = half == 0 ? ip : f.nring - 1 - ip;
-    cplx *Xr = X + (size_t)ring * pitch;
-    const double *in = map + start;
-    if (M == 0) {
-      for (int m = ctx.tid(); m <= mmax; m += ctx.nthr()) {
-        cplx acc = mk(0.0, 0.0);
-        for (int j = 0; j < n; ++j) {
-          cplx e = expipi32(-m * (shifted + 2 * j), n);
-          acc = acc + in[j] * e;
-        }
-        Xr[m] = wgt * acc;
-      }
-      continue;
+  const int nhalf = f.start_s[ip] >= 0 ? 2 : 1;
+  if (M == 0) {
+    for (int w = ctx.tid(); w < nhalf * (mmax + 1); w += ctx.nthr()) {
+      const int half = w / (mmax + 1), m = w - half * (mmax + 1);
+      const double *in = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]);
+      cplx acc = mk(0.0, 0.0);
+      for (int j = 0; j < n; ++j) acc = acc + in[j] * expipi32(-m * (shifted + 2 * j), n);
+      X[(size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch + m] = wgt * acc;
     }
-    for (int a = 0; a < 2; ++a) {
-      for (int i = ctx.tid(); i < M; i += ctx.nthr()) {
-        cplx v = mk(0.0, 0.0);
-        if (i < q) {
-          v = mk(in[4 * i + 2 * a], -in[4 * i + 2 * a + 1]);   // conj(y_t)
-          if (M != q) v = v * chirp(i, q);
-        }
-        buf[i] = v;
+    return;
+  }
+  const int bits = lg2(M);
+  const cplx *Vq = (f.voff[ip] >= 0) ? f.V + f.voff[ip] : nullptr;
+  cplx *tws = smem, *buf = smem + (M >> 2);
+  load_twiddles(ctx, tws, M, f.W, f.Wn);
+  const int hstep = nbatch >= 4 ? 2 : 1;
+  for (int h0 = 0; h0 < nhalf; h0 += hstep) {
+    const int nh = (nhalf - h0) < hstep ? (nhalf - h0) : hstep;
+    for (int w = ctx.tid(); w < (nh << bits); w += ctx.nthr()) {
+      const int hh = w >> bits, i = w & (M - 1), half = h0 + hh;
+      cplx v0 = mk(0.0, 0.0), v1 = mk(0.0, 0.0);
+      if (i < q) {
+        const double *in = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]) + 4 * i;
+        v0 = mk(in[0], -in[1]);      // conj(y^{(0)}_t), y^{(a)}_t = x_{4t+2a} + i x_{4t+2a+1}
+        v1 = mk(in[2], -in[3]);
+        if (M != q) { const cplx c = chirp(i, q); v0 = v0 * c; v1 = v1 * c; }
       }
-      ctx.sync();
-      idft_q(ctx, buf, q, M, tws, M, Vq);
-      // Y_k = conj(Z_k);  S^{(2a)}_k = (Y_k + conj Y_{q-k})/2,  S^{(2a+1)}_k = (Y_k - conj Y_{q-k})/(2i)
-      // D_k = sum_r w_n^{-r k} S^{(r)}_{k mod q} ;  X_m = wgt e^{-i pi m/n * shifted} D_{m mod n}
-      for (int m = ctx.tid(); m <= mmax; m += ctx.nthr()) {
-        const int jn = m / n, k = m - jn * n;
-        const int kp = k % q, kq = (q - kp) % q;
-        const cplx Yk = conj(fetchZ(buf, kp, q, M, bits));
-        const cplx Yc = fetchZ(buf, kq, q, M, bits);           // conj(Y_{q-k})
-        const cplx S0 = 0.5 * (Yk + Yc);
-        const cplx S1 = mul_mi(0.5 * (Yk - Yc));
-        const cplx g = expipi32(-k, n);                        // e^{-i pi k/n}
-        const cplx g2 = g * g;                                 // w_n^{-k}
-        cplx wr = mk(1.0, 0.0);
-        for (int i = 0; i < 2 * a; ++i) wr = wr * g2;          // w_n^{-2a k}
-        cplx D = wr * S0 + (wr * g2) * S1;
-        cplx ph = mk(wgt, 0.0);
-        if (shifted) ph = ((jn & 1) ? -wgt : wgt) * g;
-        cplx val = ph * D;
-        if (a == 0) Xr[m] = val;
-        else Xr[m] = Xr[m] + val;
-      }
-      ctx.sync();
+      buf[((size_t)(2 * hh) << bits) + SW(i)] = v0;
+      buf[((size_t)(2 * hh + 1) << bits) + SW(i)] = v1;
     }
+    ctx.sync();
+    idft_q(ctx, buf, 2 * nh, q, M, tws, Vq);
+    // Y^{(a)}_k = conj(Z^{(a)}_k);  S^{(2a)}_k = (Y_k + conj Y_{q-k})/2,  S^{(2a+1)}_k = (Y_k - conj Y_{q-k})/(2i)
+    // D_k = sum_r w_n^{-r k} S^{(r)}_{k mod q} ;  X_m = wgt e^{-i pi m/n * shifted} D_{m mod n}
+    for (int w = ctx.tid(); w < nh * (mmax + 1); w += ctx.nthr()) {
+      const int hh = w / (mmax + 1), m = w - hh * (mmax + 1), half = h0 + hh;
+      const int jn = m / n, k = m - jn * n;
+      const int kp = k % q, kq = (q - kp) % q;
+      const cplx *b0 = buf + ((size_t)(2 * hh) << bits), *b1 = buf + ((size_t)(2 * hh + 1) << bits);
+      const cplx Y0 = conj(fetchZ(b0, kp, q, M, bits)), Y0c = fetchZ(b0, kq, q, M, bits);
+      const cplx Y1 = conj(fetchZ(b1, kp, q, M, bits)), Y1c = fetchZ(b1, kq, q, M, bits);
+      const cplx S0 = 0.5 * (Y0 + Y0c), S1 = mul_mi(0.5 * (Y0 - Y0c));
+      const cplx S2 = 0.5 * (Y1 + Y1c), S3 = mul_mi(0.5 * (Y1 - Y1c));
+      const cplx g = expipi32(-k, n);                        // e^{-i pi k/n}
+      const cplx g2 = g * g, g4 = g2 * g2, g6 = g4 * g2;     // w_n^{-k}, w_n^{-2k}, w_n^{-3k}
+      const cplx D = (S0 + g2 * S1) + (g4 * S2 + g6 * S3);
+      cplx ph = mk(wgt, 0.0);
+      if (shifted) ph = ((jn & 1) ? -wgt : wgt) * g;
+      X[(size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch + m] = ph * D;
+    }
+    ctx.sync();
   }
 }
 
 // Bluestein kernel spectrum for ring pair ip: v[t mod M] = e^{-i pi t^2/q}, |t| < q, forward DIF (kept in DIF order)
 template <class Ctx>
-PLK_HD void bluestein_setup_body(Ctx ctx, const DevFFT &f, int ip, cplx *Vout, cplx *buf) {
+PLK_HD void bluestein_setup_body(Ctx ctx, const DevFFT &f, int ip, cplx *Vout, cplx *smem) {
   if (f.voff[ip] < 0) return;
   const int q = f.nphi[ip] >> 2, M = f.M[ip];
+  cplx *tws = smem, *buf = smem + (M >> 2);
+  load_twiddles(ctx, tws, M, f.W, f.Wn);
   for (int i = ctx.tid(); i < M; i += ctx.nthr()) {
     cplx v = mk(0.0, 0.0);
     if (i < q) v = conj(chirp(i, q));
     else if (i > M - q) v = conj(chirp(M - i, q));
-    buf[i] = v;
+    buf[SW(i)] = v;
   }
   ctx.sync();
-  cplx *tws = buf + M;
-  load_twiddles(ctx, tws, M, f.W, f.Wn);
-  fft_dif<-1>(ctx, buf, M, tws, M);
-  for (int i = ctx.tid(); i < M; i += ctx.nthr()) Vout[f.voff[ip] + i] = buf[i];
+  fft_dif<-1>(ctx, buf, 1, M, tws);
+  for (int i = ctx.tid(); i < M; i += ctx.nthr()) Vout[f.voff[ip] + i] = buf[SW(i)];
 }
 
 #if defined(__CUDACC__)
-__global__ void __launch_bounds__(kFftThreads)
-ring_synth_kernel(DevFFT f, const cplx *__restrict__ X, int pitch, int mmax, double *__restrict__ map) {
+// one launch per FFT size class: `list` holds the ring pairs of the class, dynamic smem = (nbatch + 1/4) M complex.
+// <256, 3>: up to three resident blocks (<= 80 registers); <512, 1>: the largest transforms, one block per SM.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+ring_synth_kernel(DevFFT f, const int *__restrict__ list, int nbatch, const cplx *__restrict__ X, int pitch, int mmax,
+                  double *__restrict__ map) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ring_synth_body(BlockCtx(), f, f.order[blockIdx.x], X, pitch, mmax, map, reinterpret_cast<cplx *>(smem_raw));
+  ring_synth_body(BlockCtx(), f, list[blockIdx.x], X, pitch, mmax, map, reinterpret_cast<cplx *>(smem_raw), nbatch);
 }
-__global__ void __launch_bounds__(kFftThreads)
-ring_anal_kernel(DevFFT f, const double *__restrict__ map, cplx *__restrict__ X, int pitch, int mmax, double wgt) {
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+ring_anal_kernel(DevFFT f, const int *__restrict__ list, int nbatch, const double *__restrict__ map, cplx *__restrict__ X,
+                 int pitch, int mmax, double wgt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ring_anal_body(BlockCtx(), f, f.order[blockIdx.x], map, X, pitch, mmax, wgt, reinterpret_cast<cplx *>(smem_raw));
+  ring_anal_body(BlockCtx(), f, list[blockIdx.x], map, X, pitch, mmax, wgt, reinterpret_cast<cplx *>(smem_raw), nbatch);
 }
 __global__ void __launch_bounds__(kFftThreads) bluestein_setup_kernel(DevFFT f, cplx *Vout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

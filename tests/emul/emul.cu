@@ -55,19 +55,20 @@ void build_fft(const HostGeom &hg, HostFFT &h) {
 }
 }  // namespace
 
-extern "C" int emul_ring_synth(int nside, int mmax, int pitch, const cplx *X, double *map) {
+// nbatch = 2 or 4 (DFTs of one ring, or of both rings of the pair, per batch) -- both are exercised by the tests
+extern "C" int emul_ring_synth(int nside, int mmax, int pitch, const cplx *X, double *map, int nbatch) {
   HostGeom hg = make_geom(nside);
   HostFFT h; build_fft(hg, h);
-  std::vector<cplx> buf(h.Mmax + h.Mmax / 4);
-  for (int ip = 0; ip < hg.npair; ++ip) ring_synth_body(BlockCtx(), h.f, ip, X, pitch, mmax, map, buf.data());
+  std::vector<cplx> buf((size_t)nbatch * h.Mmax + h.Mmax / 4);
+  for (int ip = 0; ip < hg.npair; ++ip) ring_synth_body(BlockCtx(), h.f, ip, X, pitch, mmax, map, buf.data(), nbatch);
   return 0;
 }
-extern "C" int emul_ring_anal(int nside, int mmax, int pitch, const double *map, cplx *X) {
+extern "C" int emul_ring_anal(int nside, int mmax, int pitch, const double *map, cplx *X, int nbatch) {
   HostGeom hg = make_geom(nside);
   HostFFT h; build_fft(hg, h);
-  std::vector<cplx> buf(h.Mmax + h.Mmax / 4);
+  std::vector<cplx> buf((size_t)nbatch * h.Mmax + h.Mmax / 4);
   const double w = 4.0 * M_PI / (double)hg.npix;
-  for (int ip = 0; ip < hg.npair; ++ip) ring_anal_body(BlockCtx(), h.f, ip, map, X, pitch, mmax, w, buf.data());
+  for (int ip = 0; ip < hg.npair; ++ip) ring_anal_body(BlockCtx(), h.f, ip, map, X, pitch, mmax, w, buf.data(), nbatch);
   return 0;
 }
 

@@ -25,19 +25,20 @@ def emul():
     return ctypes.CDLL(SO)
 
 
-@pytest.mark.parametrize("nside,lmax", [(4, 11), (8, 23), (16, 40), (32, 70)])
-def test_ring_fft_stage(emul, oracle_sht, nside, lmax):
+@pytest.mark.parametrize("nbatch", [2, 4])
+@pytest.mark.parametrize("nside,lmax", [(4, 11), (8, 23), (16, 40), (32, 70), (64, 100)])
+def test_ring_fft_stage(emul, oracle_sht, nside, lmax, nbatch):
     rng = np.random.default_rng(nside)
     nring, pitch = 4 * nside - 1, (lmax + 2) & ~1
     X = np.zeros((nring, pitch), dtype=complex)
     X[:, :lmax + 1] = rng.standard_normal((nring, lmax + 1)) + 1j * rng.standard_normal((nring, lmax + 1))
     X[:, 0] = X[:, 0].real
     out = np.zeros(12 * nside ** 2)
-    emul.emul_ring_synth(nside, lmax, pitch, vp(X.ctypes.data), vp(out.ctypes.data))
+    emul.emul_ring_synth(nside, lmax, pitch, vp(X.ctypes.data), vp(out.ctypes.data), nbatch)
     assert rel_l2(out, oracle_sht.phase2map(nside, X[:, :lmax + 1])) < 1e-13
     mp = rng.standard_normal(12 * nside ** 2)
     Xo = np.zeros((nring, pitch), dtype=complex)
-    emul.emul_ring_anal(nside, lmax, pitch, vp(mp.ctypes.data), vp(Xo.ctypes.data))
+    emul.emul_ring_anal(nside, lmax, pitch, vp(mp.ctypes.data), vp(Xo.ctypes.data), nbatch)
     ref = oracle_sht.map2phase(nside, mp, lmax) * (4 * np.pi / (12 * nside ** 2))
     assert rel_l2(Xo[:, :lmax + 1], ref) < 1e-13
 
