@@ -252,10 +252,13 @@ class library:
             MF = np.zeros(hp.Alm.getsize(lmax), dtype=complex)
             if len(this_mcs) == 0:
                 return MF
-            for i, idx in ut.enumerate_progress(this_mcs, label='calculating %s MF' % k):
+            # simulations are strided over ranks (reference pattern: examples/run_qlms.py:72), then summed
+            for idx in this_mcs[mpi.rank::mpi.size]:
                 MF += self.get_sim_qlm(k, idx, lmax=lmax)
-            MF /= len(this_mcs)
-            _write_alm(fname, MF)
+            MF = mpi.allreduce_sum(MF) / len(this_mcs)
+            if mpi.rank == 0:
+                _write_alm(fname, MF)
+            mpi.barrier()
         return ut.alm_copy(hp.read_alm(fname), lmax=lmax)
 
     def eval_qlm(self, k, idx, swapped=False):

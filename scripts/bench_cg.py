@@ -1,0 +1,82 @@
+"""Masked-sky CG inverse-variance filter at full size (BASELINE.json configs[2]): cinv_t / cinv_p with the
+reference's default multigrid chains (filt_cinv.py:113-116, :237-239), synthetic Galactic mask + anisotropic
+noise.  Prints iterations to eps = 1e-5 and seconds per top-level iteration."""
+import argparse, json, os, sys, tempfile, time
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+import bench
+from golden_inputs import pix_z
+from plancklens_b200 import hp, sht, utils
+from plancklens_b200.filt import filt_cinv
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--nside', type=int, default=2048)
+ap.add_argument('--lmax', type=int, default=2048)
+ap.add_argument('--pol', action='store_true')
+ap.add_argument('--skip-t', action='store_true')
+a = ap.parse_args()
+nside, lmax = a.nside, a.lmax
+npix = 12 * nside ** 2
+cls, transf, ftl, fel, fbl = bench.fiducial(lmax)
+rng = np.random.default_rng(7)
+z = pix_z(nside)
+mask = (np.abs(z) >= np.sin(np.deg2rad(20.))).astype(float)
+# 2000 point-source discs of radius 10 arcmin
+plan = sht.get_plan(nside, lmax)
+zc = rng.uniform(-1, 1, 2000); pc = rng.uniform(0, 2 * np.pi, 2000)
+# pixel coordinates from ring geometry (host)
+phi = np.empty(npix); p = 0
+for i in range(1, 4 * nside):
+    ii = i if i < nside else (nside if i <= 3 * nside else 4 * nside - i)
+    n = 4 * ii
+    ph0 = np.pi / n if (i < nside or i > 3 * nside or (i - nside) % 2 == 0) else 0.0
+    phi[p:p + n] = ph0 + 2 * np.pi * np.arange(n) / n
+    p += n
+s = np.sqrt(1 - z * z)
+vec = np.stack([s * np.cos(phi), s * np.sin(phi), z], 1)
+cr = np.cos(np.deg2rad(10. / 60.))
+order = np.argsort(z)
+zs = z[order]
+for k in range(2000):
+    sc = np.sqrt(1 - zc[k] ** 2)
+    c = np.array([sc * np.cos(pc[k]), sc * np.sin(pc[k]), zc[k]])
+    lo, hi = np.searchsorted(zs, [zc[k] - 0.004, zc[k] + 0.004])
+    cand = order[lo:hi]
+    mask[cand[vec[cand] @ c > cr]] = 0.0
+print('fsky = %.4f' % mask.mean())
+vamin = np.sqrt(hp.nside2pixarea(nside, degrees=True)) * 60
+ninv_t = mask * (vamin / bench.NLEV_T) ** 2 * (1 + 0.5 * z ** 2)
+ninv_p = mask * (vamin / bench.NLEV_P) ** 2 * (1 + 0.5 * z ** 2)
+# data: CMB + noise map through the GPU synthesis
+alms = bench.filtered_sim(0, lmax, cls, transf, (np.ones(lmax + 1),) * 3)   # unfiltered (a + n/b)
+tmap = hp.alm2map(hp.almxfl(alms[0], transf), nside)
+out = {}
+tmp = tempfile.mkdtemp(prefix='plk_cg_')
+if not a.skip_t:
+    t0 = time.time()
+    cinv_t = filt_cinv.cinv_t(os.path.join(tmp, 'cinv_t'), lmax, nside, cls, transf, [ninv_t], marge_monopole=True, marge_dipole=True)
+    _ = cinv_t.chain.bstage     # instantiate (dense preconditioner build included)
+    torch.cuda.synchronize(); t_setup = time.time() - t0
+    n0 = sht._lib.launch_count(); t0 = time.time()
+    tlm = cinv_t.apply_ivf(tmap)
+    torch.cuda.synchronize(); dt = time.time() - t0
+    it = cinv_t.chain.niter
+    out['T'] = {'iterations': it, 'seconds': dt, 'iter_per_s': it / dt, 'setup_s': t_setup,
+                'launches': sht._lib.launch_count() - n0, 'final_eps': cinv_t.chain.last_monitor.trace[-1][1]}
+    print('CG-T', out['T'])
+if a.pol:
+    qmap, umap = hp.alm2map_spin([hp.almxfl(alms[1], transf), hp.almxfl(alms[2], transf)], nside, 2, lmax)
+    t0 = time.time()
+    cinv_p = filt_cinv.cinv_p(os.path.join(tmp, 'cinv_p'), lmax, nside, cls, transf, [[ninv_p]])
+    _ = cinv_p.chain.bstage
+    torch.cuda.synchronize(); t_setup = time.time() - t0
+    n0 = sht._lib.launch_count(); t0 = time.time()
+    elm, blm = cinv_p.apply_ivf([qmap, umap])
+    torch.cuda.synchronize(); dt = time.time() - t0
+    it = cinv_p.chain.niter
+    out['P'] = {'iterations': it, 'seconds': dt, 'iter_per_s': it / dt, 'setup_s': t_setup,
+                'launches': sht._lib.launch_count() - n0, 'final_eps': cinv_p.chain.last_monitor.trace[-1][1]}
+    print('CG-P', out['P'])
+print(json.dumps({'cg': out, 'nside': nside, 'lmax': lmax, 'fsky': float(mask.mean())}))

@@ -1,0 +1,51 @@
+"""CPU, world_size 2 over gloo: the N > 1 host logic -- rank/size shim, simulation striding and the mean-field
+all-reduce of qest.library.get_sim_qlm_mf (no GPU involved: get_sim_qlm is stubbed)."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+from plancklens_b200.helpers import mpi
+rank, size = mpi.init('gloo')
+assert size == 2 and mpi.rank == rank
+from plancklens_b200 import qest, hp
+lib = object.__new__(qest.library)
+lib.lib_dir = %(tmp)r
+lib.lmax_qlm = {'T': 8, 'P': 8, 'PS': 8}
+lib.keys_fund = ['ptt']; lib.keys_remaps = {}
+calls = []
+def fake(k, idx, lmax=None):
+    calls.append(int(idx))
+    return (idx + 1) * (np.arange(hp.Alm.getsize(8)) + 1j)
+lib.get_sim_qlm = fake
+mf = lib.get_sim_qlm_mf('ptt', np.arange(6))
+expect = np.mean([i + 1 for i in range(6)]) * (np.arange(hp.Alm.getsize(8)) + 1j)
+assert np.allclose(mf, expect), (mf[:3], expect[:3])
+assert calls == list(range(6))[rank::2], calls          # each rank evaluated only its share
+assert np.allclose(mpi.allreduce_sum(np.array([1.0 + rank])), 3.0)
+assert mpi.bcast('x' if rank == 0 else None) == 'x'
+mpi.barrier()
+print('rank', rank, 'ok')
+mpi.finalize()
+'''
+
+
+def test_mean_field_sharded_over_two_ranks():
+    with tempfile.TemporaryDirectory() as tmp:
+        script = os.path.join(tmp, 'w.py')
+        with open(script, 'w') as f:
+            f.write(WORKER % {'root': ROOT, 'tmp': tmp})
+        env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29533')
+        out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                              '--master-addr', '127.0.0.1', '--master-port', '29533', script],
+                             capture_output=True, text=True, env=env, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert 'rank 0 ok' in out.stdout and 'rank 1 ok' in out.stdout
