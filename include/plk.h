@@ -113,6 +113,9 @@ int plk_map_mul2_dev(long long n, double *g, double *c, const double *t, void *s
 /* qest.py:276-278:  (re,im) = (q - i u)(g3 + i c3) - (q + i u)(g1 - i c1) */
 int plk_map_qe_pp_dev(long long n, const double *q, const double *u, const double *g3, const double *c3,
                       const double *g1, const double *c1, double *re, double *im, void *stream);
+/* utils_qe.py:117: d += leg_a * leg_b for complex spin maps given as (re, im) real maps; ai / bi may be NULL */
+int plk_map_cmul_acc_dev(long long n, const double *ar, const double *ai, const double *br, const double *bi,
+                         double *dr, double *di, void *stream);
 /* opfilt_pp.py:292-301: (q,u) <- [[nqq, nqu],[nqu, nuu]] (q,u) */
 int plk_map_ninv3_dev(long long n, double *q, double *u, const double *nqq, const double *nqu, const double *nuu,
                       void *stream);

@@ -41,6 +41,7 @@ _SIGS = {
     'plk_map_mul_dev': (c_int, [c_ll, vp, vp, vp]),
     'plk_map_mul2_dev': (c_int, [c_ll, vp, vp, vp, vp]),
     'plk_map_qe_pp_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'plk_map_cmul_acc_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp]),
     'plk_map_ninv3_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp]),
     'plk_map_modes_dot_dev': (c_int, [vp, vp, vp, vp, vp]),
     'plk_map_modes_sub_dev': (c_int, [vp, vp, vp, vp, vp, vp]),

@@ -596,6 +596,13 @@ extern "C" int plk_map_qe_pp_dev(long long n, const double *q, const double *u, 
   LAUNCHED();
   return PLK_OK;
 }
+extern "C" int plk_map_cmul_acc_dev(long long n, const double *ar, const double *ai, const double *br, const double *bi,
+                                    double *dr, double *di, void *stream) {
+  if (!ar || !br || !dr || !di) return fail(PLK_EINVAL, "NULL buffer");
+  map_cmul_acc_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, ar, ai, br, bi, dr, di);
+  LAUNCHED();
+  return PLK_OK;
+}
 extern "C" int plk_map_ninv3_dev(long long n, double *q, double *u, const double *nqq, const double *nqu,
                                  const double *nuu, void *stream) {
   if (!q || !u || !nqq || !nqu || !nuu) return fail(PLK_EINVAL, "NULL buffer");

@@ -186,6 +186,17 @@ __global__ void map_ninv3_kernel(long long n, double *__restrict__ q, double *__
   }
 }
 
+// d += a * b for complex maps stored as (re, im) pairs of real maps; b_im may be null (real second factor)
+__global__ void map_cmul_acc_kernel(long long n, const double *__restrict__ ar, const double *__restrict__ ai,
+                                    const double *__restrict__ br, const double *__restrict__ bi,
+                                    double *__restrict__ dr, double *__restrict__ di) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = ar[i], b = ai ? ai[i] : 0.0, c = br[i], d = bi ? bi[i] : 0.0;
+    dr[i] += a * c - b * d;
+    di[i] += a * d + b * c;
+  }
+}
+
 // monopole / dipole templates: one block per ring; pixel direction from the ring geometry
 struct DevRings {
   int nring;

@@ -31,6 +31,24 @@ from .helpers import mpi
 _write_alm = lambda fn, alm: hp.write_alm(fn, alm, overwrite=True)
 
 
+def eval_qe(qe_key, lmax_ivf, cls_weight, get_alm, nside, lmax_qlm, verbose=True, get_alm2=None, transf=None):
+    """Gradient and curl terms of a quadratic estimator through the generic leg machinery
+    (reference: qest.py:19-39; `library` below is faster for the lensing keys).
+
+        Args:
+            qe_key: estimator key as defined in `qresp` (e.g. 'ptt')
+            lmax_ivf: CMB multipoles up to lmax_ivf are used
+            cls_weight: CMB spectra entering the estimator weights
+            get_alm: callable with 't', 'e', 'b' returning the inverse-variance filtered alms
+            nside: resolution of the real-space products
+            lmax_qlm: maximum multipole of the estimate
+            get_alm2: alms of the second leg if different (the estimator is then symmetrised)
+    """
+    from . import qresp, utils_qe
+    qe_list = qresp.get_qes(qe_key, lmax_ivf, cls_weight, transf=transf)
+    return utils_qe.qe_eval(qe_list, nside, get_alm, lmax_qlm, verbose=verbose, get_alm2=get_alm2)
+
+
 def library_jtTP(lib_dir, ivfs1, ivfs2, nside, lmax_qlm=None, resplib=None):
     return library(lib_dir, ivfs1, ivfs2, nside, lmax_qlm=lmax_qlm, resplib=resplib)
 

@@ -278,3 +278,8 @@ def map_qe_pp(q, u, g3, c3, g1, c1, re, im):
 
 def map_ninv3(q, u, nqq, nqu, nuu):
     check(_lib.load().plk_map_ninv3_dev(q.numel(), _ptr(q), _ptr(u), _ptr(nqq), _ptr(nqu), _ptr(nuu), _stream()))
+
+
+def map_cmul_acc(ar, ai, br, bi, dr, di):
+    """(dr + i di) += (ar + i ai)(br + i bi); ai / bi may be None"""
+    check(_lib.load().plk_map_cmul_acc_dev(ar.numel(), _ptr(ar), _ptr(ai), _ptr(br), _ptr(bi), _ptr(dr), _ptr(di), _stream()))

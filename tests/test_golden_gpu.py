@@ -188,3 +188,32 @@ def test_shts_seam_signatures(oracle_sht):
     assert rel_l2(t0, -m) < 1e-13 and zero == 0.
     with pytest.raises(TypeError):
         shts.alm2map(a[:-1], nside)
+
+
+def test_generic_qe_eval_matches_reference(gold):
+    """qest.eval_qe (qresp.get_qes -> utils_qe.qe_eval) for 'ptt' and 'p_p' vs the reference's own generic path, and
+    the 'p' key vs the fast path (the equivalence the reference claims at qest.py:23)."""
+    from plancklens_b200 import qest
+    q = gi.qe_case()
+    get_alm = lambda a: {'t': q['tlm1'], 'e': q['elm1'], 'b': q['blm1']}[a].copy()
+    for k in ['ptt', 'p_p']:
+        G, C = qest.eval_qe(k, q['lmax'], q['cls'], get_alm, q['nside'], q['lmax_qlm'], verbose=False)
+        assert rel_l2(G, gold['qe_gen_' + k]) < 1e-10
+        ref_c = gold['qe_gen_x' + k[1:]]
+        assert np.linalg.norm(C - ref_c) < 1e-10 * np.linalg.norm(gold['qe_gen_' + k])
+    G, C = qest.eval_qe('p', q['lmax'], q['cls'], get_alm, q['nside'], q['lmax_qlm'], verbose=False)
+    assert rel_l2(G, gold['qe_dd_p']) < 1e-10
+    # two different legs: symmetrised estimator equals the fast path's average of the two orderings
+    get_alm2 = lambda a: {'t': q['tlm2'], 'e': q['elm2'], 'b': q['blm2']}[a].copy()
+    G, C = qest.eval_qe('ptt', q['lmax'], q['cls'], get_alm, q['nside'], q['lmax_qlm'], verbose=False, get_alm2=get_alm2)
+    assert rel_l2(G, gold['qe_ds_ptt']) < 1e-10
+
+
+def test_qe_term_lists_match_reference_structure():
+    """qresp.get_qes: number of terms and leg spins for the lensing keys (host logic only)."""
+    from plancklens_b200 import qresp
+    cls = gi.toy_cls(20)
+    n = {k: len(qresp.get_qes(k, 20, cls)) for k in ['ptt', 'p_p', 'p', 'pee', 'p_eb']}
+    assert n['ptt'] == 1 and n['p_p'] == 4 and n['p'] == 9, n
+    for q in qresp.get_qes('p', 20, cls):
+        assert q.leg_a.spin_ou + q.leg_b.spin_ou == 1
