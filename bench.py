@@ -253,7 +253,8 @@ def main():
         dev_sims.append([p.cuda() for p in pins])
     ivfs = mem_ivfs(host_sims, cls, NSIDE)
     import tempfile
-    tmp = tempfile.mkdtemp(prefix='plk_bench_%d_' % rank)
+    # one lib_dir for all ranks (rank 0 writes the hash files, the others wait at the library's barrier)
+    tmp = os.path.join(tempfile.gettempdir(), 'plk_bench_%s_%s' % (os.environ.get('MASTER_PORT', 'single'), os.getppid()))
     lib = qest.library_sepTP(os.path.join(tmp, 'qlms_dd'), ivfs, ivfs, cls['te'], NSIDE, lmax_qlm=LMAX_QLM)
     f2 = lib.f2map2
     qe = lib._engine(LMAX_IVF)
