@@ -1,0 +1,89 @@
+"""GPU: the reference's pipeline shape end to end -- parameter file -> sims -> filtering library -> QE library --
+checked against the CPU oracle fed with the same simulated maps."""
+import importlib.util
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_params(name, env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, 'params', name + '.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_idealized_example_param_file(oracle_sht):
+    from oracle import ref_qe
+    from oracle.healpy_shim.healpy import almxfl
+    with tempfile.TemporaryDirectory() as tmp:
+        par = _load_params('idealized_example', {'PLENS': tmp, 'PLK_NSIDE': '64', 'PLK_LMAX_IVF': '96', 'PLK_LMAX_QLM': '128',
+                                                 'PLK_NSIMS': '4'})
+        G = par.qlms_dd.get_sim_qlm('p', 0)
+        Gtt = par.qlms_dd.get_sim_qlm('ptt', 0)
+        Gds = par.qlms_ds.get_sim_qlm('p_p', 1)
+        # oracle on the same simulated maps
+        def ivf(idx):
+            tmap = par.sims.get_sim_tmap(idx)
+            q, u = par.sims.get_sim_pmap(idx)
+            t = almxfl(oracle_sht.map2alm(tmap, lmax=par.lmax_ivf), par.ftl * np.where(par.transf > 0, 1 / par.transf, 0))
+            e, b = oracle_sht.map2alm_spin([q, u], 2, lmax=par.lmax_ivf)
+            fac = np.where(par.transf > 0, 1 / par.transf, 0)
+            return t, almxfl(e, par.fel * fac), almxfl(b, par.fbl * fac)
+        cls = {k: par.cl_len[k] for k in ['tt', 'ee', 'bb', 'te']}
+        t0, e0, b0 = ivf(0)
+        assert rel_l2(par.ivfs.get_sim_tlm(0), t0) < 1e-10 and rel_l2(par.ivfs.get_sim_elm(0), e0) < 1e-10
+        Gr, _ = ref_qe.qe('p', t0, e0, b0, cls, par.nside, par.lmax_qlm)
+        assert rel_l2(G, Gr) < 1e-10
+        Gr, _ = ref_qe.qe('ptt', t0, e0, b0, cls, par.nside, par.lmax_qlm)
+        assert rel_l2(Gtt, Gr) < 1e-10
+        # sim x data, symmetrised (data = index -1 -> simulation nsims)
+        t1, e1, b1 = ivf(1)
+        td, ed, bd = ivf(-1)
+        a = ref_qe.qe('p_p', t1, e1, b1, cls, par.nside, par.lmax_qlm, tbar2=td, ebar2=ed, bbar2=bd)
+        b = ref_qe.qe('p_p', td, ed, bd, cls, par.nside, par.lmax_qlm, tbar2=t1, ebar2=e1, bbar2=b1)
+        assert rel_l2(Gds, 0.5 * (a[0] + b[0])) < 1e-10
+        # cached on disk under the reference's file names
+        assert os.path.exists(os.path.join(tmp, 'temp', 'idealized_example', 'qlms_dd', 'sim_p_0000.fits'))
+        assert os.path.exists(os.path.join(tmp, 'temp', 'idealized_example', 'ivfs', 'sim_0000_tlm.fits'))
+
+
+def test_cg_filter_equals_isotropic_filter_on_full_sky():
+    """Known answer 7 of SURVEY.md section 8c: on an unmasked homogeneous-noise sky the CG solution equals the
+    isotropic filter  map2alm(d) / (C_l + N_l / b_l^2) / b_l  (filt_simple.py:397-400 vs filt_cinv.py:152-168)."""
+    from plancklens_b200 import hp, utils
+    from plancklens_b200.qcinv import cd_solve, multigrid, opfilt_tt, util_alm
+    import golden_inputs as gi
+    nside, lmax = 64, 128
+    rng = np.random.default_rng(0)
+    cls = gi.toy_cls(lmax)
+    transf = hp.gauss_beam(np.deg2rad(1.0), lmax=lmax)
+    npix = 12 * nside ** 2
+    ninv = np.full(npix, 1.0 / 50.0)
+    tmap = rng.standard_normal(npix) * 5
+    nf = opfilt_tt.alm_filter_ninv(ninv, transf, marge_monopole=False, marge_dipole=False)
+    descr = [[0, ["diag_cl"], lmax, nside, np.inf, 1.0e-9, cd_solve.tr_cg, cd_solve.cache_mem()]]
+    chain = multigrid.multigrid_chain(opfilt_tt, descr, cls, nf)
+    sol = util_alm.dalm.zeros(lmax)
+    chain.solve(sol, tmap)
+    nl = 4 * np.pi / npix / ninv[0]
+    iso = hp.almxfl(hp.map2alm(tmap, lmax=lmax, iter=0), utils.cli(cls['tt'] + nl * utils.cli(transf ** 2)) * utils.cli(transf))
+    ls = gi.alm_ls(lmax)
+    sel = (ls >= 2) & (ls <= nside)        # band-limited part, where HEALPix quadrature is accurate
+    assert rel_l2(sol.numpy()[sel], iso[sel]) < 2e-3
