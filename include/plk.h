@@ -89,6 +89,12 @@ int plk_almxfl_dev(int lmax, const void *in, const double *fl, int nfl, void *ou
 int plk_alm_axpy_dev(long long n, double a, const double *a_dev, const void *x, void *y, void *stream);
 /* result_dev[0] = sum_{l>=lmin} [ a_l0 b_l0 + 2 sum_{m>0} Re(a_lm conj b_lm) ]  (opfilt_tt/pp dot_op) */
 int plk_alm_dot_dev(int lmax, int lmin, const void *a, const void *b, double *result_dev, void *stream);
+/* two-component form (opfilt_pp.py:27-34: E and B summed), one device scalar */
+int plk_alm_dot2_dev(int lmax, int lmin, const void *a1, const void *b1, const void *a2, const void *b2,
+                     double *result_dev, void *stream);
+/* out_dev[0] = scale * num_dev[0] / den_dev[0]: CG step lengths (cd_solve.py:69-71, :95-99) kept on the device so that
+ * the fixed-iteration multigrid stages (multigrid.py:185-215) run without host synchronisation (CUDA-graph capturable) */
+int plk_scalar_ratio_dev(const double *num, const double *den, double scale, double *out, void *stream);
 /* copy with change of lmax (zero fill above lmax_in) */
 int plk_alm_copy_dev(int lmax_in, const void *in, int lmax_out, void *out, void *stream);
 /* out (lmax_hi) = lo for l <= lsplit, hi for l > lsplit */

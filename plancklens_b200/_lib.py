@@ -28,6 +28,8 @@ _SIGS = {
     'plk_almxfl_dev': (c_int, [c_int, vp, vp, c_int, vp, vp]),
     'plk_alm_axpy_dev': (c_int, [c_ll, c_dbl, vp, vp, vp, vp]),
     'plk_alm_dot_dev': (c_int, [c_int, c_int, vp, vp, vp, vp]),
+    'plk_alm_dot2_dev': (c_int, [c_int, c_int, vp, vp, vp, vp, vp, vp]),
+    'plk_scalar_ratio_dev': (c_int, [vp, vp, c_dbl, vp, vp]),
     'plk_alm_copy_dev': (c_int, [c_int, vp, c_int, vp, vp]),
     'plk_alm_splice_dev': (c_int, [c_int, vp, c_int, vp, c_int, vp, vp]),
     'plk_alm_lincomb_dev': (c_int, [c_ll, c_dbl, vp, c_dbl, vp, vp, vp]),
@@ -59,7 +61,7 @@ def load(path=None):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = path or _build.SO
+    path = path or os.environ.get('PLK_LIB_PATH') or _build.SO
     if not os.path.exists(path):
         raise PlkError("libplk_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "or `python -m plancklens_b200._build`; there is no CPU fallback." % path)

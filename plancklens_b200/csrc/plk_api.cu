@@ -192,10 +192,11 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
     for (int ip = 0; ip < hg.npair; ++ip) by_m[M[ip]].push_back(ip);
     std::vector<int> list;
     const int nb4_maxm = env_int("PLK_FFT_NB4_MAXM", 1024);
+    const int nb1_minm = env_int("PLK_FFT_NB1_MINM", 8192);   // M = 8192 (nside 4096 caps): one DFT buffer only
     for (auto it = by_m.rbegin(); it != by_m.rend(); ++it) {     // largest transforms first
       plk_plan::FftClass c;
       c.M = it->first; c.offset = (int)list.size(); c.count = (int)it->second.size();
-      c.nbatch = c.M == 0 ? 0 : (c.M <= nb4_maxm ? 4 : 2);
+      c.nbatch = c.M == 0 ? 0 : (c.M >= nb1_minm ? 1 : (c.M <= nb4_maxm ? 4 : 2));
       c.smem = c.M == 0 ? 0 : (c.nbatch * c.M + c.M / 4) * (int)sizeof(cplx);
       c.threads = (c.nbatch * c.M / 16 >= 512) ? 512 : 256;   // one radix-16 butterfly per thread and pass
       p->fft_smem = std::max(p->fft_smem, c.smem);
@@ -276,11 +277,13 @@ extern "C" long long plk_plan_device_bytes(const plk_plan *p) {
 extern "C" int plk_plan_nside(const plk_plan *p) { return p ? p->nside : 0; }
 extern "C" int plk_plan_lmax(const plk_plan *p) { return p ? p->lmax : 0; }
 
+static int leg_attrs();
 // per-spin recurrence tables + seeds (built on first use)
 static int ensure_spin(plk_plan *p, int spin) {
   if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
   SpinDev &sd = p->spins[spin];
   if (sd.ready) return 0;
+  { int rca = leg_attrs(); if (rca) return rca; }
   SpinTables t = make_spin_tables(spin, p->lmax, p->mmax);
   const size_t n = t.U.size();
   std::vector<double2> uv(n);
@@ -322,11 +325,16 @@ static int ensure_spin(plk_plan *p, int spin) {
 
 // ------------------------------------------------------------------------------------------ Legendre launches
 template <bool SPIN, bool SYNTH>
-static size_t leg_smem() {
+static size_t leg_smem(int nr) {
   size_t s = 128 + (size_t)kStages * StageBytes<SPIN, SYNTH>::stage;
   if (!SYNTH) s += (size_t)2 * kNCW * kChunk * (SPIN ? 4 : 2) * sizeof(double);
+  if (SYNTH || !SPIN) s += (size_t)nr * (SPIN ? 4 : 2) * kNCW * 32 * sizeof(double);     // seeds
   return s;
 }
+// Every variant fits the default 48 KB dynamic shared memory limit.  Do NOT raise
+// cudaFuncAttributeMaxDynamicSharedMemorySize "just in case": it moves the L1 / shared carve-out and slowed the
+// spin-s analysis kernel (divergent seed loads living in L1) from 10.4 to 11.9 ms on B200.
+static int leg_attrs() { return 0; }
 static int pick_nr(const plk_plan *p, int nrmax) {
   // enough blocks to cover the SMs a few times over; small grids get fewer pairs per thread
   int nr = nrmax;
@@ -338,22 +346,39 @@ static int pick_nr(const plk_plan *p, int nrmax) {
   return nr;
 }
 
+// Work buffers have ONE size per plan (the largest any spin needs): pointers baked into captured CUDA graphs
+// (qcinv multigrid stages) must never be invalidated by a later call with another spin.
+static int ensure_work(plk_plan *p) {
+  const size_t nalm = (size_t)alm_size(p->lmax, p->mmax);
+  int rc;
+  if ((rc = ensure(p->rec, nalm * 32 + 64))) return rc;
+  size_t pb = 0;
+  for (int sp = 0; sp < 2; ++sp) {
+    const int nr = pick_nr(p, sp ? env_int("PLK_NR_ANAS", 2) : env_int("PLK_NR_ANA0", 4));
+    const size_t ntile = (p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr);
+    pb = std::max(pb, ntile * nalm * (sp ? 4 : 2) * sizeof(double));
+  }
+  if ((rc = ensure(p->part, pb))) return rc;
+  const size_t b = (size_t)p->nring * p->pitch * sizeof(cplx);
+  if ((rc = ensure(p->X1, b)) || (rc = ensure(p->X2, b))) return rc;
+  return 0;
+}
+
 static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *alm2, const double *fl1,
                           const double *fl2, cplx *X1, cplx *X2, cudaStream_t st) {
   int rc = ensure_spin(p, spin);
   if (rc) return rc;
   const DevSpin &d = p->spins[spin].d;
-  const size_t nalm = (size_t)alm_size(p->lmax, p->mmax);
-  if ((rc = ensure(p->rec, nalm * (spin ? 32 : 16) + 64))) return rc;
+  if ((rc = ensure_work(p))) return rc;
   dim3 pg((p->lmax + 256) / 256, p->mmax + 1);
   if (spin == 0) prep_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, nullptr, fl1, nullptr, p->rec.p);
   else prep_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, (const cplx *)alm2, fl1, fl2, p->rec.p);
   LAUNCHED();
-  const int nr = pick_nr(p, spin ? env_int("PLK_NR_SYNS", 2) : env_int("PLK_NR_SYN0", 4));
+  const int nr = pick_nr(p, spin ? env_int("PLK_NR_SYNS", 4) : env_int("PLK_NR_SYN0", 4));
   dim3 grid((p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr), p->mmax + 1);
   const int nthr = (kNCW + 1) * 32;
 #define SYN(SP, NR)                                                                                              \
-  legendre_synth_kernel<SP, NR><<<grid, nthr, leg_smem<SP, true>(), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, p->morder)
+  legendre_synth_kernel<SP, NR><<<grid, nthr, leg_smem<SP, true>(NR), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, p->morder)
   prof_begin(spin ? 1 : 0, st);
   if (spin == 0) {
     if (nr == 4) SYN(false, 4); else if (nr == 2) SYN(false, 2); else SYN(false, 1);
@@ -376,11 +401,11 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   const int nr = pick_nr(p, spin ? env_int("PLK_NR_ANAS", 2) : env_int("PLK_NR_ANA0", 4));
   const int ntile = (p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr);
   const long long stride = (long long)nalm * nv;
-  if ((rc = ensure(p->part, (size_t)ntile * stride * sizeof(double)))) return rc;
+  if ((rc = ensure_work(p))) return rc;
   dim3 grid(ntile, p->mmax + 1);
   const int nthr = (kNCW + 1) * 32;
 #define ANA(SP, NR)                                                                                              \
-  legendre_anal_kernel<SP, NR><<<grid, nthr, leg_smem<SP, false>(), st>>>(p->g, d, X1, X2, p->pitch, (double *)p->part.p, stride, p->morder, env_int("PLK_DBG_ANA", 0))
+  legendre_anal_kernel<SP, NR><<<grid, nthr, leg_smem<SP, false>(NR), st>>>(p->g, d, X1, X2, p->pitch, (double *)p->part.p, stride, p->morder, env_int("PLK_DBG_ANA", 0))
   prof_begin(spin ? 3 : 2, st);
   if (spin == 0) {
     if (nr == 4) ANA(false, 4); else if (nr == 2) ANA(false, 2); else ANA(false, 1);
@@ -418,13 +443,7 @@ static int ring_anal(plk_plan *p, const double *map, cplx *X, cudaStream_t st, c
   }
   return 0;
 }
-static int ensure_phase(plk_plan *p, int ncomp) {
-  const size_t b = (size_t)p->nring * p->pitch * sizeof(cplx);
-  int rc = ensure(p->X1, b);
-  if (rc) return rc;
-  if (ncomp > 1 && (rc = ensure(p->X2, b))) return rc;
-  return 0;
-}
+static int ensure_phase(plk_plan *p, int /*ncomp*/) { return ensure_work(p); }
 
 #define CHECK_PLAN(p) do { if (!(p)) return fail(PLK_EINVAL, "plan is NULL"); } while (0)
 
@@ -558,6 +577,26 @@ extern "C" int plk_alm_dot_dev(int lmax, int lmin, const void *a, const void *b,
   dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a, (const cplx *)b, g_scratch);
   LAUNCHED();
   final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, lmax + 1, 1, result_dev);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_dot2_dev(int lmax, int lmin, const void *a1, const void *b1, const void *a2, const void *b2,
+                                double *result_dev, void *stream) {
+  if (!a1 || !b1 || !a2 || !b2 || !result_dev || lmax < 0) return fail(PLK_EINVAL, "bad argument");
+  int rc = scratch();
+  if (rc) return rc;
+  if (2 * ((size_t)lmax + 1) > kScratchDoubles) return fail(PLK_EINVAL, "lmax too large");
+  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a1, (const cplx *)b1, g_scratch);
+  LAUNCHED();
+  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a2, (const cplx *)b2, g_scratch + lmax + 1);
+  LAUNCHED();
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, 2 * (lmax + 1), 1, result_dev);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_scalar_ratio_dev(const double *num, const double *den, double scale, double *out, void *stream) {
+  if (!num || !den || !out) return fail(PLK_EINVAL, "NULL buffer");
+  scalar_ratio_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(num, den, scale, out);
   LAUNCHED();
   return PLK_OK;
 }

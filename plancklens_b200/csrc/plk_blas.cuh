@@ -138,6 +138,12 @@ __global__ void final_sum_kernel(const double *__restrict__ partial, int n, int 
   }
 }
 
+// out[0] = scale * num[0] / den[0]: the CG step lengths (cd_solve.py:69-71, :95-99) without a host round trip
+__global__ void scalar_ratio_kernel(const double *__restrict__ num, const double *__restrict__ den, double scale,
+                                    double *__restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = scale * (num[0] / den[0]);
+}
+
 __global__ void alm_copy_kernel(int lmax_in, const cplx *__restrict__ in, int lmax_out, cplx *__restrict__ out) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;

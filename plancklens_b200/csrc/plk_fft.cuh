@@ -306,6 +306,37 @@ PLK_HD void ring_synth_body(Ctx ctx, const DevFFT &f, int ip, const cplx *X, int
   const cplx *Vq = (f.voff[ip] >= 0) ? f.V + f.voff[ip] : nullptr;
   cplx *tws = smem, *buf = smem + (M >> 2);
   load_twiddles(ctx, tws, M, f.W, f.Wn);
+  if (nbatch == 1) {
+    // one DFT at a time (M = 8192 at nside 4096: two buffers do not fit in shared memory); the fold is redone for
+    // a = 1 -- cheaper than a global-memory stash, and these are the long rings where little aliasing happens
+    for (int pass = 0; pass < 2 * nhalf; ++pass) {
+      const int half = pass >> 1, a = pass & 1;
+      const cplx *Xr = X + (size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch;
+      for (int i = ctx.tid(); i < M; i += ctx.nthr()) {
+        cplx e = mk(0.0, 0.0);
+        if (i < q) {
+          cplx e0, e1;
+          synth_input2(Xr, mmax, n, q, i, shifted, e0, e1);
+          e = a ? e1 : e0;
+          if (M != q) e = e * chirp(i, q);
+        }
+        buf[SW(i)] = e;
+      }
+      ctx.sync();
+      idft_q(ctx, buf, 1, q, M, tws, Vq);
+      double *out0 = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]) + 2 * a;
+      for (int t = ctx.tid(); t < q; t += ctx.nthr()) {
+        const cplx y = fetchZ(buf, t, q, M, bits);
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<double2 *>(out0 + 4 * t) = make_double2(y.x, y.y);
+#else
+        out0[4 * t] = y.x; out0[4 * t + 1] = y.y;
+#endif
+      }
+      ctx.sync();
+    }
+    return;
+  }
   const int hstep = nbatch >= 4 ? 2 : 1;
   for (int h0 = 0; h0 < nhalf; h0 += hstep) {
     const int nh = (nhalf - h0) < hstep ? (nhalf - h0) : hstep;
@@ -360,6 +391,41 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
   const cplx *Vq = (f.voff[ip] >= 0) ? f.V + f.voff[ip] : nullptr;
   cplx *tws = smem, *buf = smem + (M >> 2);
   load_twiddles(ctx, tws, M, f.W, f.Wn);
+  if (nbatch == 1) {
+    // one DFT at a time (see ring_synth_body): pass a = 0 writes S^(0) + w S^(1), pass a = 1 adds w^2 S^(2) + w^3 S^(3);
+    // the same thread owns the same X element in both passes
+    for (int pass = 0; pass < 2 * nhalf; ++pass) {
+      const int half = pass >> 1, a = pass & 1;
+      const double *in0 = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]) + 2 * a;
+      for (int i = ctx.tid(); i < M; i += ctx.nthr()) {
+        cplx v = mk(0.0, 0.0);
+        if (i < q) {
+          v = mk(in0[4 * i], -in0[4 * i + 1]);
+          if (M != q) v = v * chirp(i, q);
+        }
+        buf[SW(i)] = v;
+      }
+      ctx.sync();
+      idft_q(ctx, buf, 1, q, M, tws, Vq);
+      cplx *Xr = X + (size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch;
+      for (int m = ctx.tid(); m <= mmax; m += ctx.nthr()) {
+        const int jn = m / n, k = m - jn * n;
+        const int kp = k % q, kq = (q - kp) % q;
+        const cplx Y = conj(fetchZ(buf, kp, q, M, bits)), Yc = fetchZ(buf, kq, q, M, bits);
+        const cplx Se = 0.5 * (Y + Yc), So = mul_mi(0.5 * (Y - Yc));
+        const cplx g = expipi32(-k, n);
+        const cplx g2 = g * g;
+        cplx D = Se + g2 * So;
+        if (a) D = (g2 * g2) * D;
+        cplx ph = mk(wgt, 0.0);
+        if (shifted) ph = ((jn & 1) ? -wgt : wgt) * g;
+        const cplx r = ph * D;
+        Xr[m] = a ? Xr[m] + r : r;
+      }
+      ctx.sync();
+    }
+    return;
+  }
   const int hstep = nbatch >= 4 ? 2 : 1;
   for (int h0 = 0; h0 < nhalf; h0 += hstep) {
     const int nh = (nhalf - h0) < hstep ? (nhalf - h0) : hstep;

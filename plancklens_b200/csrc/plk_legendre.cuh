@@ -15,7 +15,16 @@
 
 namespace plk {
 
-constexpr int kChunk = 128;      // l values per TMA stage (even)
+#ifndef PLK_CHUNK
+#define PLK_CHUNK 128
+#endif
+#ifndef PLK_SYN_MINB
+#define PLK_SYN_MINB 1
+#endif
+#ifndef PLK_ANA_MINB
+#define PLK_ANA_MINB 1
+#endif
+constexpr int kChunk = PLK_CHUNK;      // l values per TMA stage (even)
 constexpr int kStages = 4;
 constexpr int kNCW = 4;          // compute warps per block
 constexpr int kSeedThrExp = -120;  // accumulation starts once |p_l| >= 2^-120 (libsharp itself uses 2^-60)
@@ -214,7 +223,7 @@ PLK_D void producer_loop(unsigned char *stage_base, uint64_t *full, uint64_t *em
 //   H+ = -1/2 alpha (G + iC),  H- = -1/2 (-1)^s alpha (G - iC)        (prepared by prep_alm_kernel)
 // output phase arrays X1 (, X2): [ring][pitch] complex, map(phi) = X_0 + 2 Re sum_{m>0} X_m e^{i m phi}
 template <bool SPIN, int NR>
-__global__ void __launch_bounds__((kNCW + 1) * 32)
+__global__ void __launch_bounds__((kNCW + 1) * 32, PLK_SYN_MINB)
 legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *__restrict__ X1, cplx *__restrict__ X2,
                       int pitch, const int *__restrict__ morder) {
   using SB = StageBytes<SPIN, true>;
@@ -223,6 +232,10 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
   uint64_t *empty = full + kStages;
   int *s_kmin = reinterpret_cast<int *>(empty + kStages);
   unsigned char *stage_base = smem + 128;
+  // start values of every ring pair of the block, thread-private slots [j][component][thread]: the in-loop
+  // injection then costs one LDS instead of a divergent global load that stalls the whole warp
+  double *sseed = reinterpret_cast<double *>(stage_base + (size_t)kStages * SB::stage);
+  constexpr int NSD = SPIN ? 4 : 2;
 
   const int m = morder[blockIdx.y];
   const int s = t.spin, lmax = t.lmax;
@@ -243,17 +256,22 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
   // per-thread ring-pair state
   int ks[NR];
   double x[NR];
-  size_t so[NR];
   int kw_min = 1 << 30, kw_max = -1;
+  double *sd = sseed + threadIdx.x;
   if (warp < kNCW) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
       const int ip = pair0 + 32 * j;
       if (ip < g.npair) {
-        so[j] = (size_t)m * g.npair + ip;
-        ks[j] = t.ks[so[j]];
+        const size_t so = (size_t)m * g.npair + ip;
+        ks[j] = t.ks[so];
         x[j] = g.cth[ip];
-      } else { so[j] = 0; ks[j] = 1 << 30; x[j] = 0.0; }
+        if (ks[j] < K) {
+          sd[(j * NSD + 0) * (kNCW * 32)] = t.s0[so];
+          sd[(j * NSD + 1) * (kNCW * 32)] = t.s1[so];
+          if (SPIN) { sd[(j * NSD + 2) * (kNCW * 32)] = t.s2[so]; sd[(j * NSD + 3) * (kNCW * 32)] = t.s3[so]; }
+        }
+      } else { ks[j] = 1 << 30; x[j] = 0.0; }
       if (ks[j] < K) { kw_min = min(kw_min, ks[j]); kw_max = max(kw_max, ks[j]); }
     }
 #pragma unroll
@@ -308,8 +326,8 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
 #pragma unroll
           for (int j = 0; j < NR; ++j)
             if (k == ks[j]) {
-              pm_[j] = t.s0[so[j]]; pc_[j] = t.s1[so[j]];
-              if (SPIN) { qm_[j] = t.s2[so[j]]; qc_[j] = t.s3[so[j]]; }
+              pm_[j] = sd[(j * NSD + 0) * (kNCW * 32)]; pc_[j] = sd[(j * NSD + 1) * (kNCW * 32)];
+              if (SPIN) { qm_[j] = sd[(j * NSD + 2) * (kNCW * 32)]; qc_[j] = sd[(j * NSD + 3) * (kNCW * 32)]; }
             }
         }
         const int kk = k - k0;
@@ -412,7 +430,7 @@ PLK_D void butterfly16(double (&v)[16], int lane) {
 }
 
 template <bool SPIN, int NR>
-__global__ void __launch_bounds__((kNCW + 1) * 32)
+__global__ void __launch_bounds__((kNCW + 1) * 32, (SPIN && NR == 2) ? 3 : PLK_ANA_MINB)   // 3 blocks/SM: <= 136 registers
 legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cplx *__restrict__ X2, int pitch,
                      double *__restrict__ part, long long part_stride /* doubles per tile */,
                      const int *__restrict__ morder, int dbg) {
@@ -425,6 +443,9 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
   int *s_kmin = reinterpret_cast<int *>(empty + kStages);
   unsigned char *stage_base = smem + 128;
   double *red = reinterpret_cast<double *>(stage_base + (size_t)kStages * SB::stage);  // [2][kNCW][kChunk*NV]
+  double *sseed = red + (size_t)2 * kNCW * kChunk * NV;     // [j][component][thread] start values (see synthesis)
+  constexpr int NSD = SPIN ? 4 : 2;
+  constexpr bool SEED_SMEM = !SPIN;   // measured on B200: helps spin 0 (4.47 -> 3.98 ms), hurts spin s (10.4 -> 11.6 ms)
 
   const int m = morder[blockIdx.y];
   const int s = t.spin, lmax = t.lmax;
@@ -445,7 +466,8 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
 
   int ks[NR];
   double x[NR];
-  size_t so[NR];
+  size_t so_[NR];
+  double *sd = sseed + threadIdx.x;
   // lane-permuted ring constants.  spin s: fa[vs] multiplies p+, fb[vs] multiplies p-, component v = vs ^ hi of
   //   (S+re, S+im, S-re, S-im):  A = (F+n.re, F+n.im, sF-s.re, sF-s.im), B = (sF+s.re, sF+s.im, F-n.re, F-n.im)
   // spin 0: fa[vs] = (fe.re, fe.im)[vs ^ hi] used at even offsets, fb[vs] = (fo.re, fo.im)[vs ^ hi] at odd ones
@@ -458,11 +480,16 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
       const int ip = pair0 + 32 * j;
       double A[4] = {0.0, 0.0, 0.0, 0.0}, B[4] = {0.0, 0.0, 0.0, 0.0};
       if (ip < g.npair) {
-        so[j] = (size_t)m * g.npair + ip;
-        ks[j] = t.ks[so[j]];
+        const size_t so = (size_t)m * g.npair + ip;
+        ks[j] = t.ks[so];
         x[j] = g.cth[ip];
         const int rn = ip, rs = g.nring - 1 - ip;
+        so_[j] = so;
         if (ks[j] < K) {
+          if (SEED_SMEM) {
+            sd[(j * NSD + 0) * (kNCW * 32)] = t.s0[so];
+            sd[(j * NSD + 1) * (kNCW * 32)] = t.s1[so];
+          }
           const cplx n1 = X1[(size_t)rn * pitch + m];
           const cplx s1 = (rs != rn) ? X1[(size_t)rs * pitch + m] : mk(0.0, 0.0);
           if (!SPIN) {
@@ -478,7 +505,7 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
             A[2] = sg0 * (s1.x + s2.y); A[3] = sg0 * (s1.y - s2.x);         // sigma0 F- south
           }
         }
-      } else { so[j] = 0; ks[j] = 1 << 30; x[j] = 0.0; }
+      } else { ks[j] = 1 << 30; x[j] = 0.0; so_[j] = 0; }
 #pragma unroll
       for (int vs = 0; vs < NV; ++vs) {
         // static-index selection of A[vs ^ hi]
@@ -542,8 +569,12 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
 #pragma unroll
               for (int j = 0; j < NR; ++j)
                 if (k == ks[j]) {
-                  pm_[j] = t.s0[so[j]]; pc_[j] = t.s1[so[j]];
-                  if (SPIN) { qm_[j] = t.s2[so[j]]; qc_[j] = t.s3[so[j]]; }
+                  if (SEED_SMEM) {
+                    pm_[j] = sd[(j * NSD + 0) * (kNCW * 32)]; pc_[j] = sd[(j * NSD + 1) * (kNCW * 32)];
+                  } else {
+                    pm_[j] = t.s0[so_[j]]; pc_[j] = t.s1[so_[j]];
+                    if (SPIN) { qm_[j] = t.s2[so_[j]]; qc_[j] = t.s3[so_[j]]; }
+                  }
                 }
             }
             // reads past kend stay inside the stage buffer; those offsets are never written out

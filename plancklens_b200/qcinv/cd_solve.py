@@ -45,6 +45,42 @@ def _axpy(y, a, x):
     return y
 
 
+def can_solve_fixed(pre_ops, dot_op, tr, iter_max, eps_min):
+    """True when cd_solve_fixed reproduces cd_solve: one preconditioner, standard PCG recurrence (tr_cg), a
+    convergence test that can never fire (eps_min = 0) and a finite iteration count."""
+    return (len(pre_ops) == 1 and tr is tr_cg and eps_min == 0.0 and np.isfinite(iter_max)
+            and hasattr(dot_op, 'dev'))
+
+
+def cd_solve_fixed(x, b, fwd_op, pre_ops, dot_op, niter, roundoff=25):
+    """cd_solve for the inner multigrid stages (iter_max iterations, eps_min = 0, tr_cg; reference
+    multigrid.py:185-215 with the chains of filt_cinv.py:113-116): the same updates in the same order, with the
+    step lengths alpha = (d.r)/(d.Ad) and beta = (d'.Ad)/(d.Ad) kept in device memory (plk_scalar_ratio_dev), so the
+    whole solve is a fixed sequence of kernel launches with no host synchronisation -- it can be captured in a
+    CUDA graph.  The residual-norm evaluations of the monitor (only logged, never acted on when eps_min = 0)
+    and the search direction computed after the last update (never used) are skipped; x is bit-identical."""
+    from .. import sht
+    (pre_op,) = pre_ops
+    niter = int(niter)
+    # A 0 = 0: skip the operator on the zero start vector the multigrid stages use (opfilt_tt.py:68 does the same)
+    residual = b.copy() if (hasattr(x, 'is_zero') and x.is_zero()) else b - fwd_op(x)
+    d = pre_op(residual)
+    for it in range(1, niter + 1):
+        Ad = fwd_op(d)
+        delta = dot_op.dev(d, residual)
+        dTAd = dot_op.dev(d, Ad)
+        x = _axpy(x, sht.scalar_ratio(delta, dTAd), d)
+        if it == niter:
+            break
+        if it % roundoff == 0:
+            residual = b - fwd_op(x)
+        else:
+            residual = _axpy(residual, sht.scalar_ratio(delta, dTAd, -1.0), Ad)
+        dn = pre_op(residual)
+        d = _axpy(dn, sht.scalar_ratio(dot_op.dev(dn, Ad), dTAd, -1.0), d)
+    return niter
+
+
 def cd_solve(x, b, fwd_op, pre_ops, dot_op, criterion, tr, cache=None, roundoff=25):
     """Solves x = fwd_op^{-1} b in place; returns the iteration count.
 

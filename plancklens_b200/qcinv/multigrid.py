@@ -5,10 +5,12 @@ mini-language -- `split(low, lsplit, high)`, `diag_cl`, `dense`, `dense(file)`, 
 (multigrid.py:37, :113-160).  All vectors stay on the GPU from `calc_prep` to `apply_fini`.
 """
 import copy
+import os
 import re
 import sys
 
 import numpy as np
+import torch
 
 from . import cd_monitors, cd_solve, util, util_alm
 
@@ -45,6 +47,11 @@ class multigrid_chain:
                                                                n_inv_filt=self.n_inv_filt, stages=stages,
                                                                lmax=lmax, nside=nside, chain=self))
         self.bstage = stages[0]
+        # B200: the fixed-iteration inner stages are a static launch sequence (cd_solve_fixed); replay them as one
+        # CUDA graph per preconditioner call instead of a few thousand ctypes launches (PLK_CG_GRAPH=0 disables)
+        if os.environ.get('PLK_CG_GRAPH', '1') != '0':
+            self.bstage.pre_ops = [graphed_op(op) if (_has_stage(op) and _graph_safe(op)) else op
+                                   for op in self.bstage.pre_ops]
 
     def solve(self, soltn, tpn_map, apply_fini='', dot_op=None):
         """soltn <- inverse-variance filtered solution for the data map(s) tpn_map.
@@ -84,6 +91,63 @@ class multigrid_chain:
                 log.write(log_str)
             with open(self.debug_log_prefix + 'stage_' + str(stage.depth) + '.dat', 'a') as log:
                 log.write('%05d %05d %10.6e %05d %s\n' % (self.iter_tot, int(elapsed), eps, iter, str(elapsed)))
+
+
+def _has_stage(op):
+    if isinstance(op, pre_op_split):
+        return _has_stage(op.pre_op_low) or _has_stage(op.pre_op_hgh)
+    return isinstance(op, pre_op_multigrid)
+
+
+def _graph_safe(op):
+    """True when applying `op` never synchronises with the host (so it can be stream-captured)."""
+    if isinstance(op, pre_op_split):
+        return _graph_safe(op.pre_op_low) and _graph_safe(op.pre_op_hgh)
+    if isinstance(op, pre_op_multigrid):
+        return op.fixed and all(_graph_safe(p) for p in op.pre_ops)
+    return type(op).__name__ in ('pre_op_diag', 'pre_op_dense_tt', 'pre_op_dense_pp')
+
+
+def _vec_tensors(v):
+    return [v.t] if isinstance(v, util_alm.dalm) else [v.elm.t, v.blm.t]
+
+
+def _vec_clone(v):
+    if isinstance(v, util_alm.dalm):
+        return util_alm.dalm(v.t.clone(), v.lmax, v.zero)
+    return util_alm.eblm([_vec_clone(v.elm), _vec_clone(v.blm)])
+
+
+class graphed_op:
+    """Applies a host-synchronisation-free preconditioner through a CUDA graph.
+
+    Call 1 runs eagerly (plans, tables and per-l factors get allocated and uploaded); call 2 is captured
+    (torch.cuda.graph on the launching stream: every kernel is a libplk_b200 launch); later calls copy the
+    argument into the captured input, replay, and return a copy of the captured output."""
+
+    def __init__(self, op):
+        self.op = op
+        self.calls = 0
+        self.graph = None
+        self.v_in = self.v_out = None
+
+    def __call__(self, v):
+        return self.calc(v)
+
+    def calc(self, v):
+        self.calls += 1
+        if self.calls == 1:
+            return self.op(v)
+        if self.graph is None:
+            self.v_in = _vec_clone(v)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.v_out = self.op(self.v_in)
+            self.graph = g
+        for dst, src in zip(_vec_tensors(self.v_in), _vec_tensors(v)):
+            dst.copy_(src)
+        self.graph.replay()
+        return _vec_clone(self.v_out)
 
 
 def _to_device(soltn):
@@ -178,11 +242,18 @@ class pre_op_multigrid:
         self.cache = cache
         self.iter_max = iter_max
         self.eps_min = eps_min
+        self.fixed = cd_solve.can_solve_fixed(pre_ops, opfilt.dot_op(), tr, iter_max, eps_min) \
+            and os.environ.get('PLK_CG_FIXED', '1') != '0'
 
     def __call__(self, talm):
         return self.calc(talm)
 
     def calc(self, talm):
+        if self.fixed:
+            soltn = talm * 0.0
+            cd_solve.cd_solve_fixed(soltn, util_alm.alm_copy(talm, lmax=self.lmax), self.fwd_op, self.pre_ops,
+                                    self.opfilt.dot_op(), self.iter_max)
+            return util_alm.alm_splice(soltn, talm, self.lmax)
         monitor = cd_monitors.monitor_basic(self.opfilt.dot_op(), iter_max=self.iter_max, eps_min=self.eps_min,
                                             logger=self.logger)
         soltn = talm * 0.0

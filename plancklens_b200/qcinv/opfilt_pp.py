@@ -53,6 +53,11 @@ class dot_op:
         b = sht.alm_dot(alm1.blm.t, alm2.blm.t, lmin=2)
         return float(e.item()) + float(b.item())
 
+    def dev(self, alm1, alm2):
+        """same number as a 1-element device tensor: no host synchronisation (fixed-iteration multigrid stages)"""
+        assert alm1.lmax == alm2.lmax
+        return sht.alm_dot2(alm1.elm.t, alm2.elm.t, alm1.blm.t, alm2.blm.t, lmin=2)
+
 
 class _lmat2:
     """Per-l symmetric 2x2 matrix applied to an (E, B) pair: one four-term combine per component."""

@@ -63,6 +63,11 @@ class dot_op:
         assert alm1.lmax == alm2.lmax
         return float(sht.alm_dot(alm1.t, alm2.t, lmin=0).item())
 
+    def dev(self, alm1, alm2):
+        """same number as a 1-element device tensor: no host synchronisation (fixed-iteration multigrid stages)"""
+        assert alm1.lmax == alm2.lmax
+        return sht.alm_dot(alm1.t, alm2.t, lmin=0)
+
 
 class fwd_op:
     """A x = C_l^{-1} x + B^t N^{-1} B x  (reference: opfilt_tt.py:54-73)."""

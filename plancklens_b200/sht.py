@@ -221,6 +221,22 @@ def alm_dot(a, b, lmin=0, out=None):
     return out
 
 
+def alm_dot2(a1, b1, a2, b2, lmin=0, out=None):
+    """sum of the two weighted dot products (E and B of an eblm pair) as one device scalar"""
+    lib = _lib.load()
+    lmax = alm_lmax(a1.numel())
+    out = torch.empty(1, dtype=torch.float64, device='cuda') if out is None else out
+    check(lib.plk_alm_dot2_dev(lmax, lmin, _ptr(a1), _ptr(b1), _ptr(a2), _ptr(b2), _ptr(out), _stream()))
+    return out
+
+
+def scalar_ratio(num, den, scale=1.0, out=None):
+    """scale * num / den on 1-element device tensors (no host synchronisation)"""
+    out = torch.empty(1, dtype=torch.float64, device='cuda') if out is None else out
+    check(_lib.load().plk_scalar_ratio_dev(_ptr(num), _ptr(den), float(scale), _ptr(out), _stream()))
+    return out
+
+
 def alm_copy(alm, lmax_out):
     lib = _lib.load()
     lmax_in = alm_lmax(alm.numel())

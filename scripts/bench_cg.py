@@ -11,11 +11,36 @@ from golden_inputs import pix_z
 from plancklens_b200 import hp, sht, utils
 from plancklens_b200.filt import filt_cinv
 
+from plancklens_b200.qcinv import util_alm
+
+
+def times_ms(chain, v):
+    """device time of one forward operator and one preconditioner application of the top stage"""
+    fwd = chain.opfilt.fwd_op(chain.s_cls, chain.n_inv_filt)
+    if a.profile_pre_op:     # ncu --profile-from-start off: one eager application of the top-level preconditioner
+        op = chain.bstage.pre_ops[0]
+        op = getattr(op, 'op', op)
+        op(v); torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        op(v); torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    for name, op in (('fwd_op', fwd), ('pre_op', chain.bstage.pre_ops[0])):
+        op(v); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            op(v)
+        e1.record(); torch.cuda.synchronize()
+        print('   %s: %.2f ms' % (name, e0.elapsed_time(e1) / 3))
+
+
 ap = argparse.ArgumentParser()
 ap.add_argument('--nside', type=int, default=2048)
 ap.add_argument('--lmax', type=int, default=2048)
 ap.add_argument('--pol', action='store_true')
 ap.add_argument('--skip-t', action='store_true')
+ap.add_argument('--profile-pre-op', action='store_true')
 a = ap.parse_args()
 nside, lmax = a.nside, a.lmax
 npix = 12 * nside ** 2
@@ -59,11 +84,17 @@ if not a.skip_t:
     cinv_t = filt_cinv.cinv_t(os.path.join(tmp, 'cinv_t'), lmax, nside, cls, transf, [ninv_t], marge_monopole=True, marge_dipole=True)
     _ = cinv_t.chain.bstage     # instantiate (dense preconditioner build included)
     torch.cuda.synchronize(); t_setup = time.time() - t0
+    tlm = cinv_t.apply_ivf(tmap)       # first solve: plans, tables, CUDA-graph capture of the preconditioner
+    torch.cuda.synchronize()
     n0 = sht._lib.launch_count(); t0 = time.time()
     tlm = cinv_t.apply_ivf(tmap)
     torch.cuda.synchronize(); dt = time.time() - t0
     it = cinv_t.chain.niter
-    out['T'] = {'iterations': it, 'seconds': dt, 'iter_per_s': it / dt, 'setup_s': t_setup,
+    dmap = sht.dev_map(tmap); sol = util_alm.dalm.zeros(lmax); torch.cuda.synchronize(); t1 = time.time()
+    cinv_t.chain.solve(sol, dmap); torch.cuda.synchronize(); dt_dev = time.time() - t1
+    times_ms(cinv_t.chain, util_alm.dalm(sht.dev_alm(tlm)))
+    out['T'] = {'iterations': it, 'seconds': dt, 'iter_per_s': it / dt, 'seconds_device_resident': dt_dev,
+                'iter_per_s_device_resident': it / dt_dev, 'setup_s': t_setup,
                 'launches': sht._lib.launch_count() - n0, 'final_eps': cinv_t.chain.last_monitor.trace[-1][1]}
     print('CG-T', out['T'])
 if a.pol:
@@ -72,11 +103,18 @@ if a.pol:
     cinv_p = filt_cinv.cinv_p(os.path.join(tmp, 'cinv_p'), lmax, nside, cls, transf, [[ninv_p]])
     _ = cinv_p.chain.bstage
     torch.cuda.synchronize(); t_setup = time.time() - t0
+    elm, blm = cinv_p.apply_ivf([qmap, umap])
+    torch.cuda.synchronize()
     n0 = sht._lib.launch_count(); t0 = time.time()
     elm, blm = cinv_p.apply_ivf([qmap, umap])
     torch.cuda.synchronize(); dt = time.time() - t0
     it = cinv_p.chain.niter
-    out['P'] = {'iterations': it, 'seconds': dt, 'iter_per_s': it / dt, 'setup_s': t_setup,
+    dq, du = sht.dev_map(qmap), sht.dev_map(umap)
+    sol = util_alm.eblm([util_alm.dalm.zeros(lmax), util_alm.dalm.zeros(lmax)]); torch.cuda.synchronize(); t1 = time.time()
+    cinv_p.chain.solve(sol, [dq, du]); torch.cuda.synchronize(); dt_dev = time.time() - t1
+    times_ms(cinv_p.chain, util_alm.eblm([util_alm.dalm(sht.dev_alm(elm)), util_alm.dalm(sht.dev_alm(blm))]))
+    out['P'] = {'iterations': it, 'seconds': dt, 'iter_per_s': it / dt, 'seconds_device_resident': dt_dev,
+                'iter_per_s_device_resident': it / dt_dev, 'setup_s': t_setup,
                 'launches': sht._lib.launch_count() - n0, 'final_eps': cinv_p.chain.last_monitor.trace[-1][1]}
     print('CG-P', out['P'])
 print(json.dumps({'cg': out, 'nside': nside, 'lmax': lmax, 'fsky': float(mask.mean())}))

@@ -25,7 +25,7 @@ def emul():
     return ctypes.CDLL(SO)
 
 
-@pytest.mark.parametrize("nbatch", [2, 4])
+@pytest.mark.parametrize("nbatch", [1, 2, 4])
 @pytest.mark.parametrize("nside,lmax", [(4, 11), (8, 23), (16, 40), (32, 70), (64, 100)])
 def test_ring_fft_stage(emul, oracle_sht, nside, lmax, nbatch):
     rng = np.random.default_rng(nside)

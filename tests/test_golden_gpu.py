@@ -98,6 +98,37 @@ def test_cg_tt_diag_only(gold, mods):
     assert rel_l2(sol, gold['tt_diag_soltn']) < 1e-7
 
 
+@pytest.mark.parametrize('pol', [False, True])
+def test_cg_graph_and_device_scalar_stages_equal_host_loop(gold, mods, pol, monkeypatch):
+    """The inner multigrid stages run three ways -- the reference's host loop (cd_solve, PLK_CG_FIXED=0), the
+    device-scalar loop (cd_solve_fixed) launched eagerly (PLK_CG_GRAPH=0) and replayed as a CUDA graph -- and
+    must give the same solution, iteration count and eps trace."""
+    c = gi.cg_case()
+    ua = mods['util_alm']
+    res = []
+    for fixed, graph in (('0', '0'), ('1', '0'), ('1', '1')):
+        monkeypatch.setenv('PLK_CG_FIXED', fixed)
+        monkeypatch.setenv('PLK_CG_GRAPH', graph)
+        if pol:
+            nf = mods['opfilt_pp'].alm_filter_ninv(c['ninv_p1'], c['transf'])
+            n = gold['pp_soltn_e'].size
+            sol = ua.eblm([np.zeros(n, dtype=complex), np.zeros(n, dtype=complex)])
+            chain = _solve(mods, mods['opfilt_pp'], gi.chain_descr_p(mods['cd_solve']), c['cls'], nf, sol, [c['qmap'], c['umap']])
+            v = np.concatenate([sol.elm, sol.blm])
+        else:
+            nf = mods['opfilt_tt'].alm_filter_ninv(c['ninv_t'], c['transf'], marge_monopole=True, marge_dipole=True)
+            sol = np.zeros(gold['tt_soltn'].size, dtype=complex)
+            chain = _solve(mods, mods['opfilt_tt'], gi.chain_descr_t(mods['cd_solve']), c['cls'], nf, sol, c['tmap'])
+            v = sol.copy()
+        used_graph = any(type(op).__name__ == 'graphed_op' and op.graph is not None for op in chain.bstage.pre_ops)
+        assert used_graph == (graph == '1')
+        res.append((v, chain.niter, np.array([t[1] for t in chain.last_monitor.trace])))
+    for v, niter, eps in res[1:]:
+        assert niter == res[0][1]
+        assert np.allclose(eps, res[0][2], rtol=1e-6)
+        assert rel_l2(v, res[0][0]) < 1e-9
+
+
 def test_cg_pp_same_iterations_as_reference(gold, mods):
     c = gi.cg_case()
     ua = mods['util_alm']

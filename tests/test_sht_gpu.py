@@ -124,3 +124,50 @@ def test_closed_forms(sht):
     m = plan.alm2map_host(0, a)
     ref = xyz[0] * np.sin(theta) * np.cos(phi) + xyz[1] * np.sin(theta) * np.sin(phi) + xyz[2] * np.cos(theta)
     assert np.max(np.abs(m - ref)) < 1e-13
+
+
+def test_ring_stage_nside4096_lmax5000(sht, oracle_sht):
+    """BASELINE.json configs[4] size (nside 4096, mmax 5000): every ring length up to n = 16384, including the
+    single-buffer Bluestein path (M = 8192) and rings that alias (2 mmax >= n), against the numpy ring FFTs."""
+    import torch
+    nside, lmax = 4096, 5000
+    rng = np.random.default_rng(4096)
+    plan = sht.get_plan(nside, lmax)
+    X = np.zeros((plan.nring, plan.pitch), dtype=complex)
+    X[:, :lmax + 1] = rng.standard_normal((plan.nring, lmax + 1)) + 1j * rng.standard_normal((plan.nring, lmax + 1))
+    X[:, 0] = X[:, 0].real
+    got = plan.ring_synth(torch.from_numpy(X).cuda()).cpu().numpy()
+    ref = oracle_sht.phase2map(nside, X[:, :lmax + 1])
+    assert rel_l2(got, ref) < 1e-12
+    mp = rng.standard_normal(12 * nside ** 2)
+    Xo = plan.ring_anal(sht.dev_map(mp)).cpu().numpy()
+    ref = oracle_sht.map2phase(nside, mp, lmax) * (4 * np.pi / (12 * nside ** 2))
+    assert rel_l2(Xo[:, :lmax + 1], ref) < 1e-12
+
+
+@pytest.mark.parametrize("spin", [0, 2])
+def test_adjointness_nside4096(sht, spin):
+    """Size-independent property at configs[4] size (nside 4096, lmax 4000)."""
+    import torch
+    nside, lmax = 4096, 4000
+    rng = np.random.default_rng(21 + spin)
+    plan = sht.get_plan(nside, lmax)
+    npix = 12 * nside ** 2
+    w = 4 * np.pi / npix
+    if spin == 0:
+        a = rand_alm(rng, lmax)
+        m = rng.standard_normal(npix)
+        ya = plan.alm2map(sht.dev_alm(a)).cpu().numpy()
+        am = plan.map2alm(sht.dev_map(m)).cpu().numpy()
+        lhs = alm_dot(am, a, lmax)
+        rhs = w * float(np.dot(m, ya))
+    else:
+        g, c = rand_alm(rng, lmax, spin), rand_alm(rng, lmax, spin)
+        m1, m2 = rng.standard_normal(npix), rng.standard_normal(npix)
+        y = plan.alm2map_spin(sht.dev_alm(g), sht.dev_alm(c), spin)
+        gm, cm = plan.map2alm_spin(sht.dev_map(m1), sht.dev_map(m2), spin)
+        lhs = alm_dot(gm.cpu().numpy(), g, lmax) + alm_dot(cm.cpu().numpy(), c, lmax)
+        rhs = w * float(np.dot(m1, y[0].cpu().numpy()) + np.dot(m2, y[1].cpu().numpy()))
+    assert abs(lhs - rhs) < 1e-11 * max(abs(lhs), abs(rhs), 1e-300)
+    torch.cuda.synchronize()
+    sht.clear_plans()
