@@ -133,6 +133,39 @@ int plk_map_modes_dot_dev(plk_plan *plan, double *m, const double *w, double *su
 int plk_map_modes_sub_dev(plk_plan *plan, double *m, const double *w, const double *sums_dev,
                           const double *pinv_dev, void *stream);
 
+/* ---- m-partitioned ("distributed") transforms over the GPUs of one NVSwitch box: one process per GPU
+ *      (BASELINE.json configs[4]: one nside-4096 transform split over 2/4/8 GPUs).
+ *      The reference has no counterpart: a single healpy transform is one OpenMP process (shts.py:10).
+ *
+ *  Layout: the Legendre stage is split by m (blocks of `mblk` columns dealt boustrophedon to the ranks), the ring-FFT /
+ *  pixel stage by ring pair (contiguous blocks of equal pixel count).  The exchange between the two stages is fused
+ *  into the producing kernel: plk_dist_legendre_synth stores every phase row straight into the phase array of the
+ *  rank that owns the ring pair, plk_dist_ring_anal stores column m into the array of the rank that owns m -- peer
+ *  memory over NVLink (CUDA IPC mappings), no pack / all-to-all / unpack passes.  The caller provides the two
+ *  barriers per transform (before the producer stage: peers are done reading; after it: all rows have landed) and,
+ *  for analysis, sums the per-rank alm (every rank returns its own m rows, zero elsewhere).
+ *  Maps are full-size RING arrays of which a rank reads / writes only the pixel ranges of plk_dist_pixel_ranges. */
+typedef struct plk_dist plk_dist;
+/* host arithmetic only (no GPU needed): pair_lo[nranks + 1] ring-pair bounds, m_owner[mmax + 1]; either may be NULL */
+int plk_dist_partition(int nside, int mmax, int nranks, int mblk, int *pair_lo, int *m_owner);
+int plk_dist_create(plk_dist **dist, plk_plan *plan, int rank, int nranks, int mblk /* <= 0: default 64 */);
+int plk_dist_destroy(plk_dist *dist);
+/* CUDA IPC handles (2 x 64 bytes) of this rank's phase arrays / mapping of a peer's */
+int plk_dist_export(plk_dist *dist, void *handles128);
+int plk_dist_import(plk_dist *dist, int peer, const void *handles128);
+/* same-process peers (simulated ranks on one GPU in the tests) */
+int plk_dist_set_peer(plk_dist *dist, int peer, void *x1, void *x2);
+int plk_dist_phase_ptrs(plk_dist *dist, void **x1, void **x2);
+int plk_dist_num_m(const plk_dist *dist);
+/* [north lo, north hi, south lo, south hi) pixel ranges of this rank's rings */
+int plk_dist_pixel_ranges(const plk_dist *dist, long long *ranges4);
+int plk_dist_legendre_synth(plk_dist *dist, int spin, const void *alm1, const void *alm2, const double *fl1,
+                            const double *fl2, void *stream);
+int plk_dist_ring_synth(plk_dist *dist, int spin, double *map1, double *map2, void *stream);
+int plk_dist_ring_anal(plk_dist *dist, int spin, const double *map1, const double *map2, void *stream);
+int plk_dist_legendre_anal(plk_dist *dist, int spin, const double *fl1, const double *fl2, void *alm1, void *alm2,
+                           void *stream);
+
 /* ---- measurement helpers (bench.py): per-kernel CUDA-event timing of the Legendre launches and the device's
  *      FP64 FMA peak.  kinds: 0 synthesis spin 0, 1 synthesis spin s, 2 analysis spin 0, 3 analysis spin s. */
 int plk_profile_enable(int on);

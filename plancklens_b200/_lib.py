@@ -37,6 +37,19 @@ _SIGS = {
     'plk_alm2rlm_dev': (c_int, [c_int, vp, vp, vp]),
     'plk_rlm2alm_dev': (c_int, [c_int, vp, vp, vp]),
     'plk_dense_matvec_dev': (c_int, [c_int, vp, vp, vp, vp]),
+    'plk_dist_partition': (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    'plk_dist_create': (c_int, [ctypes.POINTER(vp), vp, c_int, c_int, c_int]),
+    'plk_dist_destroy': (c_int, [vp]),
+    'plk_dist_export': (c_int, [vp, vp]),
+    'plk_dist_import': (c_int, [vp, c_int, vp]),
+    'plk_dist_set_peer': (c_int, [vp, c_int, vp, vp]),
+    'plk_dist_phase_ptrs': (c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]),
+    'plk_dist_num_m': (c_int, [vp]),
+    'plk_dist_pixel_ranges': (c_int, [vp, ctypes.POINTER(c_ll)]),
+    'plk_dist_legendre_synth': (c_int, [vp, c_int, vp, vp, vp, vp, vp]),
+    'plk_dist_ring_synth': (c_int, [vp, c_int, vp, vp, vp]),
+    'plk_dist_ring_anal': (c_int, [vp, c_int, vp, vp, vp]),
+    'plk_dist_legendre_anal': (c_int, [vp, c_int, vp, vp, vp, vp, vp]),
     'plk_profile_enable': (c_int, [c_int]),
     'plk_profile_read': (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)]),
     'plk_fp64_peak': (c_int, [ctypes.POINTER(c_dbl), c_int]),

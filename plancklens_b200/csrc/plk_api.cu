@@ -94,6 +94,20 @@ struct plk_plan {
   long long table_bytes = 0;
 };
 
+// m-partitioned execution of one plan over the GPUs of a box (include/plk.h, "distributed transforms")
+struct plk_dist {
+  plk_plan *plan = nullptr;
+  int rank = 0, nranks = 1, mblk = 64;
+  std::vector<int> pair_lo;          // [nranks + 1]
+  std::vector<int> mlist;            // local m, longest recurrences first
+  int *d_mlist = nullptr;
+  int *d_fft_list = nullptr;         // local ring pairs grouped by FFT size class
+  std::vector<plk_plan::FftClass> classes;
+  cplx *X1 = nullptr, *X2 = nullptr; // own phase arrays: plain cudaMalloc so that CUDA IPC can export them
+  cplx *px1[kMaxRanks] = {}, *px2[kMaxRanks] = {};
+  bool opened[kMaxRanks] = {};
+};
+
 template <class T>
 static int upload(plk_plan *p, const std::vector<T> &h, T **d, std::vector<void *> *owned = nullptr) {
   const size_t b = std::max<size_t>(h.size() * sizeof(T), 16);
@@ -193,6 +207,7 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
     std::vector<int> list;
     const int nb4_maxm = env_int("PLK_FFT_NB4_MAXM", 1024);
     const int nb1_minm = env_int("PLK_FFT_NB1_MINM", 8192);   // M = 8192 (nside 4096 caps): one DFT buffer only
+    f.nb4_maxm = nb4_maxm; f.nb1_minm = nb1_minm;
     for (auto it = by_m.rbegin(); it != by_m.rend(); ++it) {     // largest transforms first
       plk_plan::FftClass c;
       c.M = it->first; c.offset = (int)list.size(); c.count = (int)it->second.size();
@@ -204,6 +219,14 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
       p->fft_classes.push_back(c);
     }
     int *di; int rc = upload(p, list, &di); if (rc) { plk_plan_destroy(p); return rc; } p->fft_list = di;
+    // Small plans (the coarse multigrid levels of the qcinv chains): one launch over all classes with the largest
+    // shared-memory request -- each per-class launch holds a handful of blocks for ~20 us, so six of them back to back
+    // cost more than the transform itself.
+    if (hg.npair <= env_int("PLK_FFT_MERGE_MAXPAIR", 1024) && p->fft_classes.size() > 1) {
+      plk_plan::FftClass c;
+      c.M = -1; c.nbatch = 0; c.offset = 0; c.count = hg.npair; c.smem = p->fft_smem; c.threads = 256;
+      p->fft_classes.assign(1, c);
+    }
   }
   if (p->fft_smem > 227 * 1024) { plk_plan_destroy(p); return fail(PLK_EINVAL, "ring FFT needs %d bytes of shared memory", p->fft_smem); }
   {
@@ -233,6 +256,7 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
     f.V = nullptr;
   }
   f.mtop = nullptr;
+  f.dist_n = 0; f.dist_mblk = 1;
 
   // per-ring table for the template (monopole / dipole) kernels
   {
@@ -364,21 +388,34 @@ static int ensure_work(plk_plan *p) {
   return 0;
 }
 
+static DistX no_dist() { DistX d; memset(&d, 0, sizeof d); d.nranks = 1; d.mblk = 1; return d; }
+static DistX dist_x(const plk_dist *d) {
+  DistX x = no_dist();
+  x.nranks = d->nranks; x.mblk = d->mblk;
+  for (int q = 0; q <= d->nranks; ++q) x.pair_lo[q] = d->pair_lo[q];
+  for (int q = 0; q < d->nranks; ++q) { x.x1[q] = d->px1[q]; x.x2[q] = d->px2[q]; }
+  return x;
+}
+
 static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *alm2, const double *fl1,
-                          const double *fl2, cplx *X1, cplx *X2, cudaStream_t st) {
+                          const double *fl2, cplx *X1, cplx *X2, cudaStream_t st, const plk_dist *dd = nullptr) {
   int rc = ensure_spin(p, spin);
   if (rc) return rc;
   const DevSpin &d = p->spins[spin].d;
   if ((rc = ensure_work(p))) return rc;
-  dim3 pg((p->lmax + 256) / 256, p->mmax + 1);
-  if (spin == 0) prep_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, nullptr, fl1, nullptr, p->rec.p);
-  else prep_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, (const cplx *)alm2, fl1, fl2, p->rec.p);
+  const int nm = dd ? (int)dd->mlist.size() : p->mmax + 1;        // m columns handled by this process
+  const int *morder = dd ? dd->d_mlist : p->morder;
+  const DistX dx = dd ? dist_x(dd) : no_dist();
+  if (nm == 0) return 0;
+  dim3 pg((p->lmax + 256) / 256, nm);
+  if (spin == 0) prep_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, nullptr, fl1, nullptr, p->rec.p, morder);
+  else prep_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const cplx *)alm1, (const cplx *)alm2, fl1, fl2, p->rec.p, morder);
   LAUNCHED();
   const int nr = pick_nr(p, spin ? env_int("PLK_NR_SYNS", 4) : env_int("PLK_NR_SYN0", 4));
-  dim3 grid((p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr), p->mmax + 1);
+  dim3 grid((p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr), nm);
   const int nthr = (kNCW + 1) * 32;
 #define SYN(SP, NR)                                                                                              \
-  legendre_synth_kernel<SP, NR><<<grid, nthr, leg_smem<SP, true>(NR), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, p->morder)
+  legendre_synth_kernel<SP, NR><<<grid, nthr, leg_smem<SP, true>(NR), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, morder, dx)
   prof_begin(spin ? 1 : 0, st);
   if (spin == 0) {
     if (nr == 4) SYN(false, 4); else if (nr == 2) SYN(false, 2); else SYN(false, 1);
@@ -392,7 +429,7 @@ static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *a
 }
 
 static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, const double *fl1, const double *fl2,
-                         void *alm1, void *alm2, cudaStream_t st) {
+                         void *alm1, void *alm2, cudaStream_t st, const plk_dist *dd = nullptr) {
   int rc = ensure_spin(p, spin);
   if (rc) return rc;
   const DevSpin &d = p->spins[spin].d;
@@ -402,10 +439,17 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   const int ntile = (p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr);
   const long long stride = (long long)nalm * nv;
   if ((rc = ensure_work(p))) return rc;
-  dim3 grid(ntile, p->mmax + 1);
+  const int nm = dd ? (int)dd->mlist.size() : p->mmax + 1;
+  const int *morder = dd ? dd->d_mlist : p->morder;
+  if (dd) {   // rows of other ranks stay zero: the caller sums the per-rank alms (or keeps them m-distributed)
+    CK(cudaMemsetAsync(alm1, 0, nalm * sizeof(cplx), st));
+    if (spin) CK(cudaMemsetAsync(alm2, 0, nalm * sizeof(cplx), st));
+  }
+  if (nm == 0) return 0;
+  dim3 grid(ntile, nm);
   const int nthr = (kNCW + 1) * 32;
 #define ANA(SP, NR)                                                                                              \
-  legendre_anal_kernel<SP, NR><<<grid, nthr, leg_smem<SP, false>(NR), st>>>(p->g, d, X1, X2, p->pitch, (double *)p->part.p, stride, p->morder, env_int("PLK_DBG_ANA", 0))
+  legendre_anal_kernel<SP, NR><<<grid, nthr, leg_smem<SP, false>(NR), st>>>(p->g, d, X1, X2, p->pitch, (double *)p->part.p, stride, morder, env_int("PLK_DBG_ANA", 0))
   prof_begin(spin ? 3 : 2, st);
   if (spin == 0) {
     if (nr == 4) ANA(false, 4); else if (nr == 2) ANA(false, 2); else ANA(false, 1);
@@ -415,30 +459,41 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
 #undef ANA
   prof_end(st);
   LAUNCHED();
-  dim3 pg((p->lmax + 256) / 256, p->mmax + 1);
-  if (spin == 0) finish_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, nullptr, (cplx *)alm1, nullptr);
-  else finish_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, fl2, (cplx *)alm1, (cplx *)alm2);
+  dim3 pg((p->lmax + 256) / 256, nm);
+  if (spin == 0) finish_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, nullptr, (cplx *)alm1, nullptr, morder);
+  else finish_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, fl2, (cplx *)alm1, (cplx *)alm2, morder);
   LAUNCHED();
   return 0;
 }
 
-static int ring_synth(plk_plan *p, const cplx *X, double *map, cudaStream_t st, const int *mtop = nullptr) {
+// dd != null: only this rank's ring pairs; analysis scatters column m to the rank owning it (which = 0: X1, 1: X2)
+static int ring_synth(plk_plan *p, const cplx *X, double *map, cudaStream_t st, const int *mtop = nullptr,
+                      const plk_dist *dd = nullptr) {
   DevFFT f = p->f;
   f.mtop = mtop;
-  for (const auto &c : p->fft_classes) {
-    if (c.threads == 512) ring_synth_kernel<512, 1><<<c.count, 512, c.smem, st>>>(f, p->fft_list + c.offset, c.nbatch, X, p->pitch, p->mmax, map);
-    else ring_synth_kernel<256, 3><<<c.count, 256, c.smem, st>>>(f, p->fft_list + c.offset, c.nbatch, X, p->pitch, p->mmax, map);
+  const int *list = dd ? dd->d_fft_list : p->fft_list;
+  for (const auto &c : (dd ? dd->classes : p->fft_classes)) {
+    if (c.count == 0) continue;
+    if (c.threads == 512) ring_synth_kernel<512, 1><<<c.count, 512, c.smem, st>>>(f, list + c.offset, c.nbatch, X, p->pitch, p->mmax, map);
+    else ring_synth_kernel<256, 3><<<c.count, 256, c.smem, st>>>(f, list + c.offset, c.nbatch, X, p->pitch, p->mmax, map);
     LAUNCHED();
   }
   return 0;
 }
-static int ring_anal(plk_plan *p, const double *map, cplx *X, cudaStream_t st, const int *mtop = nullptr) {
+static int ring_anal(plk_plan *p, const double *map, cplx *X, cudaStream_t st, const int *mtop = nullptr,
+                     const plk_dist *dd = nullptr, int which = 0) {
   const double w = 4.0 * M_PI / (double)p->npix;
   DevFFT f = p->f;
   f.mtop = mtop;
-  for (const auto &c : p->fft_classes) {
-    if (c.threads == 512) ring_anal_kernel<512, 1><<<c.count, 512, c.smem, st>>>(f, p->fft_list + c.offset, c.nbatch, map, X, p->pitch, p->mmax, w);
-    else ring_anal_kernel<256, 3><<<c.count, 256, c.smem, st>>>(f, p->fft_list + c.offset, c.nbatch, map, X, p->pitch, p->mmax, w);
+  if (dd) {
+    f.dist_n = dd->nranks; f.dist_mblk = dd->mblk;
+    for (int q = 0; q < dd->nranks; ++q) f.dist_x[q] = which ? dd->px2[q] : dd->px1[q];
+  }
+  const int *list = dd ? dd->d_fft_list : p->fft_list;
+  for (const auto &c : (dd ? dd->classes : p->fft_classes)) {
+    if (c.count == 0) continue;
+    if (c.threads == 512) ring_anal_kernel<512, 1><<<c.count, 512, c.smem, st>>>(f, list + c.offset, c.nbatch, map, X, p->pitch, p->mmax, w);
+    else ring_anal_kernel<256, 3><<<c.count, 256, c.smem, st>>>(f, list + c.offset, c.nbatch, map, X, p->pitch, p->mmax, w);
     LAUNCHED();
   }
   return 0;
@@ -498,6 +553,190 @@ extern "C" int plk_map2alm_dev(plk_plan *p, int spin, const double *map1, const 
   if ((rc = ring_anal(p, map1, (cplx *)p->X1.p, st, mtop))) return rc;
   if (spin > 0 && (rc = ring_anal(p, map2, (cplx *)p->X2.p, st, mtop))) return rc;
   return legendre_anal(p, spin, (const cplx *)p->X1.p, (const cplx *)p->X2.p, fl1, fl2, alm1, alm2, st);
+}
+
+// ------------------------------------------------------------------------------------------ m-partitioned transforms
+// Pure host arithmetic (callable without a GPU): ring-pair bounds per rank (balanced by pixel count) and the owner of
+// every m column.
+extern "C" int plk_dist_partition(int nside, int mmax, int nranks, int mblk, int *pair_lo, int *m_owner) {
+  if (nside < 1 || (nside & (nside - 1)) || nranks < 1 || nranks > kMaxRanks || mblk < 1 || mmax < 0)
+    return fail(PLK_EINVAL, "bad argument (nside %d, nranks %d, mblk %d)", nside, nranks, mblk);
+  const int npair = 2 * nside;
+  if (pair_lo) {
+    // pixels of ring pair ip: both rings except the equator (last pair)
+    std::vector<long long> cum(npair + 1, 0);
+    for (int ip = 0; ip < npair; ++ip) {
+      const long long n = 4LL * (ip < nside ? ip + 1 : nside);
+      cum[ip + 1] = cum[ip] + (ip == npair - 1 ? n : 2 * n);
+    }
+    pair_lo[0] = 0;
+    for (int q = 1; q < nranks; ++q) {
+      const long long target = cum[npair] * q / nranks;
+      int ip = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+      pair_lo[q] = std::min(std::max(ip, pair_lo[q - 1]), npair);
+    }
+    pair_lo[nranks] = npair;
+  }
+  if (m_owner) for (int m = 0; m <= mmax; ++m) m_owner[m] = dist_owner_of_m(m, mblk, nranks);
+  return PLK_OK;
+}
+
+extern "C" int plk_dist_destroy(plk_dist *d) {
+  if (!d) return PLK_OK;
+  for (int q = 0; q < d->nranks; ++q)
+    if (d->opened[q]) { cudaIpcCloseMemHandle(d->px1[q]); cudaIpcCloseMemHandle(d->px2[q]); }
+  if (d->X1) cudaFree(d->X1);
+  if (d->X2) cudaFree(d->X2);
+  if (d->d_mlist) cudaFree(d->d_mlist);
+  if (d->d_fft_list) cudaFree(d->d_fft_list);
+  delete d;
+  return PLK_OK;
+}
+
+extern "C" int plk_dist_create(plk_dist **out, plk_plan *p, int rank, int nranks, int mblk) {
+  if (!out) return fail(PLK_EINVAL, "dist pointer is NULL");
+  *out = nullptr;
+  CHECK_PLAN(p);
+  if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(PLK_EINVAL, "bad rank %d / %d", rank, nranks);
+  if (mblk <= 0) mblk = 64;
+  plk_dist *d = new plk_dist();
+  d->plan = p; d->rank = rank; d->nranks = nranks; d->mblk = mblk;
+  d->pair_lo.resize(nranks + 1);
+  std::vector<int> owner(p->mmax + 1);
+  int rc = plk_dist_partition(p->nside, p->mmax, nranks, mblk, d->pair_lo.data(), owner.data());
+  if (rc) { delete d; return rc; }
+  for (int m = 0; m <= p->mmax; ++m) if (owner[m] == rank) d->mlist.push_back(m);
+#define DCK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { plk_dist_destroy(d); \
+    return fail(PLK_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+  DCK(cudaMalloc((void **)&d->d_mlist, std::max<size_t>(d->mlist.size(), 1) * sizeof(int)));
+  if (!d->mlist.empty()) DCK(cudaMemcpy(d->d_mlist, d->mlist.data(), d->mlist.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // this rank's ring pairs, grouped by the plan's FFT size classes
+  {
+    std::vector<int> full(p->npair);
+    DCK(cudaMemcpy(full.data(), p->fft_list, (size_t)p->npair * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> list;
+    for (const auto &c : p->fft_classes) {
+      plk_plan::FftClass lc = c;
+      lc.offset = (int)list.size();
+      for (int i = 0; i < c.count; ++i) {
+        const int ip = full[c.offset + i];
+        if (ip >= d->pair_lo[rank] && ip < d->pair_lo[rank + 1]) list.push_back(ip);
+      }
+      lc.count = (int)list.size() - lc.offset;
+      d->classes.push_back(lc);
+    }
+    DCK(cudaMalloc((void **)&d->d_fft_list, std::max<size_t>(list.size(), 1) * sizeof(int)));
+    if (!list.empty()) DCK(cudaMemcpy(d->d_fft_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  const size_t xb = (size_t)p->nring * p->pitch * sizeof(cplx);
+  DCK(cudaMalloc((void **)&d->X1, xb));
+  DCK(cudaMalloc((void **)&d->X2, xb));
+  DCK(cudaMemset(d->X1, 0, xb));
+  DCK(cudaMemset(d->X2, 0, xb));
+#undef DCK
+  d->px1[rank] = d->X1; d->px2[rank] = d->X2;
+  *out = d;
+  return PLK_OK;
+}
+
+// CUDA IPC handles of the two phase arrays (2 x 64 bytes), to be exchanged between the processes of the box
+extern "C" int plk_dist_export(plk_dist *d, void *handles) {
+  if (!d || !handles) return fail(PLK_EINVAL, "NULL argument");
+  cudaIpcMemHandle_t h[2];
+  CK(cudaIpcGetMemHandle(&h[0], d->X1));
+  CK(cudaIpcGetMemHandle(&h[1], d->X2));
+  memcpy(handles, h, sizeof h);
+  return PLK_OK;
+}
+extern "C" int plk_dist_import(plk_dist *d, int peer, const void *handles) {
+  if (!d || !handles || peer < 0 || peer >= d->nranks) return fail(PLK_EINVAL, "bad argument");
+  if (peer == d->rank) return PLK_OK;
+  cudaIpcMemHandle_t h[2];
+  memcpy(h, handles, sizeof h);
+  void *a = nullptr, *b = nullptr;
+  CK(cudaIpcOpenMemHandle(&a, h[0], cudaIpcMemLazyEnablePeerAccess));
+  CK(cudaIpcOpenMemHandle(&b, h[1], cudaIpcMemLazyEnablePeerAccess));
+  d->px1[peer] = (cplx *)a; d->px2[peer] = (cplx *)b; d->opened[peer] = true;
+  return PLK_OK;
+}
+// same-process peers (several simulated ranks on one GPU, or one process driving peer-enabled GPUs)
+extern "C" int plk_dist_set_peer(plk_dist *d, int peer, void *x1, void *x2) {
+  if (!d || peer < 0 || peer >= d->nranks || !x1 || !x2) return fail(PLK_EINVAL, "bad argument");
+  d->px1[peer] = (cplx *)x1; d->px2[peer] = (cplx *)x2;
+  return PLK_OK;
+}
+extern "C" int plk_dist_phase_ptrs(plk_dist *d, void **x1, void **x2) {
+  if (!d || !x1 || !x2) return fail(PLK_EINVAL, "NULL argument");
+  *x1 = d->X1; *x2 = d->X2;
+  return PLK_OK;
+}
+extern "C" int plk_dist_num_m(const plk_dist *d) { return d ? (int)d->mlist.size() : 0; }
+// pixel index ranges [lo, hi) of this rank's rings in a RING map: north block, south block
+extern "C" int plk_dist_pixel_ranges(const plk_dist *d, long long *r4) {
+  if (!d || !r4) return fail(PLK_EINVAL, "NULL argument");
+  const HostGeom &hg = d->plan->hg;
+  const int lo = d->pair_lo[d->rank], hi = d->pair_lo[d->rank + 1];
+  if (lo >= hi) { r4[0] = r4[1] = r4[2] = r4[3] = 0; return PLK_OK; }
+  r4[0] = hg.start_n[lo];
+  r4[1] = hg.start_n[hi - 1] + hg.nphi[hi - 1];
+  // southern twins run backwards: pair hi-1 has the first southern ring of the block (the equator has none)
+  int last = hi - 1;
+  if (hg.start_s[last] < 0) --last;
+  if (last < lo) { r4[2] = r4[3] = 0; return PLK_OK; }
+  r4[2] = hg.start_s[last];
+  r4[3] = hg.start_s[lo] + hg.nphi[lo];
+  return PLK_OK;
+}
+
+static int dist_ready(const plk_dist *d) {
+  if (!d) return fail(PLK_EINVAL, "dist is NULL");
+  for (int q = 0; q < d->nranks; ++q)
+    if (!d->px1[q] || !d->px2[q]) return fail(PLK_EINVAL, "peer %d has not been imported (plk_dist_import / plk_dist_set_peer)", q);
+  return 0;
+}
+// Stage 1 of a distributed synthesis: Legendre sums of this rank's m columns over ALL ring pairs; every row is
+// stored into the phase array of the rank that owns the ring pair (peer stores).  Callers place a barrier before
+// (peers have consumed their arrays) and after (all rows have landed) -- see plancklens_b200/dist_sht.py.
+extern "C" int plk_dist_legendre_synth(plk_dist *d, int spin, const void *alm1, const void *alm2, const double *fl1,
+                                       const double *fl2, void *stream) {
+  int rc = dist_ready(d);
+  if (rc) return rc;
+  if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
+  if (!alm1) return fail(PLK_EINVAL, "NULL buffer");
+  return legendre_synth(d->plan, spin, alm1, alm2, fl1, fl2, d->X1, d->X2, (cudaStream_t)stream, d);
+}
+// Stage 2: ring FFTs of this rank's ring pairs; writes only this rank's pixels of map1 (, map2)
+extern "C" int plk_dist_ring_synth(plk_dist *d, int spin, double *map1, double *map2, void *stream) {
+  int rc = dist_ready(d);
+  if (rc) return rc;
+  if (!map1 || (spin > 0 && !map2)) return fail(PLK_EINVAL, "NULL buffer");
+  plk_plan *p = d->plan;
+  if ((rc = ensure_spin(p, spin))) return rc;
+  const int *mtop = p->spins[spin].d.mtop;
+  if ((rc = ring_synth(p, d->X1, map1, (cudaStream_t)stream, mtop, d))) return rc;
+  if (spin > 0 && (rc = ring_synth(p, d->X2, map2, (cudaStream_t)stream, mtop, d))) return rc;
+  return PLK_OK;
+}
+// Analysis stage 1: ring FFTs of this rank's rings; column m goes to the phase array of the rank owning m
+extern "C" int plk_dist_ring_anal(plk_dist *d, int spin, const double *map1, const double *map2, void *stream) {
+  int rc = dist_ready(d);
+  if (rc) return rc;
+  if (!map1 || (spin > 0 && !map2)) return fail(PLK_EINVAL, "NULL buffer");
+  plk_plan *p = d->plan;
+  if ((rc = ensure_spin(p, spin))) return rc;
+  const int *mtop = p->spins[spin].d.mtop;
+  if ((rc = ring_anal(p, map1, d->X1, (cudaStream_t)stream, mtop, d, 0))) return rc;
+  if (spin > 0 && (rc = ring_anal(p, map2, d->X2, (cudaStream_t)stream, mtop, d, 1))) return rc;
+  return PLK_OK;
+}
+// Analysis stage 2: Legendre analysis of this rank's m columns; rows of other ranks are set to zero
+extern "C" int plk_dist_legendre_anal(plk_dist *d, int spin, const double *fl1, const double *fl2, void *alm1, void *alm2,
+                                      void *stream) {
+  int rc = dist_ready(d);
+  if (rc) return rc;
+  if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
+  if (!alm1 || (spin > 0 && !alm2)) return fail(PLK_EINVAL, "NULL buffer");
+  return legendre_anal(d->plan, spin, d->X1, d->X2, fl1, fl2, alm1, alm2, (cudaStream_t)stream, d);
 }
 
 // ------------------------------------------------------------------------------------------ host-pointer variants

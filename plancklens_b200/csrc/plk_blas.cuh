@@ -11,9 +11,10 @@ namespace plk {
 // grid: (ceil((lmax+1)/256), mmax+1).  spin 0: rec = double2 alpha*fl1*a ; spin s: rec = double4 {H+, H-}
 template <bool SPIN>
 __global__ void prep_alm_kernel(DevSpin t, const cplx *__restrict__ a1, const cplx *__restrict__ a2,
-                                const double *__restrict__ fl1, const double *__restrict__ fl2, void *__restrict__ rec) {
+                                const double *__restrict__ fl1, const double *__restrict__ fl2, void *__restrict__ rec,
+                                const int *__restrict__ morder) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = blockIdx.y;
+  const int m = morder[blockIdx.y];
   if (l > t.lmax || l < m) return;
   const int64_t i = alm_idx(t.lmax, l, m);
   const double al = t.alpha[i];
@@ -38,10 +39,10 @@ __global__ void prep_alm_kernel(DevSpin t, const cplx *__restrict__ a1, const cp
 template <bool SPIN>
 __global__ void finish_alm_kernel(DevSpin t, const double *__restrict__ part, long long part_stride, int ntile,
                                   const double *__restrict__ fl1, const double *__restrict__ fl2,
-                                  cplx *__restrict__ a1, cplx *__restrict__ a2) {
+                                  cplx *__restrict__ a1, cplx *__restrict__ a2, const int *__restrict__ morder) {
   constexpr int NV = SPIN ? 4 : 2;
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = blockIdx.y;
+  const int m = morder[blockIdx.y];
   if (l > t.lmax || l < m) return;
   const int64_t i = alm_idx(t.lmax, l, m);
   const int l0 = m > t.spin ? m : t.spin;

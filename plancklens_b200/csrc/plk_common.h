@@ -30,6 +30,23 @@ PLK_HD cplx conj(cplx a) { return mk(a.x, -a.y); }
 PLK_HD cplx mul_i(cplx a) { return mk(-a.y, a.x); }    // i*a
 PLK_HD cplx mul_mi(cplx a) { return mk(a.y, -a.x); }   // -i*a
 
+// ---- m-partitioned transforms over the GPUs of one NVSwitch box -------------------------
+// The Legendre stage is split by m, the ring-FFT / pixel stage by ring pair.  m is dealt to ranks in blocks of
+// `mblk` columns, boustrophedon (0 1 .. N-1 N-1 .. 1 0 ...) so that every rank gets the same mix of short (high m)
+// and long (low m) recurrences; ring pairs are owned in contiguous blocks of (almost) equal pixel count.
+constexpr int kMaxRanks = 8;
+PLK_HD int dist_owner_of_m(int m, int mblk, int nranks) {
+  const int c = (m / mblk) % (2 * nranks);
+  return c < nranks ? c : 2 * nranks - 1 - c;
+}
+struct cplx;
+struct DistX {                    // phase-array rows of ring pair ip live on rank q: pair_lo[q] <= ip < pair_lo[q+1]
+  int nranks;                     // <= 1: single GPU (the plain X1 / X2 kernel arguments are used)
+  int mblk;
+  int pair_lo[kMaxRanks + 1];
+  cplx *x1[kMaxRanks], *x2[kMaxRanks];   // every rank's phase arrays (own + CUDA-IPC peer mappings over NVLink)
+};
+
 // healpy m-major triangular index (mmax == lmax): idx(l,m) = m(2 lmax + 1 - m)/2 + l
 PLK_HD int64_t alm_idx(int lmax, int l, int m) { return (int64_t)m * (2 * lmax + 1 - m) / 2 + l; }
 PLK_HD int64_t alm_size(int lmax, int mmax) { return (int64_t)mmax * (2 * lmax + 1 - mmax) / 2 + lmax + 1; }

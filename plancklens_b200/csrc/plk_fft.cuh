@@ -38,7 +38,15 @@ struct DevFFT {
   const long long *start_n, *start_s;   // [npair] first pixel of the north / south ring (-1: none)
   const int *order;         // [npair] block -> ring pair, most expensive first
   const int *mtop;          // [npair] highest m the Legendre stage touches on this pair (or null = mmax)
+  // m-partitioned analysis: column m of the phase array is written into the array of the rank that owns m
+  int dist_n, dist_mblk;    // dist_n <= 1: single GPU
+  cplx *dist_x[kMaxRanks];
+  int nb4_maxm, nb1_minm;   // DFTs batched per pass: 4 (M <= nb4_maxm), 1 (M >= nb1_minm), else 2
 };
+PLK_HD int auto_nbatch(const DevFFT &f, int M) { return M == 0 ? 0 : (M >= f.nb1_minm ? 1 : (M <= f.nb4_maxm ? 4 : 2)); }
+PLK_HD cplx *phase_out(const DevFFT &f, cplx *X, int m) {
+  return f.dist_n > 1 ? f.dist_x[dist_owner_of_m(m, f.dist_mblk, f.dist_n)] : X;
+}
 
 PLK_HD int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
 PLK_HD int lg2(int v) {   // exact log2 of a power of two
@@ -383,7 +391,7 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
       const double *in = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]);
       cplx acc = mk(0.0, 0.0);
       for (int j = 0; j < n; ++j) acc = acc + in[j] * expipi32(-m * (shifted + 2 * j), n);
-      X[(size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch + m] = wgt * acc;
+      phase_out(f, X, m)[(size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch + m] = wgt * acc;
     }
     return;
   }
@@ -407,8 +415,9 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
       }
       ctx.sync();
       idft_q(ctx, buf, 1, q, M, tws, Vq);
-      cplx *Xr = X + (size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch;
+      const size_t xrow = (size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch;
       for (int m = ctx.tid(); m <= mmax; m += ctx.nthr()) {
+        cplx *Xr = phase_out(f, X, m) + xrow;
         const int jn = m / n, k = m - jn * n;
         const int kp = k % q, kq = (q - kp) % q;
         const cplx Y = conj(fetchZ(buf, kp, q, M, bits)), Yc = fetchZ(buf, kq, q, M, bits);
@@ -459,7 +468,7 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
       const cplx D = (S0 + g2 * S1) + (g4 * S2 + g6 * S3);
       cplx ph = mk(wgt, 0.0);
       if (shifted) ph = ((jn & 1) ? -wgt : wgt) * g;
-      X[(size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch + m] = ph * D;
+      phase_out(f, X, m)[(size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch + m] = ph * D;
     }
     ctx.sync();
   }
@@ -491,14 +500,19 @@ __global__ void __launch_bounds__(NT, MINB)
 ring_synth_kernel(DevFFT f, const int *__restrict__ list, int nbatch, const cplx *__restrict__ X, int pitch, int mmax,
                   double *__restrict__ map) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ring_synth_body(BlockCtx(), f, list[blockIdx.x], X, pitch, mmax, map, reinterpret_cast<cplx *>(smem_raw), nbatch);
+  const int ip = list[blockIdx.x];
+  // nbatch == 0: merged launch over all size classes (small plans, where launch latency beats occupancy)
+  ring_synth_body(BlockCtx(), f, ip, X, pitch, mmax, map, reinterpret_cast<cplx *>(smem_raw),
+                  nbatch ? nbatch : auto_nbatch(f, f.M[ip]));
 }
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 ring_anal_kernel(DevFFT f, const int *__restrict__ list, int nbatch, const double *__restrict__ map, cplx *__restrict__ X,
                  int pitch, int mmax, double wgt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ring_anal_body(BlockCtx(), f, list[blockIdx.x], map, X, pitch, mmax, wgt, reinterpret_cast<cplx *>(smem_raw), nbatch);
+  const int ip = list[blockIdx.x];
+  ring_anal_body(BlockCtx(), f, ip, map, X, pitch, mmax, wgt, reinterpret_cast<cplx *>(smem_raw),
+                 nbatch ? nbatch : auto_nbatch(f, f.M[ip]));
 }
 __global__ void __launch_bounds__(kFftThreads) bluestein_setup_kernel(DevFFT f, cplx *Vout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -24,6 +24,12 @@ namespace plk {
 #ifndef PLK_ANA_MINB
 #define PLK_ANA_MINB 1
 #endif
+#ifndef PLK_ANA_PIPE
+#define PLK_ANA_PIPE 1     // software-pipelined butterfly in the analysis kernel (0: plain loop)
+#endif
+#ifndef PLK_ANA_MINB_S2
+#define PLK_ANA_MINB_S2 3  // resident blocks asked for the spin-s NR = 2 analysis kernel
+#endif
 constexpr int kChunk = PLK_CHUNK;      // l values per TMA stage (even)
 constexpr int kStages = 4;
 constexpr int kNCW = 4;          // compute warps per block
@@ -225,7 +231,7 @@ PLK_D void producer_loop(unsigned char *stage_base, uint64_t *full, uint64_t *em
 template <bool SPIN, int NR>
 __global__ void __launch_bounds__((kNCW + 1) * 32, PLK_SYN_MINB)
 legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *__restrict__ X1, cplx *__restrict__ X2,
-                      int pitch, const int *__restrict__ morder) {
+                      int pitch, const int *__restrict__ morder, DistX dx) {
   using SB = StageBytes<SPIN, true>;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -379,6 +385,13 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
     const int ip = pair0 + 32 * j;
     if (ip >= g.npair) continue;
     const int rn = ip, rs = g.nring - 1 - ip;
+    if (dx.nranks > 1) {
+      // m-partitioned transform: this rank holds only its m columns; the rows go straight into the phase array of
+      // the rank that owns the ring pair (peer-memory stores over NVLink -- the all-to-all is fused into the kernel)
+      int q = 0;
+      while (q + 1 < dx.nranks && ip >= dx.pair_lo[q + 1]) ++q;
+      X1 = dx.x1[q]; X2 = dx.x2[q];
+    }
     if (!SPIN) {
       X1[(size_t)rn * pitch + m] = mk(a0r[j] + a1r[j], a0i[j] + a1i[j]);
       if (rs != rn) X1[(size_t)rs * pitch + m] = mk(sg0 * (a0r[j] - a1r[j]), sg0 * (a0i[j] - a1i[j]));
@@ -430,7 +443,7 @@ PLK_D void butterfly16(double (&v)[16], int lane) {
 }
 
 template <bool SPIN, int NR>
-__global__ void __launch_bounds__((kNCW + 1) * 32, (SPIN && NR == 2) ? 3 : PLK_ANA_MINB)   // 3 blocks/SM: <= 136 registers
+__global__ void __launch_bounds__((kNCW + 1) * 32, (SPIN && NR == 2) ? PLK_ANA_MINB_S2 : PLK_ANA_MINB)
 legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cplx *__restrict__ X2, int pitch,
                      double *__restrict__ part, long long part_stride /* doubles per tile */,
                      const int *__restrict__ morder, int dbg) {
@@ -557,11 +570,53 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
     if (kend <= kw_min) {
       for (int i = lane; i < kChunk * NV; i += 32) myred[i] = 0.0;
     } else {
-      for (int kb = k0; kb < k0 + kChunk; kb += NB) {
+// one (even, odd) pair of l offsets K, K + 1 accumulated into slots B, B + 1 of ACC for all NR ring pairs of the thread;
+// reads past kend stay inside the stage buffer, those offsets are never written out
+#define PLK_ANA_STEP(ACC, K, B)                                                                                   \
+  {                                                                                                               \
+    const double2 ue = uvs[(K) - k0], uo = uvs[(K) - k0 + 1];                                                     \
+    _Pragma("unroll") for (int j = 0; j < NR; ++j) {                                                              \
+      if (!SPIN) {                                                                                                \
+        _Pragma("unroll") for (int vs = 0; vs < 2; ++vs) ACC[vs * NB + (B)] = fma(pc_[j], fa[j][vs], ACC[vs * NB + (B)]); \
+        const double n1 = fma(x[j] * ue.x, pc_[j], -pm_[j]);                                                      \
+        _Pragma("unroll") for (int vs = 0; vs < 2; ++vs) ACC[vs * NB + (B) + 1] = fma(n1, fb[j][vs], ACC[vs * NB + (B) + 1]); \
+        const double n2 = fma(x[j] * uo.x, n1, -pc_[j]);                                                          \
+        pm_[j] = n1; pc_[j] = n2;                                                                                 \
+      } else {                                                                                                    \
+        /* even offset: component v += p+ A_v + p- B_v */                                                         \
+        _Pragma("unroll") for (int vs = 0; vs < 4; ++vs)                                                          \
+          ACC[vs * NB + (B)] = fma(pc_[j], fa[j][vs], fma(qc_[j], fb[j][vs], ACC[vs * NB + (B)]));                \
+        const double np = fma(fma(x[j], ue.x, ue.y), pc_[j], -pm_[j]);                                            \
+        const double nq = fma(fma(x[j], ue.x, -ue.y), qc_[j], -qm_[j]);                                           \
+        /* odd offset: S+ += p+ A - p- B and S- += -(p+ A - p- B); the minus on S- is applied after the */      \
+        /* butterfly (flip) so that all four slots run the same instruction */                                    \
+        _Pragma("unroll") for (int vs = 0; vs < 4; ++vs)                                                          \
+          ACC[vs * NB + (B) + 1] = fma(np, fa[j][vs], fma(-nq, fb[j][vs], ACC[vs * NB + (B) + 1]));               \
+        const double np2 = fma(fma(x[j], uo.x, uo.y), np, -pc_[j]);                                               \
+        const double nq2 = fma(fma(x[j], uo.x, -uo.y), nq, -qc_[j]);                                              \
+        pm_[j] = np; pc_[j] = np2; qm_[j] = nq; qc_[j] = nq2;                                                     \
+      }                                                                                                           \
+    }                                                                                                             \
+  }
+#define PLK_ANA_BATCH(ACC, KB)                                                                                    \
+  {                                                                                                               \
+    _Pragma("unroll") for (int i = 0; i < 16; ++i) ACC[i] = 0.0;                                                  \
+    _Pragma("unroll") for (int b = 0; b < NB; b += 2) PLK_ANA_STEP(ACC, (KB) + b, b)                              \
+  }
+#define PLK_ANA_FINISH(ACC, KB)                                                                                   \
+  {                                                                                                               \
+    butterfly16<SPIN ? 2 : 1>(ACC, lane);                                                                         \
+    if ((lane & 1) == 0) myred[((KB) - k0 + bout) * NV + vout] = flip ? -ACC[0] : ACC[0];                         \
+  }
+      // batches that start beyond the end of the band produce nothing that is read back
+      const int kstop = min(k0 + kChunk, (kend + NB - 1) / NB * NB);
+      int kb = k0;
+      // ramp-up part of the band: some ring pair of the warp still waits for its start offset (seed injection)
+      for (; kb < kstop && (PLK_ANA_PIPE == 0 || kb <= kw_max); kb += NB) {
         double acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-        if (kb + NB > kw_min && kb < kend) {
+        if (kb + NB > kw_min) {
 #pragma unroll
           for (int b = 0; b < NB; b += 2) {
             const int k = kb + b;
@@ -577,40 +632,38 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
                   }
                 }
             }
-            // reads past kend stay inside the stage buffer; those offsets are never written out
-            const double2 ue = uvs[k - k0], uo = uvs[k - k0 + 1];
-#pragma unroll
-            for (int j = 0; j < NR; ++j) {
-              if (!SPIN) {
-#pragma unroll
-                for (int vs = 0; vs < 2; ++vs) acc[vs * NB + b] = fma(pc_[j], fa[j][vs], acc[vs * NB + b]);
-                const double n1 = fma(x[j] * ue.x, pc_[j], -pm_[j]);
-#pragma unroll
-                for (int vs = 0; vs < 2; ++vs) acc[vs * NB + b + 1] = fma(n1, fb[j][vs], acc[vs * NB + b + 1]);
-                const double n2 = fma(x[j] * uo.x, n1, -pc_[j]);
-                pm_[j] = n1; pc_[j] = n2;
-              } else {
-                // even offset: component v += p+ A_v + p- B_v
-#pragma unroll
-                for (int vs = 0; vs < 4; ++vs)
-                  acc[vs * NB + b] = fma(pc_[j], fa[j][vs], fma(qc_[j], fb[j][vs], acc[vs * NB + b]));
-                const double np = fma(fma(x[j], ue.x, ue.y), pc_[j], -pm_[j]);
-                const double nq = fma(fma(x[j], ue.x, -ue.y), qc_[j], -qm_[j]);
-                // odd offset: S+ += p+ A - p- B and S- += -(p+ A - p- B); the minus on S- is applied after the
-                // butterfly (flip) so that all four slots run the same instruction
-#pragma unroll
-                for (int vs = 0; vs < 4; ++vs)
-                  acc[vs * NB + b + 1] = fma(np, fa[j][vs], fma(-nq, fb[j][vs], acc[vs * NB + b + 1]));
-                const double np2 = fma(fma(x[j], uo.x, uo.y), np, -pc_[j]);
-                const double nq2 = fma(fma(x[j], uo.x, -uo.y), nq, -qc_[j]);
-                pm_[j] = np; pc_[j] = np2; qm_[j] = nq; qc_[j] = nq2;
-              }
-            }
+            PLK_ANA_STEP(acc, k, b)
           }
           if (!(dbg & 1)) butterfly16<SPIN ? 2 : 1>(acc, lane);
         }
         if ((lane & 1) == 0) myred[(kb - k0 + bout) * NV + vout] = flip ? -acc[0] : acc[0];
       }
+      // steady state: software pipeline -- the cross-lane butterfly of one batch (a chain of five dependent
+      // SHFL + DADD levels, ~150 cycles of latency for an in-order warp) is issued next to the independent FMAs of
+      // the following batch, both in one basic block so that ptxas interleaves them
+      if (PLK_ANA_PIPE != 0 && kb < kstop) {
+        double A[16], B[16];
+        PLK_ANA_BATCH(A, kb)
+        kb += NB;
+#pragma unroll 1
+        while (kb + NB < kstop) {
+          PLK_ANA_BATCH(B, kb)
+          PLK_ANA_FINISH(A, kb - NB)
+          PLK_ANA_BATCH(A, kb + NB)
+          PLK_ANA_FINISH(B, kb)
+          kb += 2 * NB;
+        }
+        if (kb < kstop) {
+          PLK_ANA_BATCH(B, kb)
+          PLK_ANA_FINISH(A, kb - NB)
+          PLK_ANA_FINISH(B, kb)
+        } else {
+          PLK_ANA_FINISH(A, kb - NB)
+        }
+      }
+#undef PLK_ANA_STEP
+#undef PLK_ANA_BATCH
+#undef PLK_ANA_FINISH
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);

@@ -90,10 +90,12 @@ class qe_device:
     legs (already including the C^TE cross terms when relevant).  All are complex128 CUDA tensors of lmax_ivf.
     """
 
-    def __init__(self, nside, lmax_ivf, lmax_qlm):
+    def __init__(self, nside, lmax_ivf, lmax_qlm, plan_ivf=None, plan_qlm=None):
+        """plan_ivf / plan_qlm: objects with the `sht.Plan` transform methods; pass `dist_sht.DistPlan`s to split every
+        transform of one estimate over the GPUs of a box by m (BASELINE.json configs[4])."""
         self.nside, self.lmax_ivf, self.lmax_qlm = nside, lmax_ivf, lmax_qlm
-        self.plan_ivf = sht.get_plan(nside, lmax_ivf)
-        self.plan_qlm = sht.get_plan(nside, lmax_qlm)
+        self.plan_ivf = sht.get_plan(nside, lmax_ivf) if plan_ivf is None else plan_ivf
+        self.plan_qlm = sht.get_plan(nside, lmax_qlm) if plan_qlm is None else plan_qlm
         self.fl_t1 = _dfl(_grad_fl(lmax_ivf, 1, 't'))
         self.fl_p1 = _dfl(_grad_fl(lmax_ivf, 1, 'p'))
         self.fl_p3 = _dfl(_grad_fl(lmax_ivf, 3, 'p'))
