@@ -28,7 +28,7 @@ namespace plk {
 #define PLK_ANA_PIPE 1     // software-pipelined butterfly in the analysis kernel (0: plain loop)
 #endif
 #ifndef PLK_ANA_MINB_S2
-#define PLK_ANA_MINB_S2 3  // resident blocks asked for the spin-s NR = 2 analysis kernel
+#define PLK_ANA_MINB_S2 2  // resident blocks asked for the spin-s NR = 2 analysis kernel
 #endif
 constexpr int kChunk = PLK_CHUNK;      // l values per TMA stage (even)
 constexpr int kStages = 4;
