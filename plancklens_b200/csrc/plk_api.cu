@@ -103,7 +103,9 @@ struct plk_dist {
   int *d_mlist = nullptr;
   int *d_fft_list = nullptr;         // local ring pairs grouped by FFT size class
   std::vector<plk_plan::FftClass> classes;
-  cplx *X1 = nullptr, *X2 = nullptr; // own phase arrays: plain cudaMalloc so that CUDA IPC can export them
+  cplx *X1 = nullptr, *X2 = nullptr; // own exchange buffers: plain cudaMalloc so that CUDA IPC can export them.
+                                     // analysis: phase arrays [ring][pitch]; synthesis: transposed, [m][tpitch]
+  int tpitch = 0;
   cplx *px1[kMaxRanks] = {}, *px2[kMaxRanks] = {};
   bool opened[kMaxRanks] = {};
 };
@@ -391,7 +393,7 @@ static int ensure_work(plk_plan *p) {
 static DistX no_dist() { DistX d; memset(&d, 0, sizeof d); d.nranks = 1; d.mblk = 1; return d; }
 static DistX dist_x(const plk_dist *d) {
   DistX x = no_dist();
-  x.nranks = d->nranks; x.mblk = d->mblk;
+  x.nranks = d->nranks; x.mblk = d->mblk; x.tpitch = d->tpitch;
   for (int q = 0; q <= d->nranks; ++q) x.pair_lo[q] = d->pair_lo[q];
   for (int q = 0; q < d->nranks; ++q) { x.x1[q] = d->px1[q]; x.x2[q] = d->px2[q]; }
   return x;
@@ -563,15 +565,21 @@ extern "C" int plk_dist_partition(int nside, int mmax, int nranks, int mblk, int
     return fail(PLK_EINVAL, "bad argument (nside %d, nranks %d, mblk %d)", nside, nranks, mblk);
   const int npair = 2 * nside;
   if (pair_lo) {
-    // pixels of ring pair ip: both rings except the equator (last pair)
-    std::vector<long long> cum(npair + 1, 0);
+    // cost of ring pair ip in the ring-FFT / pixel stage: pixels (both rings except the equator, the last pair)
+    // times the measured relative cost per pixel of its FFT path (B200, nside 4096: power-of-two rings 1, Bluestein
+    // 2.6, single-buffer Bluestein with M = 8192 4.2)
+    std::vector<double> cum(npair + 1, 0.0);
+    const int nb1 = env_int("PLK_FFT_NB1_MINM", 8192);
     for (int ip = 0; ip < npair; ++ip) {
-      const long long n = 4LL * (ip < nside ? ip + 1 : nside);
-      cum[ip + 1] = cum[ip] + (ip == npair - 1 ? n : 2 * n);
+      const int q = ip < nside ? ip + 1 : nside;
+      const double n = 4.0 * q * (ip == npair - 1 ? 1 : 2);
+      double w = 1.0;
+      if (q > kTinyQ && (q & (q - 1)) != 0) w = nextpow2(2 * q - 1) >= nb1 ? 4.2 : 2.6;
+      cum[ip + 1] = cum[ip] + n * w;
     }
     pair_lo[0] = 0;
     for (int q = 1; q < nranks; ++q) {
-      const long long target = cum[npair] * q / nranks;
+      const double target = cum[npair] * q / nranks;
       int ip = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
       pair_lo[q] = std::min(std::max(ip, pair_lo[q - 1]), npair);
     }
@@ -628,7 +636,8 @@ extern "C" int plk_dist_create(plk_dist **out, plk_plan *p, int rank, int nranks
     DCK(cudaMalloc((void **)&d->d_fft_list, std::max<size_t>(list.size(), 1) * sizeof(int)));
     if (!list.empty()) DCK(cudaMemcpy(d->d_fft_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
-  const size_t xb = (size_t)p->nring * p->pitch * sizeof(cplx);
+  d->tpitch = (p->nring + 1) & ~1;
+  const size_t xb = std::max((size_t)p->nring * p->pitch, (size_t)(p->mmax + 1) * d->tpitch) * sizeof(cplx);
   DCK(cudaMalloc((void **)&d->X1, xb));
   DCK(cudaMalloc((void **)&d->X2, xb));
   DCK(cudaMemset(d->X1, 0, xb));
@@ -712,9 +721,25 @@ extern "C" int plk_dist_ring_synth(plk_dist *d, int spin, double *map1, double *
   if (!map1 || (spin > 0 && !map2)) return fail(PLK_EINVAL, "NULL buffer");
   plk_plan *p = d->plan;
   if ((rc = ensure_spin(p, spin))) return rc;
+  if ((rc = ensure_work(p))) return rc;
   const int *mtop = p->spins[spin].d.mtop;
-  if ((rc = ring_synth(p, d->X1, map1, (cudaStream_t)stream, mtop, d))) return rc;
-  if (spin > 0 && (rc = ring_synth(p, d->X2, map2, (cudaStream_t)stream, mtop, d))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // exchange buffer T[m][ring] -> phase array X[ring][m] for this rank's rings (north block, mirrored south block)
+  const int lo = d->pair_lo[d->rank], hi = d->pair_lo[d->rank + 1];
+  if (hi > lo) {
+    const int rr[2][2] = {{lo, hi}, {p->nring - hi, p->nring - lo}};
+    for (int c = 0; c < (spin ? 2 : 1); ++c)
+      for (int k = 0; k < 2; ++k) {
+        int r0 = rr[k][0], r1 = rr[k][1];
+        if (k == 1 && r0 < hi) r0 = hi;          // the equator belongs to the north block
+        if (r1 <= r0) continue;
+        dim3 g((r1 - r0 + 31) / 32, (p->mmax + 32) / 32), b(32, 8);
+        phase_transpose_kernel<<<g, b, 0, st>>>(c ? d->X2 : d->X1, d->tpitch, (cplx *)(c ? p->X2.p : p->X1.p), p->pitch, p->mmax, r0, r1);
+        LAUNCHED();
+      }
+  }
+  if ((rc = ring_synth(p, (const cplx *)p->X1.p, map1, st, mtop, d))) return rc;
+  if (spin > 0 && (rc = ring_synth(p, (const cplx *)p->X2.p, map2, st, mtop, d))) return rc;
   return PLK_OK;
 }
 // Analysis stage 1: ring FFTs of this rank's rings; column m goes to the phase array of the rank owning m

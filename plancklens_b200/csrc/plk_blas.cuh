@@ -282,6 +282,22 @@ __global__ void alm_combine_kernel(int lmax, AlmTerms t, cplx *__restrict__ out)
   out[i] = mk(re, im);
 }
 
+// X[r][m] = T[m][r] for rings r0 <= r < r1 and 0 <= m <= mmax (m-partitioned synthesis: exchange buffer -> phase array)
+__global__ void phase_transpose_kernel(const cplx *__restrict__ T, int tpitch, cplx *__restrict__ X, int pitch, int mmax,
+                                       int r0, int r1) {
+  __shared__ cplx tile[32][33];
+  const int rb = r0 + blockIdx.x * 32, mb = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int m = mb + i, r = rb + threadIdx.x;
+    if (m <= mmax && r < r1) tile[i][threadIdx.x] = T[(size_t)m * tpitch + r];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = rb + i, m = mb + threadIdx.x;
+    if (m <= mmax && r < r1) X[(size_t)r * pitch + m] = tile[threadIdx.x][i];
+  }
+}
+
 // real-harmonic packing used by the dense preconditioner (reference: qcinv/dense.py:16-53)
 __global__ void alm2rlm_kernel(int lmax, const cplx *__restrict__ alm, double *__restrict__ rlm) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;

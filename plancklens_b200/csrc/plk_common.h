@@ -43,8 +43,9 @@ struct cplx;
 struct DistX {                    // phase-array rows of ring pair ip live on rank q: pair_lo[q] <= ip < pair_lo[q+1]
   int nranks;                     // <= 1: single GPU (the plain X1 / X2 kernel arguments are used)
   int mblk;
+  int tpitch;                     // row pitch of the TRANSPOSED exchange buffers T[m][ring] (synthesis)
   int pair_lo[kMaxRanks + 1];
-  cplx *x1[kMaxRanks], *x2[kMaxRanks];   // every rank's phase arrays (own + CUDA-IPC peer mappings over NVLink)
+  cplx *x1[kMaxRanks], *x2[kMaxRanks];   // every rank's exchange buffers (own + CUDA-IPC peer mappings over NVLink)
 };
 
 // healpy m-major triangular index (mmax == lmax): idx(l,m) = m(2 lmax + 1 - m)/2 + l

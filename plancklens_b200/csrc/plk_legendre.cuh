@@ -386,11 +386,26 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
     if (ip >= g.npair) continue;
     const int rn = ip, rs = g.nring - 1 - ip;
     if (dx.nranks > 1) {
-      // m-partitioned transform: this rank holds only its m columns; the rows go straight into the phase array of
-      // the rank that owns the ring pair (peer-memory stores over NVLink -- the all-to-all is fused into the kernel)
+      // m-partitioned transform: this rank holds only its m columns; the values go straight into the exchange
+      // buffer of the rank that owns the ring pair (peer-memory stores over NVLink -- the all-to-all is fused into
+      // the kernel).  The exchange buffer is TRANSPOSED, T[m][ring]: the 32 ring pairs of a warp then form one
+      // contiguous 512-byte run per store instruction instead of 32 isolated 16-byte NVLink writes
+      // (measured: 2.8x slower Legendre stage with the [ring][m] layout); the owner transposes locally.
       int q = 0;
       while (q + 1 < dx.nranks && ip >= dx.pair_lo[q + 1]) ++q;
-      X1 = dx.x1[q]; X2 = dx.x2[q];
+      cplx *T1 = dx.x1[q] + (size_t)m * dx.tpitch, *T2 = dx.x2[q] + (size_t)m * dx.tpitch;
+      if (!SPIN) {
+        T1[rn] = mk(a0r[j] + a1r[j], a0i[j] + a1i[j]);
+        if (rs != rn) T1[rs] = mk(sg0 * (a0r[j] - a1r[j]), sg0 * (a0i[j] - a1i[j]));
+      } else {
+        T1[rn] = mk(a0r[j] + a1r[j], a0i[j] + a1i[j]);
+        T2[rn] = mk(a0i[j] - a1i[j], -(a0r[j] - a1r[j]));
+        if (rs != rn) {
+          T1[rs] = mk(sg0 * (b0r[j] + b1r[j]), sg0 * (b0i[j] + b1i[j]));
+          T2[rs] = mk(sg0 * (b0i[j] - b1i[j]), -sg0 * (b0r[j] - b1r[j]));
+        }
+      }
+      continue;
     }
     if (!SPIN) {
       X1[(size_t)rn * pitch + m] = mk(a0r[j] + a1r[j], a0i[j] + a1i[j]);

@@ -110,7 +110,28 @@ class DistPlan:
             if q != self.rank:
                 self.h.import_peer(q, bytes(t.cpu().numpy().tobytes()))
         self._tok = torch.zeros(1, device='cuda')
+        self._ev = None          # stage timing (enable_timing())
         self.barrier()
+
+    def enable_timing(self, on=True):
+        """CUDA-event timing of the stages of every transform; read with stage_times()."""
+        self._ev = [] if on else None
+
+    def _mark(self, name):
+        if self._ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._ev.append((name, e))
+
+    def stage_times(self):
+        """-> {stage: total ms since enable_timing()} ('barrier1' includes waiting for the slowest rank)"""
+        torch.cuda.synchronize()
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self._ev[:-1], self._ev[1:]):
+            if n1 != 'start':
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        self._ev = []
+        return out
 
     def barrier(self):
         """stream-ordered rendez-vous of all ranks (a one-element NCCL all-reduce on the current stream)"""
@@ -122,20 +143,30 @@ class DistPlan:
     # ---- sht.Plan call signatures
     def alm2map(self, alm, fl=None, out=None):
         out = torch.empty(self.npix, dtype=torch.float64, device='cuda') if out is None else out
+        self._mark('start')
         self.barrier()
+        self._mark('barrier0')
         self.h.legendre_synth(0, alm, None, fl, None)
+        self._mark('legendre_synth')
         self.barrier()
+        self._mark('barrier1')
         self.h.ring_synth(0, out, None)
+        self._mark('ring_synth')
         return out
 
     def alm2map_spin(self, glm, clm, spin, flg=None, flc=None, out=None):
         if out is None:
             out = (torch.empty(self.npix, dtype=torch.float64, device='cuda'),
                    torch.empty(self.npix, dtype=torch.float64, device='cuda'))
+        self._mark('start')
         self.barrier()
+        self._mark('barrier0')
         self.h.legendre_synth(spin, glm, clm, flg, flc)
+        self._mark('legendre_synth')
         self.barrier()
+        self._mark('barrier1')
         self.h.ring_synth(spin, out[0], out[1])
+        self._mark('ring_synth')
         return out
 
     def _reduce(self, *alms):
@@ -144,24 +175,36 @@ class DistPlan:
 
     def map2alm(self, m, fl=None, out=None, reduce=True):
         out = torch.empty(self.nalm, dtype=torch.complex128, device='cuda') if out is None else out
+        self._mark('start')
         self.barrier()
+        self._mark('barrier0')
         self.h.ring_anal(0, m, None)
+        self._mark('ring_anal')
         self.barrier()
+        self._mark('barrier1')
         self.h.legendre_anal(0, fl, None, out, None)
+        self._mark('legendre_anal')
         if reduce:
             self._reduce(out)
+            self._mark('allreduce_alm')
         return out
 
     def map2alm_spin(self, m1, m2, spin, flg=None, flc=None, out=None, reduce=True):
         if out is None:
             out = (torch.empty(self.nalm, dtype=torch.complex128, device='cuda'),
                    torch.empty(self.nalm, dtype=torch.complex128, device='cuda'))
+        self._mark('start')
         self.barrier()
+        self._mark('barrier0')
         self.h.ring_anal(spin, m1, m2)
+        self._mark('ring_anal')
         self.barrier()
+        self._mark('barrier1')
         self.h.legendre_anal(spin, flg, flc, out[0], out[1])
+        self._mark('legendre_anal')
         if reduce:
             self._reduce(out[0], out[1])
+            self._mark('allreduce_alm')
         return out
 
 

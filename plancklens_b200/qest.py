@@ -104,13 +104,18 @@ class qe_device:
         self.fl_out = _dfl(-np.sqrt(L * (L + 1)))
         npix = 12 * nside ** 2
         self._buf = [torch.empty(npix, dtype=torch.float64, device='cuda') for _ in range(10)]
+        # m-partitioned plans: this process owns (and multiplies) only the pixels of its own rings
+        pr = getattr(self.plan_ivf, 'pixel_ranges', None)
+        self._pix = [slice(lo, hi) for lo, hi in pr() if hi > lo] if (pr is not None and hasattr(self.plan_ivf, 'rank')) \
+            else [slice(None)]
 
     def t_products(self, tbar, twf, out=None):
         """(G t, C t) maps of the temperature estimator."""
         b = self._buf
         t = self.plan_ivf.alm2map(tbar, out=b[0])
         G, C = self.plan_ivf.alm2map_spin(twf, None, 1, flg=self.fl_t1, out=(b[1], b[2]) if out is None else out)
-        sht.map_mul2(G, C, t)
+        for s in self._pix:
+            sht.map_mul2(G[s], C[s], t[s])
         return G, C
 
     def p_products(self, ebar, bbar, ewf, bwf, out=None):
@@ -120,7 +125,8 @@ class qe_device:
         G3, C3 = self.plan_ivf.alm2map_spin(ewf, bwf, 3, flg=self.fl_p3, flc=self.fl_p3, out=(b[4], b[5]))
         G1, C1 = self.plan_ivf.alm2map_spin(ewf, bwf, 1, flg=self.fl_p1, flc=self.fl_p1, out=(b[6], b[7]))
         re, im = (b[8], b[9]) if out is None else out
-        sht.map_qe_pp(Q, U, G3, C3, G1, C1, re, im)
+        for s in self._pix:
+            sht.map_qe_pp(Q[s], U[s], G3[s], C3[s], G1[s], C1[s], re[s], im[s])
         return re, im
 
     def analyse(self, re, im):
@@ -146,8 +152,9 @@ class qe_device:
         re, im = self.p_products(ebar, bbar, ewf, bwf)             # in b[8], b[9]
         if merge_analysis:
             G, C = self.t_products(tbar, twf)                       # in b[1], b[2]
-            sht.map_axpy(re, G, 1.0)
-            sht.map_axpy(im, C, 1.0)
+            for s in self._pix:
+                sht.map_axpy(re[s], G[s], 1.0)
+                sht.map_axpy(im[s], C[s], 1.0)
             return self.analyse(re, im)
         GP, CP = self.analyse(re, im)
         GT, CT = self.analyse(*self.t_products(tbar, twf))
