@@ -9,8 +9,8 @@ with the FFP10 fiducial spectra, 5' beam, 35 / 55 uK-arcmin).  One step = `qest.
 one simulation starting from its cached inverse-variance filtered alms (what `run_qlms.py -k p -dd` does after
 `-ivt -ivp`): 1 spin-0 + 4 spin-s syntheses, per-pixel products, spin-1 analysis -> (glm, clm).
   value : steps/s with the filtered alms resident in HBM (CUDA events, max over ranks)
-  e2e   : the same through `qest.library.eval_qlm` with numpy (pinned host) inputs and outputs, H2D + D2H in the
-          timed region
+  e2e   : the same through `qest.library.eval_qlms` (the pipelined form of `eval_qlm`) with numpy (pinned host) inputs
+          and numpy outputs, every H2D + D2H inside the timed region
   roofline : the dominant kernel, `legendre_synth_kernel<spin>`; achieved = 24 flop x N_lm x 2 nside per launch
            / its mean CUDA-event duration inside the timed region; bound = FP64 FMA pipe
   cpu_baseline : the CPU oracle port of the same step on a bounded sample (every MSTEP-th m), host cores stated
@@ -302,12 +302,12 @@ def main():
     ms_dev = float(t_dev.item())
 
     # ---------------- end to end through the public API (numpy in pinned host memory -> numpy out)
-    for i in range(2):
-        lib.eval_qlm('p', i)
+    for _ in lib.eval_qlms('p', range(3)):
+        pass
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        G, C = lib.eval_qlm('p', args.warmup + i)
+    for _, G, C in lib.eval_qlms('p', range(args.warmup, args.warmup + args.steps)):
+        pass
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -331,9 +331,10 @@ def main():
             "config": workload_config(),
             "e2e": {"value": world * args.steps / s_e2e, "unit": "qlm/s",
                     "h2d_bytes_per_step": 3 * alm_size(LMAX_IVF) * 16, "d2h_bytes_per_step": 2 * nalm_q * 16,
-                    "api": "plancklens_b200.qest.library.eval_qlm('p', idx) with numpy alms in pinned host memory"},
+                    "api": "plancklens_b200.qest.library.eval_qlms('p', idxs): numpy alms in pinned host memory in, numpy qlm out; "
+                           "H2D of sim i+1 / transforms of sim i / D2H of sim i-1 overlap on two streams, every copy inside the timed region"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "legendre_synth_kernel<spin,NR=2>", "achieved": achieved, "peak": peak_meas,
+            "roofline": {"bound": "fp64", "kernel": "legendre_synth_kernel<spin,NR=4>", "achieved": achieved, "peak": peak_meas,
                          "unit": "TFLOP/s", "frac": achieved / peak_meas,
                          "peak_source": "DFMA microbenchmark in libplk_b200 (plk_fp64_peak) run in this process; MEASURED_PEAKS.json "
                                         "holds only HBM and bf16 peaks, neither bounds this kernel",

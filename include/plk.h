@@ -114,6 +114,8 @@ int plk_dense_matvec_dev(int n, const double *A, const double *x, double *y, voi
 /* ---- per-pixel passes (device pointers, n pixels) */
 /* y = y * a            */
 int plk_map_mul_dev(long long n, double *y, const double *a, void *stream);
+/* result_dev[0] = sum_p a_p b_p: template_removal.py:53, :80, :107 (template_map / qmap / umap .dot) */
+int plk_map_dot_dev(long long n, const double *a, const double *b, double *result_dev, void *stream);
 /* QE leg products (qest.py:256-257): g *= t ; c *= t */
 int plk_map_mul2_dev(long long n, double *g, double *c, const double *t, void *stream);
 /* qest.py:276-278:  (re,im) = (q - i u)(g3 + i c3) - (q + i u)(g1 - i c1) */

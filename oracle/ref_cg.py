@@ -42,13 +42,13 @@ def dot_pp(a, b):
 class ninv_tt:
     """opfilt_tt.alm_filter_ninv with monopole + dipole marginalisation (opfilt_tt.py:99-205)."""
 
-    def __init__(self, n_inv, b_transf, marge_monopole=True, marge_dipole=True):
+    def __init__(self, n_inv, b_transf, marge_monopole=True, marge_dipole=True, marge_maps=()):
         self.n_inv = np.asarray(n_inv, dtype=float)
         self.b = np.asarray(b_transf, dtype=float)
         self.npix = self.n_inv.size
         self.nside = rg.npix2nside(self.npix)
         theta, phi = rg.pix2ang(self.nside)
-        modes = []
+        modes = [np.asarray(m, dtype=float) for m in marge_maps]     # template maps first (opfilt_tt.py:115-119)
         if marge_monopole:
             modes.append(np.ones(self.npix))
         if marge_dipole:
@@ -92,17 +92,34 @@ def pre_diag_tt(cltt, nf):
 
 
 class ninv_pp:
-    """opfilt_pp.alm_filter_ninv, 1 or 3 noise maps (opfilt_pp.py:253-303)."""
+    """opfilt_pp.alm_filter_ninv, 1 or 3 noise maps (opfilt_pp.py:253-303), Q / U template maps (:149-185, :279-290)."""
 
-    def __init__(self, n_inv, b_transf):
+    def __init__(self, n_inv, b_transf, marge_qmaps=(), marge_umaps=()):
         self.n_inv = [np.asarray(n, dtype=float) for n in n_inv]
+        self.tq = [np.asarray(m, dtype=float) for m in marge_qmaps]
+        self.tu = [np.asarray(m, dtype=float) for m in marge_umaps]
+        self.tniti = []
+        for ts in (self.tq, self.tu):
+            if len(ts):
+                P = np.array(ts)
+                ev, ew = np.linalg.eigh(np.einsum('ap,p,bp->ab', P, self.n_inv[0], P))
+                self.tniti.append(ew @ np.diag(1.0 / ev) @ ew.T)
+            else:
+                self.tniti.append(None)
         self.b = np.asarray(b_transf, dtype=float)
         self.npix = self.n_inv[0].size
         self.nside = rg.npix2nside(self.npix)
 
     def apply_map(self, q, u):
         if len(self.n_inv) == 1:
-            return q * self.n_inv[0], u * self.n_inv[0]
+            q, u = q * self.n_inv[0], u * self.n_inv[0]
+            out = []
+            for m, ts, ti in ((q, self.tq, self.tniti[0]), (u, self.tu, self.tniti[1])):
+                if ti is not None:
+                    P = np.array(ts)
+                    m = m - self.n_inv[0] * ((ti @ (P @ m)) @ P)
+                out.append(m)
+            return out[0], out[1]
         return q * self.n_inv[0] + self.n_inv[1] * u, u * self.n_inv[2] + self.n_inv[1] * q
 
     def apply_alm(self, e, b):

@@ -54,6 +54,7 @@ _SIGS = {
     'plk_profile_read': (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)]),
     'plk_fp64_peak': (c_int, [ctypes.POINTER(c_dbl), c_int]),
     'plk_map_mul_dev': (c_int, [c_ll, vp, vp, vp]),
+    'plk_map_dot_dev': (c_int, [c_ll, vp, vp, vp, vp]),
     'plk_map_mul2_dev': (c_int, [c_ll, vp, vp, vp, vp]),
     'plk_map_qe_pp_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'plk_map_cmul_acc_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp]),

@@ -886,6 +886,17 @@ extern "C" int plk_map_mul_dev(long long n, double *y, const double *a, void *st
   LAUNCHED();
   return PLK_OK;
 }
+extern "C" int plk_map_dot_dev(long long n, const double *a, const double *b, double *result_dev, void *stream) {
+  if (!a || !b || !result_dev || n < 0) return fail(PLK_EINVAL, "bad argument");
+  int rc = scratch();
+  if (rc) return rc;
+  const int nb = 148 * 8;
+  map_dot_partial_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(n, a, b, g_scratch);
+  LAUNCHED();
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, nb, 1, result_dev);
+  LAUNCHED();
+  return PLK_OK;
+}
 extern "C" int plk_map_mul2_dev(long long n, double *g, double *c, const double *t, void *stream) {
   if (!g || !c || !t) return fail(PLK_EINVAL, "NULL buffer");
   map_mul2_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, g, c, t);

@@ -161,6 +161,16 @@ __global__ void alm_splice_kernel(int lmax_lo, const cplx *__restrict__ lo, int 
 }
 
 // ------------------------------------------------------------------ per-pixel passes
+// partial[b] = sum over the block's grid-stride share of a_p b_p (fixed grid -> fixed summation order)
+__global__ void map_dot_partial_kernel(long long n, const double *__restrict__ a, const double *__restrict__ b,
+                                       double *__restrict__ partial) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = fma(a[i], b[i], acc);
+  const double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
 __global__ void map_mul_kernel(long long n, double *__restrict__ y, const double *__restrict__ a) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] *= a[i];

@@ -5,6 +5,7 @@ mini-language -- `split(low, lsplit, high)`, `diag_cl`, `dense`, `dense(file)`, 
 (multigrid.py:37, :113-160).  All vectors stay on the GPU from `calc_prep` to `apply_fini`.
 """
 import copy
+import gc
 import os
 import re
 import sys
@@ -141,8 +142,17 @@ class graphed_op:
         if self.graph is None:
             self.v_in = _vec_clone(v)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.v_out = self.op(self.v_in)
+            # Dead reference cycles may own CUDA graphs / plans whose destructors call cudaFree, which is illegal while
+            # a stream is capturing: collect them now and keep the cyclic collector off during the capture.
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    self.v_out = self.op(self.v_in)
+            finally:
+                if gc_was_on:
+                    gc.enable()
             self.graph = g
         for dst, src in zip(_vec_tensors(self.v_in), _vec_tensors(v)):
             dst.copy_(src)

@@ -15,7 +15,7 @@ import torch
 
 from .. import hp, sht
 from ..utils import clhash
-from . import dense, util
+from . import dense, template_removal, util
 from .util_alm import dalm, eblm
 
 
@@ -150,8 +150,8 @@ def pre_op_dense(lmax, fwd_op, cache_fname=None):
 
 class alm_filter_ninv(object):
     """Pixel-space polarization inverse noise: one map (QQ = UU) or three (QQ, QU, UU)
-    (reference: opfilt_pp.py:110-303).  Template projection in polarization (marge_qmaps / marge_umaps)
-    is not on the GPU path yet."""
+    (reference: opfilt_pp.py:110-303), with independent Q and U template marginalisation (marge_qmaps /
+    marge_umaps, single n_inv map only -- as in the reference, opfilt_pp.py:153)."""
 
     def __init__(self, n_inv, b_transf, nlev_febl=None, b_transf_b=None, marge_qmaps=(), marge_umaps=()):
         self.b_transf_e = np.asarray(b_transf, dtype=float)
@@ -161,11 +161,10 @@ class alm_filter_ninv(object):
         self.n_inv = None
         self.nlev_febl = nlev_febl
         self._n_inv = n_inv   # maps, paths or lists of those
-        if len(marge_qmaps) > 0 or len(marge_umaps) > 0:
-            raise NotImplementedError("Q/U template marginalisation is not on the GPU path yet")
         self.marge_qmaps = marge_qmaps
         self.marge_umaps = marge_umaps
-        self.wmarg = False
+        self.wmarg = (max(len(self.marge_qmaps), len(self.marge_umaps)) > 0)
+        self.tniti = None
         self.templates_p = []
         self._ninv_d = None
         self._fl_cache = {}
@@ -178,6 +177,38 @@ class alm_filter_ninv(object):
             assert len(self.n_inv) in [1, 3], len(self.n_inv)
             self.nside = hp.npix2nside(len(self.n_inv[0]))
             self._ninv_d = [_dev(n) for n in self.n_inv]
+
+    def _build_tniti(self):
+        """(P^t N^{-1} P)^{-1} of the Q and of the U templates, block diagonal (reference: opfilt_pp.py:149-185)."""
+        if not self.wmarg or self.tniti is not None:
+            return
+        self._load_ninv()
+        assert len(self.n_inv) == 1, 'QQ QU UU not implemented'
+        blocks = []
+        for im, marge_m in enumerate((self.marge_qmaps, self.marge_umaps)):
+            if len(marge_m) == 0:
+                continue
+            tfunc = template_removal.template_qmap if im == 0 else template_removal.template_umap
+            templates = [tfunc(np.asarray(util.read_map(m), dtype=float)) for m in marge_m]
+            ntm = [sht.map_mul(t.map.clone(), self._ninv_d[0]) for t in templates]
+            n = len(templates)
+            mat = np.zeros((n, n))
+            for i in range(n):
+                for j in range(i + 1):
+                    mat[i, j] = mat[j, i] = float(sht.map_dot(templates[j].map, ntm[i]).item())
+            eigv, eigw = np.linalg.eigh(mat)
+            blocks.append(np.dot(np.dot(eigw, np.diag(1.0 / eigv)), np.transpose(eigw)))
+            self.templates_p += templates
+            self._ntm_p = getattr(self, '_ntm_p', []) + ntm
+        nmodes = sum(b.shape[0] for b in blocks)
+        self.tniti = np.zeros((nmodes, nmodes))
+        i0 = 0
+        for b in blocks:
+            self.tniti[i0:i0 + b.shape[0], i0:i0 + b.shape[0]] = b
+            i0 += b.shape[0]
+        self._mtniti_d = _dev(-self.tniti.reshape(-1))
+        self._csum = torch.zeros(nmodes, dtype=torch.float64, device='cuda')
+        self._mcoef = torch.zeros(nmodes, dtype=torch.float64, device='cuda')
 
     def _calc_febl(self):
         self._load_ninv()
@@ -207,8 +238,12 @@ class alm_filter_ninv(object):
         return n_inv_cl_e, n_inv_cl_b
 
     def hashdict(self):
+        t_hash = []
+        if self.wmarg:
+            t_hash = [util.mask_hash(m, dtype=np.float32) for m in self.marge_qmaps]
+            t_hash += [util.mask_hash(m, dtype=np.float32) for m in self.marge_umaps]
         return {'n_inv': [util.mask_hash(n, dtype=np.float16) for n in self._n_inv],
-                'b_transf': clhash(self.b_transf), 'templates_p': []}
+                'b_transf': clhash(self.b_transf), 'templates_p': t_hash}
 
     def degrade(self, nside):
         self._load_ninv()
@@ -250,6 +285,16 @@ class alm_filter_ninv(object):
         u = sht.dev_map(umap) if host else umap
         if len(self.n_inv) == 1:
             sht.map_mul2(q, u, self._ninv_d[0])
+            if self.wmarg:
+                # (q, u) -= N^{-1} P (P^t N^{-1} P)^{-1} P^t (q, u)   (reference: opfilt_pp.py:279-290), on the device
+                self._build_tniti()
+                for j, t in enumerate(self.templates_p):
+                    sht.map_dot(t.map, q if t.comp == 0 else u, out=self._csum[j:j + 1])
+                n = self._csum.numel()
+                sht.check(sht._lib.load().plk_dense_matvec_dev(n, sht._ptr(self._mtniti_d), sht._ptr(self._csum),
+                                                               sht._ptr(self._mcoef), sht._stream()))
+                for j, t in enumerate(self.templates_p):
+                    sht.map_axpy_dev(q if t.comp == 0 else u, self._ntm_p[j], self._mcoef[j:j + 1])
         else:
             sht.map_ninv3(q, u, self._ninv_d[0], self._ninv_d[1], self._ninv_d[2])
         if host:

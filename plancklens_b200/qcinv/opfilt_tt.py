@@ -156,9 +156,9 @@ class alm_filter_ninv(object):
         else:
             n_inv = util.load_map(n_inv)
         n_inv = np.asarray(n_inv, dtype=float)
-        if len(marge_maps) > 0 or marge_uptolmin >= 0:
-            raise NotImplementedError("template maps / marge_uptolmin are not on the GPU path yet; "
-                                      "monopole and dipole marginalisation are (SURVEY.md section 8a)")
+        if marge_uptolmin >= 0:
+            raise NotImplementedError("marge_uptolmin is not on the GPU path; monopole, dipole and template-map "
+                                      "marginalisation are (SURVEY.md section 8a)")
         nz = n_inv != 0.0
         print("opfilt_tt: inverse noise map std dev / av = %.3e" % (np.std(n_inv[nz]) / np.average(n_inv[nz])))
 
@@ -171,6 +171,10 @@ class alm_filter_ninv(object):
         self.marge_uptolmin = marge_uptolmin
         self.templates = []
         self.templates_hash = []
+        for tmap in [np.asarray(util.load_map(m), dtype=float) for m in marge_maps]:   # reference order: maps first
+            assert len(n_inv) == len(tmap)
+            self.templates.append(template_removal.template_map(tmap))
+            self.templates_hash.append(hashlib.sha1(np.ascontiguousarray(tmap).view(np.uint8)).hexdigest())
         if marge_monopole:
             self.templates.append(template_removal.template_monopole())
         if marge_dipole:
@@ -179,25 +183,46 @@ class alm_filter_ninv(object):
         self._ninv_d = _dev(n_inv)
         self._fl_cache = {}
         self._plan0 = sht.get_plan(self.nside, max(len(self.b_transf) - 1, 1))
-        self._sums = torch.zeros(4, dtype=torch.float64, device='cuda')
+        # Internal mode order: (1, x, y, z) analytic modes first (slots of unused ones stay empty), then the template
+        # maps; `Pt_Nn1_P_inv` is kept in the reference's order (maps, monopole, dipole).
+        self._tmaps = [t for t in self.templates if isinstance(t, template_removal.template_map)]
+        nt = 4 + len(self._tmaps)
+        self._sums = torch.zeros(nt, dtype=torch.float64, device='cuda')
         if len(self.templates) != 0:
-            modes = [i for t in self.templates for i in t.modes]
-            # P^t N^{-1} P on the active modes: row a = sum_p n_inv mode_a {1, x, y, z}
-            full = np.zeros((4, 4))
+            amodes = [i for t in self.templates for i in t.modes]
+            act = amodes + [4 + i for i in range(len(self._tmaps))]
+            # P^t N^{-1} P: row a = sum_p n_inv mode_a {1, x, y, z, tmap_0, ...}
+            full = np.zeros((nt, nt))
             minus_eye = -torch.eye(4, dtype=torch.float64, device='cuda')
-            for a in modes:
-                ea = torch.zeros(4, dtype=torch.float64, device='cuda')
-                ea[a] = 1.0
-                tmp = torch.zeros(self.npix, dtype=torch.float64, device='cuda')
-                self._plan0.modes_sub(tmp, self._ninv_d, ea, minus_eye.reshape(-1))   # tmp = n_inv * mode_a
-                full[a] = self._plan0.modes_dot(tmp).cpu().numpy()
-            sub = full[np.ix_(modes, modes)]
+            self._ntm = []                       # n_inv * template map, what apply_map subtracts
+            for a in act:
+                if a < 4:
+                    ea = torch.zeros(4, dtype=torch.float64, device='cuda')
+                    ea[a] = 1.0
+                    tmp = torch.zeros(self.npix, dtype=torch.float64, device='cuda')
+                    self._plan0.modes_sub(tmp, self._ninv_d, ea, minus_eye.reshape(-1))   # tmp = n_inv * mode_a
+                else:
+                    tmp = sht.map_mul(self._tmaps[a - 4].map.clone(), self._ninv_d)
+                    self._ntm.append(tmp)
+                full[a, :4] = self._plan0.modes_dot(tmp).cpu().numpy()
+                for j, t in enumerate(self._tmaps):
+                    full[a, 4 + j] = float(sht.map_dot(t.map, tmp).item())
+            sub = full[np.ix_(act, act)]
             sub = 0.5 * (sub + sub.T)
             eigv, eigw = np.linalg.eigh(sub)
-            self.Pt_Nn1_P_inv = np.dot(np.dot(eigw, np.diag(1.0 / eigv)), np.transpose(eigw))
-            pinv4 = np.zeros((4, 4))
-            pinv4[np.ix_(modes, modes)] = self.Pt_Nn1_P_inv
-            self._pinv_d = _dev(pinv4.reshape(-1))
+            inv = np.dot(np.dot(eigw, np.diag(1.0 / eigv)), np.transpose(eigw))
+            ref_order = [act.index(4 + i) for i in range(len(self._tmaps))] + [act.index(a) for a in amodes]
+            self.Pt_Nn1_P_inv = inv[np.ix_(ref_order, ref_order)]
+            pinv = np.zeros((nt, nt))
+            pinv[np.ix_(act, act)] = inv
+            if len(self._tmaps) == 0:
+                self._pinv_d = _dev(pinv.reshape(-1))
+            else:
+                self._pinv_d = _dev(pinv.reshape(-1))
+                self._mpinv_d = _dev(-pinv.reshape(-1))
+                self._eye4_d = torch.eye(4, dtype=torch.float64, device='cuda').reshape(-1).contiguous()
+                self._coef = torch.zeros(nt, dtype=torch.float64, device='cuda')
+                self._mcoef = torch.zeros(nt, dtype=torch.float64, device='cuda')
 
         if nlev_ftl is None:
             nlev_ftl = 10800. / np.sqrt(np.sum(self.n_inv) / (4.0 * np.pi)) / np.pi
@@ -251,9 +276,22 @@ class alm_filter_ninv(object):
         host = not isinstance(tmap, torch.Tensor)
         t = sht.dev_map(tmap) if host else tmap
         plan = sht.get_plan(self.nside, self._plan0.lmax)
-        if len(self.templates) != 0:
+        if len(self.templates) != 0 and len(self._tmaps) == 0:
             plan.modes_dot(t, w=self._ninv_d, out=self._sums)          # t *= n_inv ; sums = P^t t
             plan.modes_sub(t, self._ninv_d, self._sums, self._pinv_d)    # t -= n_inv P (P^t N^-1 P)^-1 sums
+        elif len(self.templates) != 0:
+            # with template maps (reference: opfilt_tt.py:193-205 with template_removal.template_map): all on the
+            # device, no host synchronisation
+            lib = sht._lib.load()
+            nt = self._sums.numel()
+            plan.modes_dot(t, w=self._ninv_d, out=self._sums[:4])      # t *= n_inv ; analytic sums
+            for j, tm in enumerate(self._tmaps):
+                sht.map_dot(tm.map, t, out=self._sums[4 + j:5 + j])
+            sht.check(lib.plk_dense_matvec_dev(nt, sht._ptr(self._pinv_d), sht._ptr(self._sums), sht._ptr(self._coef), sht._stream()))
+            sht.check(lib.plk_dense_matvec_dev(nt, sht._ptr(self._mpinv_d), sht._ptr(self._sums), sht._ptr(self._mcoef), sht._stream()))
+            plan.modes_sub(t, self._ninv_d, self._coef[:4], self._eye4_d)
+            for j, ntm in enumerate(self._ntm):
+                sht.map_axpy_dev(t, ntm, self._mcoef[4 + j:5 + j])
         else:
             sht.map_mul(t, self._ninv_d)
         if host:

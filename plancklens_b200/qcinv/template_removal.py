@@ -14,6 +14,26 @@ class template:
     modes = ()       # indices into (1, x, y, z)
 
 
+class template_map(template):
+    """One pixel-space template (reference: template_removal.py:36-53); `map` is a float64 CUDA tensor."""
+    nmodes = 1
+
+    def __init__(self, m):
+        import torch
+        from .. import sht
+        self.map = m if isinstance(m, torch.Tensor) else sht.dev_map(m)
+
+
+class template_qmap(template_map):
+    """Template acting on the Q map only (reference: template_removal.py:56-82)."""
+    comp = 0
+
+
+class template_umap(template_map):
+    """Template acting on the U map only (reference: template_removal.py:85-113)."""
+    comp = 1
+
+
 class template_monopole(template):
     nmodes = 1
     modes = (0,)

@@ -294,6 +294,82 @@ class library:
         fun = {'ptt': self._get_sim_Tgclm, 'p_p': self._get_sim_Pgclm, 'p': self._get_sim_MVgclm}[k]
         return fun(idx, k, swapped=swapped)
 
+    def eval_qlms(self, k, idxs):
+        """Pipelined `eval_qlm` over many simulations: yields (idx, G, C) in order (numpy out, same legs on both
+        sides -- the `qlms_dd` case).
+
+        Three things run concurrently: the host -> device copy of simulation i + 1's filtered alms (copy stream),
+        the transforms of simulation i (compute stream), and the device -> host copy plus the caller's handling of
+        estimate i - 1.  Inputs and outputs are double buffered; pinned host arrays (torch `pin_memory`) are copied
+        asynchronously, pageable ones go through pinned staging buffers."""
+        assert k in ['ptt', 'p_p', 'p'], k
+        assert self.f2map1.ivfs is self.f2map2.ivfs, "pipelined evaluation covers identical legs; use eval_qlm otherwise"
+        ivfs, f2 = self.f2map1.ivfs, self.f2map2
+        main, cs = torch.cuda.current_stream(), torch.cuda.Stream()
+        ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]
+        h2d_done, comp_done, d2h_done = ev(), ev(), ev()
+        dev_in, pin_in, pin_out, live = [None, None], [None, None], [None, None], [None, None]
+        names = {'ptt': ('t',), 'p_p': ('e', 'b'), 'p': ('t', 'e', 'b')}[k]
+
+        def fetch(idx):
+            return [getattr(ivfs, 'get_sim_%slm' % n)(idx) for n in names]
+
+        def finish(slot, idx):
+            d2h_done[slot].synchronize()
+            G, C = pin_out[slot][0].numpy().copy(), pin_out[slot][1].numpy().copy()
+            live[slot] = None
+            return idx, G, C
+
+        prev = None
+        for i, idx in enumerate(idxs):
+            s = i % 2
+            host = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128)) for a in fetch(idx)]
+            if dev_in[s] is None:
+                dev_in[s] = [torch.empty(h.numel(), dtype=torch.complex128, device='cuda') for h in host]
+                pin_in[s] = [None] * len(host)
+            if i >= 2:
+                cs.wait_event(comp_done[s])              # the transforms of simulation i - 2 have consumed this slot
+            with torch.cuda.stream(cs):
+                for j, h in enumerate(host):
+                    if not h.is_pinned():
+                        if pin_in[s][j] is None:
+                            pin_in[s][j] = torch.empty(h.numel(), dtype=torch.complex128, pin_memory=True)
+                        if i >= 2:
+                            h2d_done[s].synchronize()    # staging buffer free again
+                        pin_in[s][j].copy_(h)
+                        h = pin_in[s][j]
+                    dev_in[s][j].copy_(h, non_blocking=True)
+                h2d_done[s].record(cs)
+            live[s] = [host]                             # keep the host arrays alive until the copy has run
+            main.wait_event(h2d_done[s])
+            qe = self._engine(sht.alm_lmax(dev_in[s][0].numel()))
+            if k == 'ptt':
+                (dt,) = dev_in[s]
+                G, C = qe.ptt(dt, sht.almxfl(dt, f2._cl_dev()['tt']))
+            elif k == 'p_p':
+                de, db = dev_in[s]
+                c = f2._cl_dev()
+                G, C = qe.p_p(de, db, sht.almxfl(de, c['ee']), sht.almxfl(db, c['bb']))
+            else:
+                dt, de, db = dev_in[s]
+                wf = f2.wf_device(idx, 'p', (dt, de, db))
+                assert wf is not None, "the filtering library must expose its weights as `cl` (library_sepTP does)"
+                G, C = qe.p(dt, de, db, *wf, merge_analysis=self.merge_analysis)
+            comp_done[s].record(main)
+            if pin_out[s] is None:
+                pin_out[s] = [torch.empty(G.numel(), dtype=torch.complex128, pin_memory=True) for _ in range(2)]
+            cs.wait_event(comp_done[s])
+            with torch.cuda.stream(cs):
+                pin_out[s][0].copy_(G, non_blocking=True)
+                pin_out[s][1].copy_(C, non_blocking=True)
+                d2h_done[s].record(cs)
+            live[s].append((G, C))                       # device results stay allocated until their copy is done
+            if prev is not None:
+                yield finish(*prev)
+            prev = (s, idx)
+        if prev is not None:
+            yield finish(*prev)
+
     # ---- GPU evaluation
     def _engine(self, lmax_ivf):
         if self._qe is None or self._qe.lmax_ivf != lmax_ivf:
@@ -446,6 +522,14 @@ class lib_filt2map_sepTP(lib_filt2map):
             elm = elm + hp.almxfl(self.ivfs.get_sim_tlm(idx), self.clte)      # qest.py:613-618
         return elm, blm
 
+    def _cl_dev(self):
+        """filtering weights C_l^{TT, EE, BB} of the ivfs and C_l^{TE}, on the device"""
+        if not hasattr(self, '_cl_d'):
+            cl = self.ivfs.cl
+            self._cl_d = {x: _dfl(cl[x]) for x in ('tt', 'ee', 'bb')}
+            self._cl_d['te'] = _dfl(self.clte)
+        return self._cl_d
+
     def wf_device(self, idx, k, dev_bars=None):
         cl = getattr(self.ivfs, 'cl', None)
         if not isinstance(cl, dict) or not all(x in cl for x in ('tt', 'ee', 'bb')) or type(self.ivfs).__name__ in ('library_ftl', 'library_shuffle'):
@@ -453,10 +537,7 @@ class lib_filt2map_sepTP(lib_filt2map):
         if dev_bars is None:
             dev_bars = [sht.dev_alm(a) for a in (self.ivfs.get_sim_tlm(idx), self.ivfs.get_sim_elm(idx), self.ivfs.get_sim_blm(idx))]
         dt, de, db = dev_bars
-        if not hasattr(self, '_cl_d'):
-            self._cl_d = {x: _dfl(cl[x]) for x in ('tt', 'ee', 'bb')}
-            self._cl_d['te'] = _dfl(self.clte)
-        c = self._cl_d
+        c = self._cl_dev()
         lmax = sht.alm_lmax(dt.numel())
         if k == 'p':
             twf = _combine(lmax, [(dt, c['tt']), (de, c['te'])])       # qest.py:582-588

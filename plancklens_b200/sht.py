@@ -283,6 +283,20 @@ def map_mul(y, a):
     return y
 
 
+def map_dot(a, b, out=None):
+    """sum_p a_p b_p as a 1-element device tensor"""
+    out = torch.empty(1, dtype=torch.float64, device='cuda') if out is None else out
+    check(_lib.load().plk_map_dot_dev(a.numel(), _ptr(a), _ptr(b), _ptr(out), _stream()))
+    return out
+
+
+def map_axpy_dev(y, x, a_dev):
+    """y += a x on real maps, a read from device memory (1-element tensor); even number of pixels"""
+    assert y.numel() % 2 == 0
+    check(_lib.load().plk_alm_axpy_dev(y.numel() // 2, 0.0, _ptr(a_dev), _ptr(x), _ptr(y), _stream()))
+    return y
+
+
 def map_mul2(g, c, t):
     check(_lib.load().plk_map_mul2_dev(g.numel(), _ptr(g), _ptr(c), _ptr(t), _stream()))
 

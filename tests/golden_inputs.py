@@ -88,3 +88,13 @@ def qe_case(nside=32, lmax=48, lmax_qlm=64, seed=4321):
         q['elm' + tag] = rand_alm(rng, lmax, 2) * 1e-1
         q['blm' + tag] = rand_alm(rng, lmax, 2) * 1e-1
     return q
+
+
+def template_case(nside=32, seed=99):
+    """Pixel-space templates for the marginalisation tests: two T maps, one Q map, two U maps (seeded)."""
+    rng = np.random.default_rng(seed)
+    npix = 12 * nside ** 2
+    z = pix_z(nside)
+    return {'tmaps': [z ** 2 + 0.1 * rng.standard_normal(npix), np.cos(7 * z) + 0.3 * rng.standard_normal(npix)],
+            'qmaps': [1.0 + 0.5 * z + 0.2 * rng.standard_normal(npix)],
+            'umaps': [z ** 3 + 0.2 * rng.standard_normal(npix), rng.standard_normal(npix)]}

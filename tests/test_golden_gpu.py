@@ -66,6 +66,32 @@ def test_opfilt_pp_operators(gold, mods):
             assert rel_l2(e, gold['pp_prediag_e']) < 1e-12 and rel_l2(b, gold['pp_prediag_b']) < 1e-12
 
 
+def test_template_marginalisation_matches_reference(mods):
+    """opfilt_tt marge_maps (+ monopole + dipole) and opfilt_pp marge_qmaps / marge_umaps on the GPU against the
+    unmodified reference (tests/golden/reference_golden_templates.npz)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_templates.npz'))
+    c, t = gi.cg_case(), gi.template_case()
+    ua = mods['util_alm']
+    for tag, kw in (('tm', dict(marge_monopole=True, marge_dipole=True, marge_maps=t['tmaps'])),
+                    ('tmonly', dict(marge_maps=t['tmaps'][:1]))):
+        nf = mods['opfilt_tt'].alm_filter_ninv(c['ninv_t'], c['transf'], **kw)
+        assert rel_l2(nf.Pt_Nn1_P_inv, g[tag + '_pinv']) < 1e-9
+        m = c['tmap'].copy()
+        nf.apply_map(m)
+        assert rel_l2(m, g[tag + '_apply_map']) < 1e-11
+        y = mods['opfilt_tt'].fwd_op(c['cls'], nf)(ua.dalm.from_numpy(c['x_t'])).numpy()
+        assert rel_l2(y, g[tag + '_fwd']) < 1e-10
+        assert rel_l2(mods['opfilt_tt'].calc_prep(c['tmap'], c['cls'], nf).numpy(), g[tag + '_prep']) < 1e-10
+    nf = mods['opfilt_pp'].alm_filter_ninv(c['ninv_p1'], c['transf'], marge_qmaps=t['qmaps'], marge_umaps=t['umaps'])
+    q, u = c['qmap'].copy(), c['umap'].copy()
+    nf.apply_map([q, u])
+    assert rel_l2(q, g['pm_apply_q']) < 1e-11 and rel_l2(u, g['pm_apply_u']) < 1e-11
+    assert rel_l2(nf.tniti, g['pm_tniti']) < 1e-9
+    x = ua.eblm([ua.dalm.from_numpy(c['x_e']), ua.dalm.from_numpy(c['x_b'])])
+    e, b = mods['opfilt_pp'].fwd_op(c['cls'], nf)(x).numpy()
+    assert rel_l2(e, g['pm_fwd_e']) < 1e-10 and rel_l2(b, g['pm_fwd_b']) < 1e-10
+
+
 def _solve(mods, opfilt, descr, cls, nf, sol, data):
     chain = mods['multigrid'].multigrid_chain(opfilt, descr, cls, nf)
     chain.solve(sol, data)

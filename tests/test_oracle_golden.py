@@ -89,3 +89,22 @@ def test_pcg_iteration_count_and_trace(gold, built):
     assert np.allclose(eps, ref_trace[:, 2], rtol=1e-6)
     sol = almxfl(x, ref_cg._cli(c['cls']['tt']))     # apply_fini (opfilt_tt.py:39-41)
     assert rel_l2(sol, gold['tt_diag_soltn']) < 1e-8
+
+
+def test_template_marginalisation_matches_reference(built):
+    """Pixel-space templates (opfilt_tt marge_maps, opfilt_pp marge_qmaps / marge_umaps): oracle vs the unmodified
+    reference (tests/golden/make_golden_templates.py)."""
+    from oracle import ref_cg
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_templates.npz'))
+    c, t = gi.cg_case(), gi.template_case()
+    nf = ref_cg.ninv_tt(c['ninv_t'][0], c['transf'], marge_maps=t['tmaps'])
+    assert rel_l2(nf.Minv, g['tm_pinv']) < 1e-9
+    assert rel_l2(nf.apply_map(c['tmap']), g['tm_apply_map']) < 1e-11
+    assert rel_l2(ref_cg.fwd_tt(c['x_t'], c['cls']['tt'], nf), g['tm_fwd']) < 1e-11
+    nf = ref_cg.ninv_tt(c['ninv_t'][0], c['transf'], marge_monopole=False, marge_dipole=False, marge_maps=t['tmaps'][:1])
+    assert rel_l2(nf.apply_map(c['tmap']), g['tmonly_apply_map']) < 1e-11
+    nfp = ref_cg.ninv_pp([c['ninv_p1'][0][0]], c['transf'], marge_qmaps=t['qmaps'], marge_umaps=t['umaps'])
+    q, u = nfp.apply_map(c['qmap'], c['umap'])
+    assert rel_l2(q, g['pm_apply_q']) < 1e-11 and rel_l2(u, g['pm_apply_u']) < 1e-11
+    fe, fb = ref_cg.fwd_pp(c['x_e'], c['x_b'], c['cls'], nfp)
+    assert rel_l2(fe, g['pm_fwd_e']) < 1e-11 and rel_l2(fb, g['pm_fwd_b']) < 1e-11

@@ -87,3 +87,29 @@ def test_cg_filter_equals_isotropic_filter_on_full_sky():
     ls = gi.alm_ls(lmax)
     sel = (ls >= 2) & (ls <= nside)        # band-limited part, where HEALPix quadrature is accurate
     assert rel_l2(sol.numpy()[sel], iso[sel]) < 2e-3
+
+
+@pytest.mark.parametrize('key', ['ptt', 'p_p', 'p'])
+def test_pipelined_eval_qlms_equals_eval_qlm(key, tmp_path):
+    """The double-buffered generator (H2D / transforms / D2H overlapped over consecutive simulations) returns exactly
+    what the one-at-a-time call returns, for pinned and for pageable host inputs."""
+    import torch
+    import bench
+    import golden_inputs as gi
+    from plancklens_b200 import qest
+    q = gi.qe_case()
+    rng = np.random.default_rng(3)
+    sims = []
+    for i in range(5):
+        alms = [gi.rand_alm(rng, q['lmax'], 2) * sc for sc in (1e-2, 1e-1, 1e-1)]
+        if i % 2 == 0:   # pinned
+            alms = [torch.from_numpy(a).pin_memory().numpy() for a in alms]
+        sims.append(alms)
+    ivfs = bench.mem_ivfs(sims, q['cls'], q['nside'])
+    lib = qest.library_sepTP(str(tmp_path / 'qlms'), ivfs, ivfs, q['cls']['te'], q['nside'], lmax_qlm=q['lmax_qlm'])
+    idxs = [0, 1, 2, 3, 4, 1]
+    got = list(lib.eval_qlms(key, idxs))
+    assert [g[0] for g in got] == idxs
+    for idx, G, C in got:
+        Gr, Cr = lib.eval_qlm(key, idx)
+        assert np.array_equal(G, Gr) and np.array_equal(C, Cr)
