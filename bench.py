@@ -229,6 +229,7 @@ def main():
     ap.add_argument('--impl', type=str, default='b200')
     ap.add_argument('--cpu-mstep', type=int, default=32)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cg', action='store_true', help="skip the masked-sky CG part of the metric (N = 1 only, ~2 min)")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -315,6 +316,44 @@ def main():
     s_e2e = float(t_e2e.item())
     assert np.all(np.isfinite(G[:100])) and np.any(G != 0)
 
+    # ---------------- the other estimators of the metric ('ptt', 'p_p'), device resident, rank 0 of a single-GPU run
+    extra = {}
+    if world == 1:
+        for key in ('ptt', 'p_p'):
+            def step_k(i, key=key):
+                dt, de, db = dev_sims[i % NPOOL]
+                c = f2._cl_dev()
+                if key == 'ptt':
+                    return qe.ptt(dt, sht.almxfl(dt, c['tt']))
+                return qe.p_p(de, db, sht.almxfl(de, c['ee']), sht.almxfl(db, c['bb']))
+            for i in range(2):
+                step_k(i)
+            torch.cuda.synchronize()
+            nk = max(4, args.steps // 2)
+            e0.record()
+            for i in range(nk):
+                step_k(i)
+            e1.record()
+            torch.cuda.synchronize()
+            extra['%s_qlm_per_s' % key] = nk / (e0.elapsed_time(e1) * 1e-3)
+        F0 = 8.0 * n_lm(LMAX_IVF) * 2 * NSIDE
+        Fs_ = 24.0 * n_lm(LMAX_IVF) * 2 * NSIDE
+        # flop per launch: SURVEY.md section 8d (8 / 24 per unit); the gradient-only kernel executes 16 per unit and is
+        # credited with what it executes
+        fl_k = {'synth_spin0': F0, 'anal_spin0': F0, 'synth_spins': Fs_, 'anal_spins': Fs_, 'synth_grad': Fs_ * 16. / 24.}
+        extra['legendre_kernels'] = {k: {"launches": v[0], "ms_per_launch": v[1] / max(v[0], 1),
+                                         "tflops": fl_k[k] / (v[1] / max(v[0], 1) * 1e-3) / 1e12}
+                                     for k, v in prof.items() if v[0] > 0}
+        if not args.no_cg:
+            import contextlib
+            sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+            try:
+                import bench_cg
+                with contextlib.redirect_stdout(sys.stderr):
+                    extra['masked_cg'] = bench_cg.run(NSIDE, LMAX_IVF, True, True, verbose=False)
+            except Exception as ex:
+                extra['masked_cg'] = {'failed': repr(ex)}
+
     if rank == 0:
         Fs = 24.0 * n_lm(LMAX_IVF) * 2 * NSIDE
         cnt, tot = prof['synth_spins']
@@ -324,6 +363,7 @@ def main():
         peak_nominal = 148 * 64 * 2 * sm_max * 1e6 / 1e12
         achieved = Fs / (k_ms * 1e-3) / 1e12
         share = {k: round(v[1] / ms_dev, 4) for k, v in prof.items()}
+        act = sht.get_plan(NSIDE, LMAX_IVF).active_fraction(2)
         line = {
             "metric": "QE qlms/sec ('p', nside 2048, lmax 2048)", "value": world * args.steps / (ms_dev * 1e-3), "unit": "qlm/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -339,10 +379,16 @@ def main():
                          "peak_source": "DFMA microbenchmark in libplk_b200 (plk_fp64_peak) run in this process; MEASURED_PEAKS.json "
                                         "holds only HBM and bf16 peaks, neither bounds this kernel",
                          "peak_nominal": peak_nominal, "frac_of_nominal": achieved / peak_nominal,
+                         "executed_share_of_volume": act, "achieved_executed": achieved * act,
+                         "frac_executed": achieved * act / peak_meas,
+                         "note": "achieved counts the full (l, m, ring-pair) volume of SURVEY.md section 8d; the kernel skips the "
+                                 "share below the 2^-120 start threshold near the poles (executed_share_of_volume), so frac can "
+                                 "exceed 1 -- frac_executed is the DFMA rate actually sustained",
                          "launch_ms": k_ms, "launches_timed": cnt, "flop_per_launch": Fs,
                          "traffic": 851e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_summary.md",
                          "kernel_share_of_step": share},
             "clocks": clocks,
+            "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

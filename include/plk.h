@@ -169,10 +169,14 @@ int plk_dist_legendre_anal(plk_dist *dist, int spin, const double *fl1, const do
                            void *stream);
 
 /* ---- measurement helpers (bench.py): per-kernel CUDA-event timing of the Legendre launches and the device's
- *      FP64 FMA peak.  kinds: 0 synthesis spin 0, 1 synthesis spin s, 2 analysis spin 0, 3 analysis spin s. */
+ *      FP64 FMA peak.  kinds: 0 synthesis spin 0, 1 synthesis spin s, 2 analysis spin 0, 3 analysis spin s,
+ *      4 synthesis spin s with zero curl input (gradient-only kernel: 16 instead of 24 flop per unit). */
 int plk_profile_enable(int on);
-int plk_profile_read(int *counts4, double *total_ms4);
+int plk_profile_read(int *counts5, double *total_ms5);
 int plk_fp64_peak(double *tflops, int reps);
+/* share of the (l, m, ring pair) volume the Legendre kernels walk for this spin (the rest lies below the 2^-120
+ * start threshold near the poles and is skipped) */
+int plk_plan_active_fraction(plk_plan *plan, int spin, double *frac);
 
 #ifdef __cplusplus
 }

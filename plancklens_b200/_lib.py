@@ -52,6 +52,7 @@ _SIGS = {
     'plk_dist_legendre_anal': (c_int, [vp, c_int, vp, vp, vp, vp, vp]),
     'plk_profile_enable': (c_int, [c_int]),
     'plk_profile_read': (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)]),
+    'plk_plan_active_fraction': (c_int, [vp, c_int, ctypes.POINTER(c_dbl)]),
     'plk_fp64_peak': (c_int, [ctypes.POINTER(c_dbl), c_int]),
     'plk_map_mul_dev': (c_int, [c_ll, vp, vp, vp]),
     'plk_map_dot_dev': (c_int, [c_ll, vp, vp, vp, vp]),

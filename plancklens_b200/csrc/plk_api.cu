@@ -43,7 +43,8 @@ static int fail(int code, const char *fmt, ...) {
   } while (0)
 
 // optional per-kernel timing of the Legendre launches (CUDA events on the launching stream)
-struct ProfRec { cudaEvent_t e0, e1; int kind; };   // kind: 0 synth spin0, 1 synth spin s, 2 anal spin0, 3 anal spin s
+struct ProfRec { cudaEvent_t e0, e1; int kind; };   // kind: 0 synth spin0, 1 synth spin s, 2 anal spin0, 3 anal spin s,
+                                                    //       4 synth spin s gradient-only
 static bool g_prof = false;
 static std::vector<ProfRec> g_prof_recs;
 static void prof_begin(int kind, cudaStream_t st) {
@@ -228,6 +229,22 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
       plk_plan::FftClass c;
       c.M = -1; c.nbatch = 0; c.offset = 0; c.count = hg.npair; c.smem = p->fft_smem; c.threads = 256;
       p->fft_classes.assign(1, c);
+    } else if (env_int("PLK_FFT_MERGE_256", 1)) {
+      // Large plans: all 256-thread classes (M <= 2048) ask for at most ~74 KB, i.e. the same three blocks per SM as
+      // the largest of them, so they run as ONE launch.  The near-polar classes hold a handful of ring pairs each and
+      // have long serial tails (aliasing folds of mmax / n terms per bin); launched one after the other they cost
+      // 50 - 110 us apiece, inside the big launch they hide behind the equatorial rings.
+      std::vector<plk_plan::FftClass> out;
+      plk_plan::FftClass m;
+      m.M = -1; m.nbatch = 0; m.offset = -1; m.count = 0; m.smem = 0; m.threads = 256;
+      for (const auto &c : p->fft_classes) {
+        if (c.threads != 256) { out.push_back(c); continue; }
+        if (m.offset < 0) m.offset = c.offset;
+        m.count += c.count;
+        m.smem = std::max(m.smem, c.smem);
+      }
+      if (m.count > 0) out.push_back(m);
+      p->fft_classes = out;
     }
   }
   if (p->fft_smem > 227 * 1024) { plk_plan_destroy(p); return fail(PLK_EINVAL, "ring FFT needs %d bytes of shared memory", p->fft_smem); }
@@ -418,13 +435,19 @@ static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *a
   const int nthr = (kNCW + 1) * 32;
 #define SYN(SP, NR)                                                                                              \
   legendre_synth_kernel<SP, NR><<<grid, nthr, leg_smem<SP, true>(NR), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, morder, dx)
-  prof_begin(spin ? 1 : 0, st);
+#define SYNG(NR)                                                                                                  \
+  legendre_synth_kernel<true, NR, true><<<grid, nthr, leg_smem<true, true>(NR), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, morder, dx)
+  const bool grad = spin > 0 && !alm2 && env_int("PLK_SYN_GRAD", 1);
+  prof_begin(spin ? (grad ? 4 : 1) : 0, st);
   if (spin == 0) {
     if (nr == 4) SYN(false, 4); else if (nr == 2) SYN(false, 2); else SYN(false, 1);
+  } else if (grad) {                                      // zero curl component: gradient-only kernel
+    if (nr == 4) SYNG(4); else if (nr == 2) SYNG(2); else SYNG(1);
   } else {
     if (nr == 4) SYN(true, 4); else if (nr == 2) SYN(true, 2); else SYN(true, 1);
   }
 #undef SYN
+#undef SYNG
   prof_end(st);
   LAUNCHED();
   return 0;
@@ -993,15 +1016,41 @@ extern "C" int plk_profile_enable(int on) {
   g_prof = on != 0;
   return PLK_OK;
 }
-// sums the recorded durations per kind (4 entries each): counts[k], total_ms[k]; synchronises the device
+// sums the recorded durations per kind (5 entries each): counts[k], total_ms[k]; synchronises the device
 extern "C" int plk_profile_read(int *counts, double *total_ms) {
   CK(cudaDeviceSynchronize());
-  for (int k = 0; k < 4; ++k) { counts[k] = 0; total_ms[k] = 0.0; }
+  for (int k = 0; k < 5; ++k) { counts[k] = 0; total_ms[k] = 0.0; }
   for (auto &r : g_prof_recs) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
     counts[r.kind] += 1; total_ms[r.kind] += ms;
   }
+  return PLK_OK;
+}
+
+// Share of the (l, m, ring pair) volume the Legendre kernels actually walk for this spin: 1 - the part below the
+// 2^-120 start threshold near the poles (skipped).  bench.py reports the roofline both on the algorithmic count of
+// SURVEY.md section 8d (full volume) and on this executed share.
+extern "C" int plk_plan_active_fraction(plk_plan *p, int spin, double *frac) {
+  CHECK_PLAN(p);
+  if (!frac) return fail(PLK_EINVAL, "NULL");
+  int rc = ensure_spin(p, spin);
+  if (rc) return rc;
+  const size_t ns = (size_t)(p->mmax + 1) * p->npair;
+  std::vector<int> ks(ns);
+  CK(cudaMemcpy(ks.data(), p->spins[spin].d.ks, ns * sizeof(int), cudaMemcpyDeviceToHost));
+  double act = 0.0, tot = 0.0;
+  for (int m = 0; m <= p->mmax; ++m) {
+    const int l0 = m > spin ? m : spin;
+    const int K = p->lmax - l0 + 1;
+    if (K <= 0) continue;
+    for (int ip = 0; ip < p->npair; ++ip) {
+      const int k = ks[(size_t)m * p->npair + ip];
+      tot += K;
+      if (k < K) act += K - k;
+    }
+  }
+  *frac = tot > 0 ? act / tot : 0.0;
   return PLK_OK;
 }
 

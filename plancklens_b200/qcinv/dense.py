@@ -99,14 +99,35 @@ class _pre_op_dense:
         print("computing dense preconditioner:")
         print("     lmax  =", lmax)
         print("     ntmpl =", ntmpl)
+        # Row i of the (symmetric) matrix = fwd_op applied to unit vector i.  The operator is a fixed, host-sync-free
+        # launch sequence, so it is captured once as a CUDA graph and replayed nrlm times (4225 for the default T
+        # chain): the fill is then bound by the small transforms, not by ~40 Python -> ctypes launches per row.
         tmat_d = torch.empty((nrlm, nrlm), dtype=torch.float64, device='cuda')
         unit = torch.zeros(nrlm, dtype=torch.float64, device='cuda')
+        col = self._pack(fwd_op(self._unpack(unit + 1.0)))     # eager warm-up: plans, tables, per-l factors
+        graph = None
+        if os.environ.get('PLK_CG_GRAPH', '1') != '0':
+            import gc
+            graph = torch.cuda.CUDAGraph()
+            gc.collect()
+            gc_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                    col = self._pack(fwd_op(self._unpack(unit)))
+            finally:
+                if gc_on:
+                    gc.enable()
+        one = torch.ones(1, dtype=torch.float64, device='cuda')
         for j, i in enumerate_progress(np.arange(nrlm), label='filling matrix'):
-            unit[i] = 1.0
-            col = self._pack(fwd_op(self._unpack(unit)))
-            tmat_d[:, i] = col
-            unit[i] = 0.0
-        tmat = tmat_d.cpu().numpy()
+            unit[i:i + 1].copy_(one)
+            if graph is not None:
+                graph.replay()
+            else:
+                col = self._pack(fwd_op(self._unpack(unit)))
+            tmat_d[i].copy_(col)
+            unit[i:i + 1].zero_()
+        tmat = tmat_d.cpu().numpy().T.copy()   # rows were filled (contiguous copies): column i = A e_i as in the reference
         print("   inverting M...")
         eigv, eigw = np.linalg.eigh(tmat)
         assert np.all(eigv[ntmpl:] > 0.)

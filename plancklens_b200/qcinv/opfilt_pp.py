@@ -117,6 +117,10 @@ class fwd_op:
         return self.calc(alm)
 
     def calc(self, alm):
+        if alm.is_zero():
+            # A 0 = 0 exactly (every stage is linear): skip the two spin-2 transforms on the zero start vector of the
+            # solver.  The reference has this shortcut in opfilt_tt (opfilt_tt.py:68) only; the result is identical.
+            return alm * 1.0
         nlm = alm * 1.0
         self.n_inv_filt.apply_alm(nlm)
         slm = self.s_inv_filt.calc(alm)

@@ -84,6 +84,12 @@ class Plan:
         except Exception:
             pass
 
+    def active_fraction(self, spin):
+        """share of the (l, m, ring pair) volume the Legendre kernels walk (the rest is skipped near the poles)"""
+        v = ctypes.c_double()
+        check(self.lib.plk_plan_active_fraction(self._h, int(spin), ctypes.byref(v)))
+        return float(v.value)
+
     def device_bytes(self):
         return int(self.lib.plk_plan_device_bytes(self._h))
 
@@ -265,10 +271,10 @@ def profile_enable(on=True):
 
 def profile_read():
     """-> {kind: (count, total_ms)} for kinds synth0, synths, anal0, anals"""
-    c = (ctypes.c_int * 4)()
-    t = (ctypes.c_double * 4)()
+    c = (ctypes.c_int * 5)()
+    t = (ctypes.c_double * 5)()
     check(_lib.load().plk_profile_read(c, t))
-    names = ['synth_spin0', 'synth_spins', 'anal_spin0', 'anal_spins']
+    names = ['synth_spin0', 'synth_spins', 'anal_spin0', 'anal_spins', 'synth_grad']
     return {n: (int(c[i]), float(t[i])) for i, n in enumerate(names)}
 
 
