@@ -91,8 +91,6 @@ class _pre_op_dense:
         raise NotImplementedError
 
     def compute_minv(self, lmax, fwd_op, cache_fname=None):
-        if cache_fname is not None:
-            assert not os.path.exists(cache_fname)
         self.lmax = lmax
         nrlm = self.ncomp * (lmax + 1) ** 2
         ntmpl = self._ntmpl(fwd_op)
@@ -140,8 +138,11 @@ class _pre_op_dense:
             eigv_inv[0:ntmpl] = 1.0
         self.minv = np.dot(np.dot(eigw, np.diag(eigv_inv)), np.transpose(eigw))
         if cache_fname is not None:
-            with open(cache_fname, 'wb') as f:
+            # several ranks may build the same matrix at once (one process per GPU): write-then-rename keeps readers safe
+            tmp = '%s.%d.tmp' % (cache_fname, os.getpid())
+            with open(tmp, 'wb') as f:
                 pk.dump([lmax, self.hashdict(lmax, fwd_op), self.minv], f)
+            os.replace(tmp, cache_fname)
 
     @staticmethod
     def hashdict(lmax, fwd_op):

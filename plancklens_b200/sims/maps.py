@@ -14,6 +14,9 @@ class cmb_maps(object):
         self.cl_transf_T = cl_transf
         self.cl_transf_P = np.copy(cl_transf) if cl_transf_P is None else cl_transf_P
         self.nside = nside
+        # device_maps = True: get_sim_tmap / get_sim_pmap return float64 CUDA tensors (signal synthesised and noise
+        # added on the GPU) which the cinv filters take as they are -- no 400 MB round trip through the host per map
+        self.device_maps = False
 
     def hashdict(self):
         ret = {'sims_cmb_len': self.sims_cmb_len.hashdict(), 'nside': self.nside, 'cl_transf': clhash(self.cl_transf_T)}
@@ -23,11 +26,21 @@ class cmb_maps(object):
 
     def get_sim_tmap(self, idx):
         tlm = hp.almxfl(self.sims_cmb_len.get_sim_tlm(idx), self.cl_transf_T)
+        if self.device_maps:
+            from .. import sht
+            t = sht.get_plan(self.nside, hp.Alm.getlmax(tlm.size)).alm2map(sht.dev_alm(tlm))
+            return sht.map_axpy(t, sht.dev_map(self.get_sim_tnoise(idx)), 1.0)
         return hp.alm2map(tlm, self.nside) + self.get_sim_tnoise(idx)
 
     def get_sim_pmap(self, idx):
         elm = hp.almxfl(self.sims_cmb_len.get_sim_elm(idx), self.cl_transf_P)
         blm = hp.almxfl(self.sims_cmb_len.get_sim_blm(idx), self.cl_transf_P)
+        if self.device_maps:
+            from .. import sht
+            Q, U = sht.get_plan(self.nside, hp.Alm.getlmax(elm.size)).alm2map_spin(sht.dev_alm(elm), sht.dev_alm(blm), 2)
+            sht.map_axpy(Q, sht.dev_map(self.get_sim_qnoise(idx)), 1.0)
+            sht.map_axpy(U, sht.dev_map(self.get_sim_unoise(idx)), 1.0)
+            return Q, U
         Q, U = hp.alm2map_spin([elm, blm], self.nside, 2, hp.Alm.getlmax(elm.size))
         return Q + self.get_sim_qnoise(idx), U + self.get_sim_unoise(idx)
 

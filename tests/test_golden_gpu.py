@@ -224,6 +224,23 @@ def test_qest_library_matches_reference(gold, merge):
         assert rel_l2(mf, gold['qe_dd_ptt']) < 1e-10    # both indices map to the same in-memory sim
 
 
+def test_qlm_auto_spectra_match_reference(gold):
+    """north_star tolerance: auto-spectra of the estimates within 1e-8 of the reference's, all three estimators,
+    gradient and curl."""
+    from plancklens_b200 import hp, qest
+    import tempfile as _tf
+    q = gi.qe_case()
+    with _tf.TemporaryDirectory() as tmp:
+        iv = _mem_ivfs(q, '1')
+        lib = qest.library_sepTP(os.path.join(tmp, 'dd'), iv, iv, q['cls']['te'], q['nside'], lmax_qlm=q['lmax_qlm'])
+        for k in ['ptt', 'p_p', 'p']:
+            G, C = lib.eval_qlm(k, 0)
+            for mine, ref in ((G, gold['qe_dd_' + k]), (C, gold['qe_dd_x' + k[1:]])):
+                cl, clr = hp.alm2cl(mine), hp.alm2cl(ref)
+                sel = clr > 1e-30 * clr.max()
+                assert np.max(np.abs(cl[sel] / clr[sel] - 1)) < 1e-8
+
+
 def test_shts_seam_signatures(oracle_sht):
     """plancklens_b200.shts exposes the four functions of the reference seam with its signatures."""
     from plancklens_b200 import shts, utils_spin
