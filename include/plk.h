@@ -92,6 +92,9 @@ int plk_alm_dot_dev(int lmax, int lmin, const void *a, const void *b, double *re
 /* two-component form (opfilt_pp.py:27-34: E and B summed), one device scalar */
 int plk_alm_dot2_dev(int lmax, int lmin, const void *a1, const void *b1, const void *a2, const void *b2,
                      double *result_dev, void *stream);
+/* n <= 4 components (opfilt_tp.py:46-58: T, E and B summed, all from lmin), host arrays of device pointers */
+int plk_alm_dotn_dev(int lmax, int lmin, int n, const void *const *a, const void *const *b, double *result_dev,
+                     void *stream);
 /* out_dev[0] = scale * num_dev[0] / den_dev[0]: CG step lengths (cd_solve.py:69-71, :95-99) kept on the device so that
  * the fixed-iteration multigrid stages (multigrid.py:185-215) run without host synchronisation (CUDA-graph capturable) */
 int plk_scalar_ratio_dev(const double *num, const double *den, double scale, double *out, void *stream);

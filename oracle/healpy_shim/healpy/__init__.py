@@ -13,8 +13,28 @@ from oracle import ref_sht as _sht
 
 from . import projector  # noqa: F401  (plancklens.utils imports healpy.projector.CartesianProj)
 
-alm2map = _sht.alm2map
-map2alm = _sht.map2alm
+
+
+def alm2map(alms, nside, lmax=None, mmax=None, pol=True, **kw):
+    """hp.alm2map; a (tlm, elm, blm) triple with pol=True gives (T, Q, U): a spin-0 and a spin-2 synthesis in the
+    HEALPix polarization convention (the only multi-alm form the reference uses, qcinv/opfilt_tp.py:279)."""
+    if isinstance(alms, (list, tuple)) or (isinstance(alms, np.ndarray) and alms.ndim == 2):
+        assert len(alms) == 3 and pol
+        L = _rg.alm_getlmax(np.asarray(alms[0]).size) if lmax is None else lmax
+        q, u = _sht.alm2map_spin([alms[1], alms[2]], nside, 2, L)
+        return [_sht.alm2map(alms[0], nside, lmax=L), q, u]
+    return _sht.alm2map(alms, nside, lmax=lmax, mmax=mmax, **kw)
+
+
+def map2alm(maps, lmax=None, mmax=None, iter=0, pol=True, **kw):
+    """hp.map2alm(iter=0); (T, Q, U) with pol=True gives (tlm, elm, blm) (qcinv/opfilt_tp.py:22, :285)."""
+    if isinstance(maps, (list, tuple)) or (isinstance(maps, np.ndarray) and maps.ndim == 2):
+        assert len(maps) == 3 and pol and iter == 0
+        e, b = _sht.map2alm_spin([maps[1], maps[2]], 2, lmax=lmax)
+        return [_sht.map2alm(maps[0], lmax=lmax, iter=0), e, b]
+    return _sht.map2alm(maps, lmax=lmax, mmax=mmax, iter=iter, **kw)
+
+
 alm2map_spin = _sht.alm2map_spin
 map2alm_spin = _sht.map2alm_spin
 nside2npix = _rg.nside2npix

@@ -181,3 +181,75 @@ def pcg(b, fwd, pre, dot, eps_min, iter_max=10000, roundoff=25):
         beta = prev[0] * dot(searchdir, prev[2])
         searchdir = add(searchdir, prev[1], -beta)
     return x, it, trace
+
+
+# ---------------------------------------------------------------------------------------------- joint T + P
+class ninv_tp:
+    """opfilt_tp.alm_filter_ninv (opfilt_tp.py:166-326): n_inv = [TT, PP] or [TT, QQ, QU, UU]; T templates."""
+
+    def __init__(self, n_inv, b_transf, marge_monopole=False, marge_dipole=False, marge_maps_t=()):
+        self.t = ninv_tt(n_inv[0], b_transf, marge_monopole=marge_monopole, marge_dipole=marge_dipole, marge_maps=marge_maps_t)
+        self.p = ninv_pp(n_inv[1:], b_transf)
+        self.n_inv = [np.asarray(n, dtype=float) for n in n_inv]
+        self.b = np.asarray(b_transf, dtype=float)
+        self.npix, self.nside = self.t.npix, self.t.nside
+
+    def apply_map(self, t, q, u):
+        q, u = self.p.apply_map(q, u)
+        return self.t.apply_map(t), q, u
+
+    def apply_alm(self, t, e, b):
+        lmax = _lmax(t)
+        tm = sht.alm2map(almxfl(t, self.b), self.nside, lmax=lmax)
+        q, u = sht.alm2map_spin([almxfl(e, self.b), almxfl(b, self.b)], self.nside, 2, lmax)
+        tm, q, u = self.apply_map(tm, q, u)
+        f = self.b * (self.npix / (4. * np.pi))
+        te, tb = sht.map2alm_spin([q, u], 2, lmax=lmax)
+        return almxfl(sht.map2alm(tm, lmax=lmax), f), almxfl(te, f), almxfl(tb, f)
+
+    def calc_prep(self, t, q, u):
+        lmax = len(self.b) - 1
+        tm, q, u = self.apply_map(np.array(t, dtype=float), np.array(q, dtype=float), np.array(u, dtype=float))
+        f = self.b * (self.npix / (4. * np.pi))
+        te, tb = sht.map2alm_spin([q, u], 2, lmax=lmax)
+        return almxfl(sht.map2alm(tm, lmax=lmax), f), almxfl(te, f), almxfl(tb, f)
+
+    def ftebl(self):
+        s = lambda m: np.sum(m) / (4.0 * np.pi)
+        npp = s(self.n_inv[1]) if len(self.n_inv) == 2 else s(0.5 * (self.n_inv[1] + self.n_inv[3]))
+        return s(self.n_inv[0]) * self.b ** 2, npp * self.b ** 2, npp * self.b ** 2
+
+
+def slinv_tp(cls, lmax):
+    """opfilt_tp.alm_filter_sinv (:126-147): per-l pinv of the TEB covariance"""
+    m = np.zeros((lmax + 1, 3, 3))
+    z = np.zeros(lmax + 1)
+    for (i, j), k in {(0, 0): 'tt', (0, 1): 'te', (0, 2): 'tb', (1, 1): 'ee', (1, 2): 'eb', (2, 2): 'bb'}.items():
+        m[:, i, j] = m[:, j, i] = cls.get(k, z)[:lmax + 1]
+    return np.linalg.pinv(m)
+
+
+def lmat3(mat, t, e, b):
+    v = (t, e, b)
+    return tuple(sum(almxfl(v[j], mat[:, i, j]) for j in range(3)) for i in range(3))
+
+
+def fwd_tp(t, e, b, cls, nf):
+    """opfilt_tp.fwd_op.calc (:75-82)"""
+    n = nf.apply_alm(t, e, b)
+    s = lmat3(slinv_tp(cls, _lmax(t)), t, e, b)
+    return tuple(ni + si for ni, si in zip(n, s))
+
+
+def pre_diag_tp(cls, nf):
+    """opfilt_tp.pre_op_diag (:87-104)"""
+    lmax = len(nf.b) - 1
+    fl = slinv_tp(cls, lmax)
+    for i, f in enumerate(nf.ftebl()):
+        fl[:, i, i] += f
+    return np.linalg.pinv(fl)
+
+
+def dot_tp(a, b):
+    """opfilt_tp.dot_op (:46-58): all multipoles, T + E + B"""
+    return sum(dot_tt(x, y) for x, y in zip(a, b))

@@ -881,6 +881,22 @@ extern "C" int plk_alm_dot2_dev(int lmax, int lmin, const void *a1, const void *
   LAUNCHED();
   return PLK_OK;
 }
+extern "C" int plk_alm_dotn_dev(int lmax, int lmin, int n, const void *const *a, const void *const *b, double *result_dev,
+                                void *stream) {
+  if (!a || !b || !result_dev || lmax < 0 || n < 1 || n > 4) return fail(PLK_EINVAL, "bad argument");
+  int rc = scratch();
+  if (rc) return rc;
+  if ((size_t)n * ((size_t)lmax + 1) > kScratchDoubles) return fail(PLK_EINVAL, "lmax too large");
+  for (int j = 0; j < n; ++j) {
+    if (!a[j] || !b[j]) return fail(PLK_EINVAL, "NULL component");
+    dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a[j], (const cplx *)b[j],
+                                                                    g_scratch + (size_t)j * (lmax + 1));
+    LAUNCHED();
+  }
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, n * (lmax + 1), 1, result_dev);
+  LAUNCHED();
+  return PLK_OK;
+}
 extern "C" int plk_scalar_ratio_dev(const double *num, const double *den, double scale, double *out, void *stream) {
   if (!num || !den || !out) return fail(PLK_EINVAL, "NULL buffer");
   scalar_ratio_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(num, den, scale, out);

@@ -11,7 +11,7 @@ import numpy as np
 
 from .. import hp, utils
 from ..helpers import mpi
-from ..qcinv import cd_solve, multigrid, opfilt_pp, opfilt_tt, util, util_alm
+from ..qcinv import cd_solve, multigrid, opfilt_pp, opfilt_tp, opfilt_tt, util, util_alm
 from . import filt_simple
 
 
@@ -253,6 +253,165 @@ class cinv_p(cinv):
             assert hp.npix2nside(len(ninv)) == self.nside
             mask *= (ninv > 0.)
         return mask
+
+
+class cinv_tp:
+    """Joint temperature + polarization inverse-variance (Wiener) filter (reference: filt_cinv.py:341-512).
+
+    Args as the reference: `ninv` = [TT, (QQ+UU)/2] or [TT, QQ, QU, UU] (each a list of maps / numbers to multiply),
+    `marge_maps_t`, `marge_monopole`, `marge_dipole` for the temperature block, `rescal_cl` in
+    ('default', None, 'tonly'), `transf_p` if the polarization beam differs."""
+
+    def __init__(self, lib_dir, lmax, nside, cl, transf, ninv, marge_maps_t=(), marge_monopole=False, marge_dipole=False,
+                 pcf='default', rescal_cl='default', chain_descr=None, transf_p=None):
+        assert lmax >= 1024 and nside >= 512, (lmax, nside)
+        assert len(ninv) == 2 or len(ninv) == 4
+        ls = np.arange(lmax + 1, dtype=float)
+        dl_fac = np.sqrt(ls * (ls + 1.) / 2. / np.pi)
+        if rescal_cl == 'default':
+            rescal_cl = {a: dl_fac.copy() for a in ['t', 'e', 'b']}
+        elif rescal_cl is None:
+            rescal_cl = {a: np.ones(lmax + 1, dtype=float) for a in ['t', 'e', 'b']}
+        elif rescal_cl == 'tonly':
+            rescal_cl = {a: np.ones(lmax + 1, dtype=float) for a in ['e', 'b']}
+            rescal_cl['t'] = dl_fac.copy()
+        else:
+            assert 0
+        for k in rescal_cl.keys():
+            rescal_cl[k] /= np.mean(rescal_cl[k])      # keeps the relative TEB weights of the spectra
+        dl = {k: rescal_cl[k[0]] * rescal_cl[k[1]] * cl[k][:lmax + 1] for k in cl.keys()}
+        if transf_p is None:
+            transf_p = transf
+        transf_dls = {a: transf_p[:lmax + 1] * utils.cli(rescal_cl[a]) for a in ['e', 'b']}
+        transf_dls['t'] = transf[:lmax + 1] * utils.cli(rescal_cl['t'])
+        self.lmax, self.nside, self.cl = lmax, nside, cl
+        self.transf_t, self.transf_p = transf, transf_p
+        self.ninv = ninv
+        self.marge_maps_t = marge_maps_t
+        self.marge_maps_p = []
+        self.lib_dir = lib_dir
+        self.rescal_cl = rescal_cl
+        if chain_descr is None:
+            pcf = os.path.join(lib_dir, "dense_tp.pk") if pcf == 'default' else ''
+            chain_descr = \
+                [[3, ["split(dense(" + pcf + "), 64, diag_cl)"], 256, 128, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [2, ["split(stage(3),  256, diag_cl)"], 512, 256, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [1, ["split(stage(2),  512, diag_cl)"], 1024, 512, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [0, ["split(stage(1), 1024, diag_cl)"], lmax, nside, np.inf, 1.0e-5, cd_solve.tr_cg, cd_solve.cache_mem()]]
+        n_inv_filt = util.jit(opfilt_tp.alm_filter_ninv, ninv, transf_dls['t'], b_transf_e=transf_dls['e'],
+                              b_transf_b=transf_dls['b'], marge_maps_t=marge_maps_t, marge_monopole=marge_monopole,
+                              marge_dipole=marge_dipole)
+        self.chain_descr = chain_descr
+        self.chain = util.jit(multigrid.multigrid_chain, opfilt_tp, chain_descr, dl, n_inv_filt)
+        if mpi.rank == 0:
+            if not os.path.exists(lib_dir):
+                os.makedirs(lib_dir)
+            fn = os.path.join(lib_dir, "filt_hash.pk")
+            if not os.path.exists(fn):
+                with open(fn, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+            fn = os.path.join(lib_dir, "fal.pk")
+            if not os.path.exists(fn):
+                with open(fn, 'wb') as f:
+                    pk.dump(self._calc_fal(), f, protocol=2)
+            if not os.path.exists(os.path.join(lib_dir, "fmask.fits.gz")):
+                hp.write_map(os.path.join(lib_dir, "fmask.fits.gz"), self.calc_mask())
+        mpi.barrier()
+        with open(os.path.join(lib_dir, "filt_hash.pk"), 'rb') as f:
+            utils.hash_check(pk.load(f), self.hashdict(), fn=os.path.join(lib_dir, "filt_hash.pk"))
+
+    def hashdict(self):
+        ret = {'lmax': self.lmax, 'nside': self.nside,
+               'rescal_cl': {k: utils.clhash(self.rescal_cl[k]) for k in self.rescal_cl.keys()},
+               'cls': {k: utils.clhash(self.cl[k]) for k in self.cl.keys()},
+               'transf': utils.clhash(self.transf_t), 'ninv': self._ninv_hash(),
+               'marge_maps_t': self.marge_maps_t, 'marge_maps_p': self.marge_maps_p}
+        if self.transf_p is not self.transf_t:
+            ret['transf_p'] = utils.clhash(self.transf_p)
+        return ret
+
+    def get_fal(self, lmax=None):
+        with open(os.path.join(self.lib_dir, "fal.pk"), 'rb') as f:
+            fal = pk.load(f)
+        return fal if lmax is None else {k: v[:lmax + 1] for k, v in fal.items()}
+
+    def _calc_fal(self):
+        """Isotropic approximation to the filtering matrix (reference: filt_cinv.py:450-476)."""
+        ninv = self.chain.n_inv_filt.n_inv
+        assert len(ninv) == 2, 'implement this, easy'
+        npix = 12 * self.nside ** 2
+        assert ninv[0].size == npix and ninv[1].size == npix
+        lev = lambda m: np.sqrt(4. * np.pi / npix / np.sum(m) * len(np.where(m != 0.0)[0])) * 180. * 60. / np.pi
+        nlevt, nlevp = lev(ninv[0]), lev(ninv[1])
+        print("cinv_tp::noiseT_uk_arcmin = %.3f" % nlevt)
+        print("cinv_tp::noiseP_uk_arcmin = %.3f" % nlevp)
+        fals = np.zeros((self.lmax + 1, 3, 3), dtype=float)
+        for i, a in enumerate(['t', 'e', 'b']):
+            for j, b in enumerate(['t', 'e', 'b']):
+                fals[:, i, j] = self.cl.get(a + b, self.cl.get(b + a, np.zeros(self.lmax + 1)))[:self.lmax + 1]
+        fals[1:, 0, 0] += ((nlevt / 180 / 60 * np.pi) / self.transf_t[1:self.lmax + 1]) ** 2
+        fals[2:, 1, 1] += ((nlevp / 180 / 60 * np.pi) / self.transf_p[2:self.lmax + 1]) ** 2
+        fals[2:, 2, 2] += ((nlevp / 180 / 60 * np.pi) / self.transf_p[2:self.lmax + 1]) ** 2
+        fals = np.linalg.pinv(fals)
+        fals_dict = {}
+        for i, a in enumerate(['t', 'e', 'b']):
+            for j, b in enumerate(['t', 'e', 'b'][i:]):
+                if np.any(fals[:, i, i + j]):
+                    fals_dict[a + b] = fals[:, i, i + j]
+        return fals_dict
+
+    def calc_mask(self):
+        mask = np.ones(hp.nside2npix(self.nside), dtype=float)
+        for ninv in self.chain.n_inv_filt.n_inv:
+            assert hp.npix2nside(len(ninv)) == self.nside
+            mask *= (ninv > 0.)
+        return mask
+
+    def get_fmask(self):
+        return hp.read_map(os.path.join(self.lib_dir, "fmask.fits.gz"))
+
+    def apply_ivf(self, tqumap, soltn=None, apply_fini=''):
+        """Inverse-variance filtered (T, E, B) alms of a (T, Q, U) map triple; the solve runs on the GPU."""
+        assert len(tqumap) == 3
+        if soltn is None:
+            talm = util_alm.teblm([util_alm.dalm.zeros(self.lmax) for _ in range(3)])
+        else:
+            talm = util_alm.teblm([util_alm.dalm.from_numpy(hp.almxfl(s, self.rescal_cl[a])) for s, a in zip(soltn, 'teb')])
+        self.chain.solve(talm, [tqumap[0], tqumap[1], tqumap[2]], apply_fini=apply_fini)
+        t, e, b = talm.numpy()
+        return hp.almxfl(t, self.rescal_cl['t']), hp.almxfl(e, self.rescal_cl['e']), hp.almxfl(b, self.rescal_cl['b'])
+
+    def _ninv_hash(self):
+        # lists of maps / numbers per component are hashed element-wise (the reference hashes bare arrays only,
+        # filt_cinv.py:503-510, and would compare arrays by value inside lists)
+        return [[_ninv_hash(c) if isinstance(c, (list, tuple)) else _ninv_hash([c])[0] for c in self.ninv]]
+
+
+class library_cinv_jTP(filt_simple.library_jTP):
+    """CG inverse-variance filtering of a simulation library, T and P filtered jointly
+    (reference: filt_cinv.py:584-627)."""
+
+    def __init__(self, lib_dir, sim_lib, cinv_jtp, cl_weights, soltn_lib=None):
+        self.cinv_tp = cinv_jtp
+        super(library_cinv_jTP, self).__init__(lib_dir, sim_lib, cl_weights, soltn_lib=soltn_lib)
+        if mpi.rank == 0:
+            fname_mask = os.path.join(self.lib_dir, "fmask.fits.gz")
+            if not os.path.exists(fname_mask):
+                hp.write_map(fname_mask, self.cinv_tp.get_fmask())
+        mpi.barrier()
+
+    def hashdict(self):
+        return {'cinv_tp': self.cinv_tp.hashdict(), 'clw': {k: utils.clhash(self.cl[k]) for k in self.cl.keys()},
+                'sim_lib': self.sim_lib.hashdict()}
+
+    def get_fmask(self):
+        return hp.read_map(os.path.join(self.lib_dir, "fmask.fits.gz"))
+
+    def get_fal(self, lmax=None):
+        return self.cinv_tp.get_fal(lmax=lmax)
+
+    def _apply_ivf(self, tqumap, soltn=None):
+        return self.cinv_tp.apply_ivf(tqumap, soltn=soltn)
 
 
 class library_cinv_sepTP(filt_simple.library_sepTP):

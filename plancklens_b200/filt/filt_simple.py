@@ -114,6 +114,90 @@ class library_sepTP(object):
         return hp.almxfl(self.get_sim_blm(idx), self.cl['bb'])
 
 
+class library_jTP(object):
+    """Inverse-variance and Wiener filtering of a simulation library, T and P filtered JOINTLY
+    (reference: filt_simple.py:187-343).  Concrete filters provide `hashdict`, `get_fmask`, `_apply_ivf`, `get_fal`."""
+
+    def __init__(self, lib_dir, sim_lib, cl_weights, soltn_lib=None, cache=True):
+        assert np.all([k in cl_weights.keys() for k in ['tt', 'ee', 'bb']])
+        self.lib_dir = lib_dir
+        self.sim_lib = sim_lib
+        self.cl = cl_weights
+        self.soltn_lib = soltn_lib
+        self.cache = cache
+        fn_hash = os.path.join(lib_dir, 'filt_hash.pk')
+        if mpi.rank == 0:
+            if not os.path.exists(lib_dir):
+                os.makedirs(lib_dir)
+            if not os.path.exists(fn_hash):
+                with open(fn_hash, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+        mpi.barrier()
+        with open(fn_hash, 'rb') as f:
+            utils.hash_check(pk.load(f), self.hashdict(), fn=fn_hash)
+
+    def hashdict(self):
+        assert 0, 'override this'
+
+    def get_fmask(self):
+        assert 0, 'override this'
+
+    def _apply_ivf(self, tqumap, soltn=None):
+        assert 0, 'override this'
+
+    def get_fal(self):
+        r"""Isotropic matrix approximation :math:`F_\ell \sim (C_\ell + N_\ell / b_\ell^2)^{-1}` ('tt', 'ee', 'te', ...)."""
+        assert 0, 'override this'
+
+    def _get_alms(self, a, idx):
+        assert a in ['t', 'e', 'b']
+        tfname = os.path.join(self.lib_dir, 'sim_%04d_tlm.fits' % idx if idx >= 0 else 'dat_tlm.fits')
+        fname = tfname.replace('tlm.fits', a + 'lm.fits')
+        if not os.path.exists(fname):
+            T = self.sim_lib.get_sim_tmap(idx)
+            Q, U = self.sim_lib.get_sim_pmap(idx)
+            soltn = None
+            if self.soltn_lib is not None:
+                soltn = (self.soltn_lib.get_sim_tmliklm(idx), self.soltn_lib.get_sim_emliklm(idx),
+                         self.soltn_lib.get_sim_bmliklm(idx))
+            tlm, elm, blm = self._apply_ivf([T, Q, U], soltn=soltn)
+            if not self.cache:
+                return {'t': tlm, 'e': elm, 'b': blm}[a]
+            hp.write_alm(tfname, tlm, overwrite=True)
+            hp.write_alm(tfname.replace('tlm.fits', 'elm.fits'), elm, overwrite=True)
+            hp.write_alm(tfname.replace('tlm.fits', 'blm.fits'), blm, overwrite=True)
+        return hp.read_alm(fname)
+
+    def get_sim_tlm(self, idx):
+        return self._get_alms('t', idx)
+
+    def get_sim_elm(self, idx):
+        return self._get_alms('e', idx)
+
+    def get_sim_blm(self, idx):
+        return self._get_alms('b', idx)
+
+    def _mlik(self, a, idx):
+        """Wiener-filtered alm: sum_b C_l^{ab} (inverse-variance filtered b), b over t, e, b (reference: :294-343)."""
+        ret = hp.almxfl(self._get_alms(a, idx), self.cl[a + a])
+        for b in 'teb':
+            if b == a:
+                continue
+            cl = self.cl.get(a + b, self.cl.get(b + a, None))
+            if cl is not None:
+                ret = ret + hp.almxfl(self._get_alms(b, idx), cl)
+        return ret
+
+    def get_sim_tmliklm(self, idx):
+        return self._mlik('t', idx)
+
+    def get_sim_emliklm(self, idx):
+        return self._mlik('e', idx)
+
+    def get_sim_bmliklm(self, idx):
+        return self._mlik('b', idx)
+
+
 class library_fullsky_sepTP(library_sepTP):
     """Full-sky isotropic filter: filtered alm = f_l / transf_l * map2alm(map) (reference: filt_simple.py:346-407).
 

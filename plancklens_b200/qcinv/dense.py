@@ -12,7 +12,7 @@ import torch
 
 from .. import sht
 from ..utils import enumerate_progress
-from .util_alm import dalm, eblm
+from .util_alm import dalm, eblm, teblm
 
 
 def alm2rlm(alm):
@@ -198,3 +198,29 @@ class pre_op_dense_pp(_pre_op_dense):
     def rlm2alm(rlm):
         n1 = len(rlm) // 2
         return eblm([rlm2alm(rlm[:n1]), rlm2alm(rlm[n1:])])
+
+
+class pre_op_dense_tp(_pre_op_dense):
+    """reference: dense.py:204-283"""
+    ncomp = 3
+
+    def _comps(self, v):
+        return [v.tlm, v.elm, v.blm]
+
+    def _wrap(self, comps):
+        return teblm(comps)
+
+    def _ntmpl(self, fwd_op):
+        n = sum(t.nmodes for t in fwd_op.n_inv_filt.templates_t)     # includes mono and possibly dip
+        n += sum(t.nmodes for t in fwd_op.n_inv_filt.templates_p)
+        return int(n + 8)   # (1 mono + 3 dip) * (e + b)
+
+    @staticmethod
+    def alm2rlm(alm):
+        t, e, b = alm.numpy() if hasattr(alm, 'numpy') else (alm.tlm, alm.elm, alm.blm)
+        return np.concatenate([alm2rlm(t), alm2rlm(e), alm2rlm(b)])
+
+    @staticmethod
+    def rlm2alm(rlm):
+        n1 = len(rlm) // 3
+        return teblm([rlm2alm(rlm[:n1]), rlm2alm(rlm[n1:2 * n1]), rlm2alm(rlm[2 * n1:])])

@@ -106,16 +106,22 @@ def _graph_safe(op):
         return _graph_safe(op.pre_op_low) and _graph_safe(op.pre_op_hgh)
     if isinstance(op, pre_op_multigrid):
         return op.fixed and all(_graph_safe(p) for p in op.pre_ops)
-    return type(op).__name__ in ('pre_op_diag', 'pre_op_dense_tt', 'pre_op_dense_pp')
+    return type(op).__name__ in ('pre_op_diag', 'pre_op_dense_tt', 'pre_op_dense_pp', 'pre_op_dense_tp')
 
 
 def _vec_tensors(v):
-    return [v.t] if isinstance(v, util_alm.dalm) else [v.elm.t, v.blm.t]
+    if isinstance(v, util_alm.dalm):
+        return [v.t]
+    if isinstance(v, util_alm.teblm):
+        return [v.tlm.t, v.elm.t, v.blm.t]
+    return [v.elm.t, v.blm.t]
 
 
 def _vec_clone(v):
     if isinstance(v, util_alm.dalm):
         return util_alm.dalm(v.t.clone(), v.lmax, v.zero)
+    if isinstance(v, util_alm.teblm):
+        return util_alm.teblm([_vec_clone(v.tlm), _vec_clone(v.elm), _vec_clone(v.blm)])
     return util_alm.eblm([_vec_clone(v.elm), _vec_clone(v.blm)])
 
 
@@ -164,6 +170,17 @@ def _to_device(soltn):
     """-> (device vector, writeback or None)"""
     if isinstance(soltn, util_alm.dalm):
         return soltn, None
+    if isinstance(soltn, util_alm.teblm):
+        if isinstance(soltn.tlm, util_alm.dalm):
+            return soltn, None
+        d = util_alm.teblm([util_alm.dalm.from_numpy(c) for c in (soltn.tlm, soltn.elm, soltn.blm)])
+
+        def wb(v):
+            t, e, b = v.numpy()
+            soltn.tlm[:] = t
+            soltn.elm[:] = e
+            soltn.blm[:] = b
+        return d, wb
     if isinstance(soltn, util_alm.eblm):
         if isinstance(soltn.elm, util_alm.dalm):
             return soltn, None

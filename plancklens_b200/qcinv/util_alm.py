@@ -185,3 +185,70 @@ class eblm:
     def numpy(self):
         f = lambda c: c.numpy() if hasattr(c, 'numpy') else np.asarray(c)
         return f(self.elm), f(self.blm)
+
+
+class teblm:
+    """(T, E, B) triple of alm vectors (numpy arrays or `dalm`), reference: util_alm.py:88-160."""
+
+    def __init__(self, alm):
+        tlm, elm, blm = alm
+        self.lmaxt = _getlmax(len(tlm))
+        self.lmaxe = _getlmax(len(elm))
+        self.lmaxb = _getlmax(len(blm))
+        self.lmax = max(self.lmaxt, self.lmaxe, self.lmaxb)
+        self.tlm, self.elm, self.blm = tlm, elm, blm
+
+    def _c(self):
+        return [self.tlm, self.elm, self.blm]
+
+    def alm_copy(self, lmax=None):
+        return teblm([alm_copy(c, lmax=lmax) for c in self._c()])
+
+    def alm_splice(self, alm_hi, lsplit):
+        return teblm([alm_splice(a, b, lsplit) for a, b in zip(self._c(), alm_hi._c())])
+
+    def is_zero(self):
+        return all(c.is_zero() if hasattr(c, 'is_zero') else not np.any(c) for c in self._c())
+
+    def copy(self):
+        return self * 1.0
+
+    def _same(self, other):
+        assert self.lmaxt == other.lmaxt and self.lmaxe == other.lmaxe and self.lmaxb == other.lmaxb
+
+    def __add__(self, other):
+        self._same(other)
+        return teblm([a + b for a, b in zip(self._c(), other._c())])
+
+    def __sub__(self, other):
+        self._same(other)
+        return teblm([a - b for a, b in zip(self._c(), other._c())])
+
+    def __iadd__(self, other):
+        self._same(other)
+        self.tlm += other.tlm
+        self.elm += other.elm
+        self.blm += other.blm
+        return self
+
+    def __isub__(self, other):
+        self._same(other)
+        self.tlm -= other.tlm
+        self.elm -= other.elm
+        self.blm -= other.blm
+        return self
+
+    def __mul__(self, other):
+        return teblm([c * other for c in self._c()])
+
+    def axpy(self, a, x):
+        for c, xc in zip(self._c(), x._c()):
+            if hasattr(c, 'axpy'):
+                c.axpy(a, xc)
+            else:
+                c += a * xc
+        return self
+
+    def numpy(self):
+        f = lambda c: c.numpy() if hasattr(c, 'numpy') else np.asarray(c)
+        return f(self.tlm), f(self.elm), f(self.blm)

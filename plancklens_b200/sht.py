@@ -236,6 +236,18 @@ def alm_dot2(a1, b1, a2, b2, lmin=0, out=None):
     return out
 
 
+def alm_dotn(avec, bvec, lmin=0, out=None):
+    """sum over components of the weighted dot products (teblm vectors) as one device scalar"""
+    lib = _lib.load()
+    n = len(avec)
+    lmax = alm_lmax(avec[0].numel())
+    out = torch.empty(1, dtype=torch.float64, device='cuda') if out is None else out
+    pa = (ctypes.c_void_p * n)(*[t.data_ptr() for t in avec])
+    pb = (ctypes.c_void_p * n)(*[t.data_ptr() for t in bvec])
+    check(lib.plk_alm_dotn_dev(lmax, lmin, n, pa, pb, _ptr(out), _stream()))
+    return out
+
+
 def scalar_ratio(num, den, scale=1.0, out=None):
     """scale * num / den on 1-element device tensors (no host synchronisation)"""
     out = torch.empty(1, dtype=torch.float64, device='cuda') if out is None else out

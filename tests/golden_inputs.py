@@ -98,3 +98,9 @@ def template_case(nside=32, seed=99):
     return {'tmaps': [z ** 2 + 0.1 * rng.standard_normal(npix), np.cos(7 * z) + 0.3 * rng.standard_normal(npix)],
             'qmaps': [1.0 + 0.5 * z + 0.2 * rng.standard_normal(npix)],
             'umaps': [z ** 3 + 0.2 * rng.standard_normal(npix), rng.standard_normal(npix)]}
+
+
+def chain_descr_tp(cd_solve):
+    """Two-level version of the reference's default joint T+P chain (filt_cinv.py:398-405), sized for nside 32."""
+    return [[1, ["split(dense, 8, diag_cl)"], 32, 16, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+            [0, ["split(stage(1), 32, diag_cl)"], 64, 32, np.inf, 1.0e-6, cd_solve.tr_cg, cd_solve.cache_mem()]]

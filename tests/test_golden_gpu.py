@@ -168,6 +168,40 @@ def test_cg_pp_same_iterations_as_reference(gold, mods):
     assert rel_l2(sol.elm, gold['pp_soltn_e']) < 1e-7 and rel_l2(sol.blm, gold['pp_soltn_b']) < 1e-7
 
 
+def test_joint_tp_filter_matches_reference(mods):
+    """qcinv/opfilt_tp.py on the GPU: operators, then a two-level multigrid solve with the dense TEB coarse
+    preconditioner -- same iteration count, eps trace and solution as the unmodified reference."""
+    from plancklens_b200.qcinv import opfilt_tp
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_tp.npz'))
+    c, t = gi.cg_case(), gi.template_case()
+    ua = mods['util_alm']
+    x = lambda: ua.teblm([ua.dalm.from_numpy(c['x_t']), ua.dalm.from_numpy(c['x_e']), ua.dalm.from_numpy(c['x_b'])])
+    for tag, ninv, kw in (('tp2', [c['ninv_t'][0], c['ninv_p1'][0][0]], dict(marge_monopole=True, marge_dipole=True)),
+                          ('tp4', [c['ninv_t'][0]] + [m[0] for m in c['ninv_p3']], dict(marge_maps_t=t['tmaps'][:1]))):
+        nf = opfilt_tp.alm_filter_ninv(ninv, c['transf'], **kw)
+        fwd = opfilt_tp.fwd_op(c['cls'], nf)
+        r = fwd(x())
+        for a, k in zip(r.numpy(), 'teb'):
+            assert rel_l2(a, g['%s_fwd_%s' % (tag, k)]) < 1e-10
+        p = opfilt_tp.calc_prep([c['tmap'], c['qmap'], c['umap']], c['cls'], nf)
+        for a, k in zip(p.numpy(), 'teb'):
+            assert rel_l2(a, g['%s_prep_%s' % (tag, k)]) < 1e-10
+        d = opfilt_tp.dot_op()(x(), r)
+        assert abs(d - g[tag + '_dot'][0]) < 1e-10 * abs(g[tag + '_dot'][0])
+        for a, k in zip(opfilt_tp.pre_op_diag(c['cls'], nf)(x()).numpy(), 'teb'):
+            assert rel_l2(a, g['%s_prediag_%s' % (tag, k)]) < 1e-11
+        if tag == 'tp2':
+            n = g['tp2_soltn_t'].size
+            sol = ua.teblm([np.zeros(n, dtype=complex), np.zeros(n, dtype=complex), np.zeros(n, dtype=complex)])
+            chain = _solve(mods, opfilt_tp, gi.chain_descr_tp(mods['cd_solve']), c['cls'], nf, sol, [c['tmap'], c['qmap'], c['umap']])
+            ref = g['tp2_trace']
+            assert chain.niter == int(ref[-1][1])
+            assert np.allclose(np.array([tr[1] for tr in chain.last_monitor.trace]), ref[:, 2], rtol=1e-5)
+            for a, k in zip((sol.tlm, sol.elm, sol.blm), 'teb'):
+                assert rel_l2(a, g['tp2_soltn_' + k]) < 1e-7
+            assert any(type(op).__name__ == 'graphed_op' and op.graph is not None for op in chain.bstage.pre_ops)
+
+
 class _mem_ivfs:
     lib_dir = None
 

@@ -108,3 +108,22 @@ def test_template_marginalisation_matches_reference(built):
     assert rel_l2(q, g['pm_apply_q']) < 1e-11 and rel_l2(u, g['pm_apply_u']) < 1e-11
     fe, fb = ref_cg.fwd_pp(c['x_e'], c['x_b'], c['cls'], nfp)
     assert rel_l2(fe, g['pm_fwd_e']) < 1e-11 and rel_l2(fb, g['pm_fwd_b']) < 1e-11
+
+
+def test_joint_tp_operators_match_reference(built):
+    """qcinv/opfilt_tp.py (joint T + P filter): oracle vs the unmodified reference (tests/golden/make_golden_tp.py)."""
+    from oracle import ref_cg
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_tp.npz'))
+    c, t = gi.cg_case(), gi.template_case()
+    x = (c['x_t'], c['x_e'], c['x_b'])
+    for tag, ninv, kw in (('tp2', [c['ninv_t'][0], c['ninv_p1'][0][0]], dict(marge_monopole=True, marge_dipole=True)),
+                          ('tp4', [c['ninv_t'][0]] + [m[0] for m in c['ninv_p3']], dict(marge_maps_t=t['tmaps'][:1]))):
+        nf = ref_cg.ninv_tp(ninv, c['transf'], **kw)
+        f = ref_cg.fwd_tp(*x, c['cls'], nf)
+        for a, k in zip(f, 'teb'):
+            assert rel_l2(a, g['%s_fwd_%s' % (tag, k)]) < 1e-11
+        for a, k in zip(nf.calc_prep(c['tmap'], c['qmap'], c['umap']), 'teb'):
+            assert rel_l2(a, g['%s_prep_%s' % (tag, k)]) < 1e-11
+        assert abs(ref_cg.dot_tp(x, f) - g[tag + '_dot'][0]) < 1e-11 * abs(g[tag + '_dot'][0])
+        for a, k in zip(ref_cg.lmat3(ref_cg.pre_diag_tp(c['cls'], nf), *x), 'teb'):
+            assert rel_l2(a, g['%s_prediag_%s' % (tag, k)]) < 1e-11

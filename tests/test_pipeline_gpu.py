@@ -113,3 +113,61 @@ def test_pipelined_eval_qlms_equals_eval_qlm(key, tmp_path):
     for idx, G, C in got:
         Gr, Cr = lib.eval_qlm(key, idx)
         assert np.array_equal(G, Gr) and np.array_equal(C, Cr)
+
+
+def test_cinv_tp_joint_filter_pipeline(tmp_path):
+    """filt_cinv.cinv_tp + library_cinv_jTP (joint T + P CG filter) end to end at the smallest size the reference's
+    constructor accepts (nside 512, lmax 1024): the returned alms solve the normal equations to the requested eps,
+    and feed a joint-filtered QE library."""
+    import torch
+    from plancklens_b200 import hp, qest, sht, utils
+    from plancklens_b200.filt import filt_cinv
+    from plancklens_b200.qcinv import cd_solve, opfilt_tp, util_alm
+    import golden_inputs as gi
+    nside, lmax = 512, 1024
+    npix = 12 * nside ** 2
+    rng = np.random.default_rng(5)
+    cls = utils.camb_clfile(os.path.join(ROOT, 'plancklens_b200', 'data', 'cls', 'FFP10_wdipole_lensedCls.dat'), lmax=lmax)
+    cls = {k: cls[k] for k in ('tt', 'ee', 'bb', 'te')}
+    transf = hp.gauss_beam(np.deg2rad(10. / 60.), lmax=lmax)
+    z = gi.pix_z(nside)
+    mask = (np.abs(z) > 0.2).astype(float)
+    vamin2 = hp.nside2pixarea(nside, degrees=True) * 3600.
+    ninv = [[np.array([vamin2 / 35. ** 2]), mask], [np.array([vamin2 / 55. ** 2]), mask]]
+    # the reference's default chain (filt_cinv.py:398-405) one level shallower and with a smaller dense block
+    descr = [[2, ["split(dense, 32, diag_cl)"], 256, 128, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+             [1, ["split(stage(2), 256, diag_cl)"], 512, 256, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+             [0, ["split(stage(1), 512, diag_cl)"], lmax, nside, np.inf, 1.0e-5, cd_solve.tr_cg, cd_solve.cache_mem()]]
+    cinv = filt_cinv.cinv_tp(str(tmp_path / 'cinv_tp'), lmax, nside, cls, transf, ninv, marge_monopole=True,
+                             marge_dipole=True, chain_descr=descr)
+    # CMB-like data: Gaussian sky with the fiducial spectra through the beam + white noise at the filter's level
+    sim = [hp.almxfl(gi.rand_alm(rng, lmax, 2) / np.sqrt(2.), np.sqrt(cls[k]) * transf) for k in ('tt', 'ee', 'bb')]
+    vamin = np.sqrt(hp.nside2pixarea(nside, degrees=True)) * 60.
+    tmap = hp.alm2map(sim[0], nside) + rng.standard_normal(npix) * 35. / vamin
+    qmap, umap = hp.alm2map_spin([sim[1], sim[2]], nside, 2, lmax)
+    qmap = qmap + rng.standard_normal(npix) * 55. / vamin
+    umap = umap + rng.standard_normal(npix) * 55. / vamin
+    tlm, elm, blm = cinv.apply_ivf([tmap, qmap, umap])
+    assert cinv.chain.last_monitor.trace[-1][1] <= 1e-5 and cinv.chain.niter < 100, cinv.chain.niter
+    # residual of the normal equations in the chain's own (rescaled) variables: A x = b with x = S (returned / rescal)
+    nf, dl = cinv.chain.n_inv_filt, cinv.chain.s_cls
+    b = opfilt_tp.calc_prep([tmap, qmap, umap], dl, nf)
+    ivf = util_alm.teblm([util_alm.dalm.from_numpy(hp.almxfl(a, utils.cli(cinv.rescal_cl[k]))) for a, k in zip((tlm, elm, blm), 'teb')])
+    smat = np.zeros((lmax + 1, 3, 3))
+    for (i, j), k in {(0, 0): 'tt', (0, 1): 'te', (1, 1): 'ee', (2, 2): 'bb'}.items():
+        smat[:, i, j] = smat[:, j, i] = dl[k][:lmax + 1]
+    x = opfilt_tp._lmat3(smat).apply(ivf)                      # Wiener solution = S * inverse-variance filtered
+    r = b - opfilt_tp.fwd_op(dl, nf)(x)
+    dot = opfilt_tp.dot_op()
+    assert np.sqrt(dot(r, r) / dot(b, b)) < 3e-5
+    torch.cuda.synchronize()
+
+    class _sims:
+        def hashdict(self): return {'sims': 'tp_test'}
+        def get_sim_tmap(self, idx): return tmap
+        def get_sim_pmap(self, idx): return qmap, umap
+    ivfs = filt_cinv.library_cinv_jTP(str(tmp_path / 'ivfs'), _sims(), cinv, cls)
+    assert rel_l2(ivfs.get_sim_elm(0), elm) < 1e-12
+    qlms = qest.library_jtTP(str(tmp_path / 'qlms'), ivfs, ivfs, nside, lmax_qlm=lmax)
+    G = qlms.get_sim_qlm('p', 0)
+    assert np.all(np.isfinite(G)) and np.any(G != 0)
