@@ -432,7 +432,7 @@ static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *a
   LAUNCHED();
   const int nr = pick_nr(p, spin ? env_int("PLK_NR_SYNS", 4) : env_int("PLK_NR_SYN0", 4));
   dim3 grid((p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr), nm);
-  const int nthr = (kNCW + 1) * 32;
+  const int nthr = kLegThreads;
 #define SYN(SP, NR)                                                                                              \
   legendre_synth_kernel<SP, NR><<<grid, nthr, leg_smem<SP, true>(NR), st>>>(p->g, d, p->rec.p, X1, X2, p->pitch, morder, dx)
 #define SYNG(NR)                                                                                                  \
@@ -472,7 +472,7 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   }
   if (nm == 0) return 0;
   dim3 grid(ntile, nm);
-  const int nthr = (kNCW + 1) * 32;
+  const int nthr = kLegThreads;
 #define ANA(SP, NR)                                                                                              \
   legendre_anal_kernel<SP, NR><<<grid, nthr, leg_smem<SP, false>(NR), st>>>(p->g, d, X1, X2, p->pitch, (double *)p->part.p, stride, morder, env_int("PLK_DBG_ANA", 0))
   prof_begin(spin ? 3 : 2, st);

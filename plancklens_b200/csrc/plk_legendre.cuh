@@ -15,24 +15,28 @@
 
 namespace plk {
 
+#ifndef PLK_PRODUCER_WARP
+#define PLK_PRODUCER_WARP 0   // 1: a fifth warp only issues the TMA copies (round-1 layout); 0: lane 0 of warp 0 issues them
+#endif                        //    between chunks -- the block shrinks to 128 threads and a third block fits each SM
 #ifndef PLK_CHUNK
 #define PLK_CHUNK 128
 #endif
 #ifndef PLK_SYN_MINB
-#define PLK_SYN_MINB 1
+#define PLK_SYN_MINB (PLK_PRODUCER_WARP ? 1 : 3)   // 128-thread blocks: three per SM if <= 170 registers
 #endif
 #ifndef PLK_ANA_MINB
-#define PLK_ANA_MINB 1
+#define PLK_ANA_MINB (PLK_PRODUCER_WARP ? 1 : 3)
 #endif
 #ifndef PLK_ANA_PIPE
 #define PLK_ANA_PIPE 1     // software-pipelined butterfly in the analysis kernel (0: plain loop)
 #endif
 #ifndef PLK_ANA_MINB_S2
-#define PLK_ANA_MINB_S2 2  // resident blocks asked for the spin-s NR = 2 analysis kernel
+#define PLK_ANA_MINB_S2 (PLK_PRODUCER_WARP ? 2 : 3)  // resident blocks asked for the spin-s NR = 2 analysis kernel
 #endif
 constexpr int kChunk = PLK_CHUNK;      // l values per TMA stage (even)
 constexpr int kStages = 4;
 constexpr int kNCW = 4;          // compute warps per block
+constexpr int kLegThreads = (kNCW + PLK_PRODUCER_WARP) * 32;
 constexpr int kSeedThrExp = -120;  // accumulation starts once |p_l| >= 2^-120 (libsharp itself uses 2^-60)
 
 struct DevGeom {
@@ -224,6 +228,36 @@ PLK_D void producer_loop(unsigned char *stage_base, uint64_t *full, uint64_t *em
   }
 }
 
+// One chunk of row m into stage (c - c0) % kStages; the caller has made sure the stage is free.
+template <bool SPIN, bool SYNTH>
+PLK_D void issue_chunk(unsigned char *stage_base, uint64_t *full, const void *rec_row, const double2 *uv_row, int K,
+                       int c0, int c) {
+  using SB = StageBytes<SPIN, SYNTH>;
+  const int st = (c - c0) % kStages;
+  const int k0 = c * kChunk;
+  const int n = min(kChunk, K - k0);
+  unsigned char *dst = stage_base + (size_t)st * SB::stage;
+  mbar_expect_tx(&full[st], (uint32_t)n * SB::per_l);
+  if (SYNTH) tma_load_1d(dst, (const unsigned char *)rec_row + (size_t)k0 * SB::rec, (uint32_t)n * SB::rec, &full[st]);
+  tma_load_1d(dst + SB::rec * kChunk, uv_row + k0, (uint32_t)n * 16, &full[st]);
+}
+// Producer duties folded into compute warp 0 (PLK_PRODUCER_WARP == 0).  Called by every thread of warp 0 after it
+// has released chunk c: refills the stage of chunk c - 1 -- which the other warps have almost always left by now,
+// so the wait is free -- with chunk c - 1 + kStages (prefetch distance kStages - 1 chunks).
+template <bool SPIN, bool SYNTH>
+PLK_D void refill_behind(unsigned char *stage_base, uint64_t *full, uint64_t *empty, const void *rec_row,
+                         const double2 *uv_row, int K, int c0, int nchunk, int c, int lane) {
+  const int cb = c - 1;                       // chunk whose stage gets refilled
+  const int cn = cb + kStages;                // chunk to load
+  if (cb < c0 || cn >= nchunk) return;
+  if (lane == 0) {
+    const int it = cb - c0;
+    mbar_wait(&empty[it % kStages], (it / kStages) & 1);
+    issue_chunk<SPIN, SYNTH>(stage_base, full, rec_row, uv_row, K, c0, cn);
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------- synthesis
 // rec rows: spin 0: double2 a'_l = alpha_l * fl_l * a_lm ; spin s: double4 {H+ re, H+ im, H- re, H- im} with
 //   H+ = -1/2 alpha (G + iC),  H- = -1/2 (-1)^s alpha (G - iC)        (prepared by prep_alm_kernel)
@@ -232,7 +266,7 @@ PLK_D void producer_loop(unsigned char *stage_base, uint64_t *full, uint64_t *em
 //   qest.py:566-595), so H- = (-1)^s H+ and the four sums collapse to even / odd partial sums of H+ p+ and H+ p-:
 //   8 instead of 12 DFMA per (l, ring pair).
 template <bool SPIN, int NR, bool GRAD = false>
-__global__ void __launch_bounds__((kNCW + 1) * 32, PLK_SYN_MINB)
+__global__ void __launch_bounds__(kLegThreads, PLK_SYN_MINB)
 legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *__restrict__ X1, cplx *__restrict__ X2,
                       int pitch, const int *__restrict__ morder, DistX dx) {
   using SB = StageBytes<SPIN, true>;
@@ -296,10 +330,14 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
   const int nchunk = (K + kChunk - 1) / kChunk;
   const int c0 = kb_min >= K ? nchunk : kb_min / kChunk;
 
-  if (warp == kNCW) {
-    const unsigned char *rec_row = (const unsigned char *)rec + row * SB::rec;
-    producer_loop<SPIN, true>(stage_base, full, empty, rec_row, t.UV + row, K, c0, nchunk);
-    return;
+  const unsigned char *rec_row = (const unsigned char *)rec + row * SB::rec;
+  if (PLK_PRODUCER_WARP) {
+    if (warp == kNCW) {
+      producer_loop<SPIN, true>(stage_base, full, empty, rec_row, t.UV + row, K, c0, nchunk);
+      return;
+    }
+  } else if (threadIdx.x == 0) {
+    for (int c = c0; c < min(nchunk, c0 + kStages); ++c) issue_chunk<SPIN, true>(stage_base, full, rec_row, t.UV + row, K, c0, c);
   }
 
   // accumulators
@@ -392,6 +430,8 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
+    if (!PLK_PRODUCER_WARP && warp == 0)
+      refill_behind<SPIN, true>(stage_base, full, empty, rec_row, t.UV + row, K, c0, nchunk, c, lane);
   }
 
   // sigma at even offset is (-1)^{l0+m}
@@ -487,7 +527,7 @@ PLK_D void butterfly16(double (&v)[16], int lane) {
 }
 
 template <bool SPIN, int NR>
-__global__ void __launch_bounds__((kNCW + 1) * 32, (SPIN && NR == 2) ? PLK_ANA_MINB_S2 : PLK_ANA_MINB)
+__global__ void __launch_bounds__(kLegThreads, (SPIN && NR == 2) ? PLK_ANA_MINB_S2 : PLK_ANA_MINB)
 legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cplx *__restrict__ X2, int pitch,
                      double *__restrict__ part, long long part_stride /* doubles per tile */,
                      const int *__restrict__ morder, int dbg) {
@@ -588,9 +628,13 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
   const int c0 = kb_min >= K ? nchunk : kb_min / kChunk;
   double *prow = part + (size_t)blockIdx.x * part_stride + row * NV;
 
-  if (warp == kNCW) {
-    producer_loop<SPIN, false>(stage_base, full, empty, nullptr, t.UV + row, K, c0, nchunk);
-    return;
+  if (PLK_PRODUCER_WARP) {
+    if (warp == kNCW) {
+      producer_loop<SPIN, false>(stage_base, full, empty, nullptr, t.UV + row, K, c0, nchunk);
+      return;
+    }
+  } else if (threadIdx.x == 0) {
+    for (int c = c0; c < min(nchunk, c0 + kStages); ++c) issue_chunk<SPIN, false>(stage_base, full, nullptr, t.UV + row, K, c0, c);
   }
   // chunks before c0 carry no contribution from this tile: write zeros
   for (int i = threadIdx.x; i < min(c0 * kChunk, K) * NV; i += kNCW * 32) prow[i] = 0.0;
@@ -711,6 +755,8 @@ legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cp
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
+    if (!PLK_PRODUCER_WARP && warp == 0)
+      refill_behind<SPIN, false>(stage_base, full, empty, nullptr, t.UV + row, K, c0, nchunk, c, lane);
     if (dbg & 2) continue;
     named_bar_sync(1, kNCW * 32);
     // sum the per-warp slices of this chunk and write the tile partial

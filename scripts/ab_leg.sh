@@ -1,6 +1,4 @@
 #!/bin/bash
-# A/B timing of Legendre kernel variants: NR settings of the in-tree library, then variants/*.so
+# A/B timing of Legendre kernel variants: the in-tree library, then variants/*.so
 python scripts/time_leg.py
-PLK_NR_ANAS=1 PLK_NR_ANA0=2 python scripts/time_leg.py
-PLK_NR_ANAS=4 PLK_NR_ANA0=1 python scripts/time_leg.py
 for f in variants/*.so; do [ -f $f ] && PLK_LIB_PATH=$f python scripts/time_leg.py; done
