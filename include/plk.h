@@ -171,6 +171,14 @@ int plk_dist_ring_anal(plk_dist *dist, int spin, const double *map1, const doubl
 int plk_dist_legendre_anal(plk_dist *dist, int spin, const double *fl1, const double *fl2, void *alm1, void *alm2,
                            void *stream);
 
+/* ---- Wigner small-d transforms on a set of nodes x_i = cos(theta_i): what
+ *      plancklens/wigners/wigners.f90:566-684 provides to utils_spin.wignerc (utils_spin.py:52-93), and through it to
+ *      qresp.get_response and nhl.get_nhl.  All pointers are device pointers.
+ *   wignerpos  : xi[i] = sum_l cl[l] (2l+1)/(4 pi) d^l_{s1 s2}(x[i])
+ *   wignercoeff: cl[l] = 2 pi sum_i f[i] d^l_{s1 s2}(x[i]),  0 <= l <= lmax   (f = function values times quadrature weights) */
+int plk_wignerpos_dev(const double *cl, int lmax, const double *x, int nx, int s1, int s2, double *xi, void *stream);
+int plk_wignercoeff_dev(const double *f, const double *x, int nx, int s1, int s2, int lmax, double *cl, void *stream);
+
 /* ---- measurement helpers (bench.py): per-kernel CUDA-event timing of the Legendre launches and the device's
  *      FP64 FMA peak.  kinds: 0 synthesis spin 0, 1 synthesis spin s, 2 analysis spin 0, 3 analysis spin s,
  *      4 synthesis spin s with zero curl input (gradient-only kernel: 16 instead of 24 flop per unit). */

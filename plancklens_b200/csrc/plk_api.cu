@@ -6,6 +6,7 @@
 #include <map>
 #include <numeric>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/plk.h"
@@ -14,6 +15,7 @@
 #include "plk_fft.cuh"
 #include "plk_legendre.cuh"
 #include "plk_tables.h"
+#include "plk_wigner.cuh"
 
 using namespace plk;
 
@@ -1021,6 +1023,81 @@ extern "C" int plk_rlm2alm_dev(int lmax, const double *rlm, void *alm, void *str
 extern "C" int plk_dense_matvec_dev(int n, const double *A, const double *x, double *y, void *stream) {
   if (!A || !x || !y || n < 1) return fail(PLK_EINVAL, "bad argument");
   matvec_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(n, A, x, y);
+  LAUNCHED();
+  return PLK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ Wigner small-d transforms
+namespace {
+struct WigDev {
+  double *A = nullptr, *B = nullptr, *C = nullptr;
+  WigCoef w{};
+};
+std::map<std::tuple<int, int, int>, WigDev> g_wig;     // (s1, s2, lmax) -> device coefficient tables (current device)
+DevBuf g_wig_partial, g_wig_clw;
+
+int wig_get(int s1, int s2, int lmax, WigCoef *out) {
+  const auto key = std::make_tuple(s1, s2, lmax);
+  auto it = g_wig.find(key);
+  if (it == g_wig.end()) {
+    const int l0 = std::max(std::abs(s1), std::abs(s2));
+    std::vector<double> A(lmax + 2, 0.0), B(lmax + 2, 0.0), C(lmax + 2, 0.0);
+    const long double m = s1, mp = s2;
+    for (int l = l0; l <= lmax; ++l) {
+      if (l == 0) { A[l] = 1.0; continue; }             // P_1 = x P_0
+      const long double j = l;
+      const long double den = j * sqrtl(((j + 1) * (j + 1) - m * m) * ((j + 1) * (j + 1) - mp * mp));
+      A[l] = (double)((2 * j + 1) * j * (j + 1) / den);
+      B[l] = (double)(-(2 * j + 1) * m * mp / den);
+      C[l] = (double)((j + 1) * sqrtl((j * j - m * m) * (j * j - mp * mp)) / den);
+    }
+    WigDev d;
+    const size_t nb = (size_t)(lmax + 2) * sizeof(double);
+    CK(cudaMalloc((void **)&d.A, nb)); CK(cudaMalloc((void **)&d.B, nb)); CK(cudaMalloc((void **)&d.C, nb));
+    CK(cudaMemcpy(d.A, A.data(), nb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.B, B.data(), nb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.C, C.data(), nb, cudaMemcpyHostToDevice));
+    const int a = std::abs(s1 - s2), b = std::abs(s1 + s2);
+    long double seed = 1.0L;                             // sqrt((a+b)! / (a! b!)) = sqrt(binomial(a+b, a))
+    for (int k = 1; k <= a; ++k) seed *= (long double)(b + k) / k;
+    seed = sqrtl(seed);
+    if (s2 < s1 && ((s1 - s2) & 1)) seed = -seed;        // xi_{m m'} = (-1)^{m' - m} for m' < m
+    d.w.A = d.A; d.w.B = d.B; d.w.C = d.C; d.w.l0 = l0; d.w.lmax = lmax; d.w.seed = (double)seed; d.w.a = a; d.w.b = b;
+    it = g_wig.emplace(key, d).first;
+  }
+  *out = it->second.w;
+  return 0;
+}
+}  // namespace
+
+extern "C" int plk_wignerpos_dev(const double *cl, int lmax, const double *x, int nx, int s1, int s2, double *xi, void *stream) {
+  if (!cl || !x || !xi || lmax < 0 || nx < 1) return fail(PLK_EINVAL, "bad argument");
+  if (std::abs(s1) > 8 || std::abs(s2) > 8) return fail(PLK_EINVAL, "spins out of range: %d %d", s1, s2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (std::max(std::abs(s1), std::abs(s2)) > lmax) { CK(cudaMemsetAsync(xi, 0, (size_t)nx * sizeof(double), st)); return PLK_OK; }
+  WigCoef w;
+  int rc = wig_get(s1, s2, lmax, &w);
+  if (rc) return rc;
+  if ((rc = ensure(g_wig_clw, (size_t)(lmax + 1) * sizeof(double)))) return rc;
+  wig_scale_kernel<<<(lmax + 256) / 256, 256, 0, st>>>(cl, lmax, (double *)g_wig_clw.p);
+  LAUNCHED();
+  wignerpos_kernel<<<(nx + 127) / 128, 128, 0, st>>>(w, (const double *)g_wig_clw.p, x, nx, xi);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_wignercoeff_dev(const double *f, const double *x, int nx, int s1, int s2, int lmax, double *cl, void *stream) {
+  if (!cl || !x || !f || lmax < 0 || nx < 1) return fail(PLK_EINVAL, "bad argument");
+  if (std::abs(s1) > 8 || std::abs(s2) > 8) return fail(PLK_EINVAL, "spins out of range: %d %d", s1, s2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (std::max(std::abs(s1), std::abs(s2)) > lmax) { CK(cudaMemsetAsync(cl, 0, (size_t)(lmax + 1) * sizeof(double), st)); return PLK_OK; }
+  WigCoef w;
+  int rc = wig_get(s1, s2, lmax, &w);
+  if (rc) return rc;
+  const int nblk = (nx + 255) / 256, pitch = lmax + 1;
+  if ((rc = ensure(g_wig_partial, (size_t)nblk * pitch * sizeof(double)))) return rc;
+  wignercoeff_kernel<<<nblk, 256, 0, st>>>(w, f, x, nx, (double *)g_wig_partial.p, pitch);
+  LAUNCHED();
+  wigner_finish_kernel<<<(lmax + 256) / 256, 256, 0, st>>>((const double *)g_wig_partial.p, nblk, pitch, lmax, 2.0 * M_PI, cl);
   LAUNCHED();
   return PLK_OK;
 }

@@ -1,11 +1,13 @@
 """Quadratic-estimator weight definitions (reference: plancklens/qresp.py:50-163).
 
-Only the part of `qresp` that is on the SHT hot path is mirrored: `get_qes` and the response-leg helpers that
-build the list of `utils_qe.qe` terms consumed by `utils_qe.qe_eval`.  The response / normalisation integrals
-(`get_response`, `resp_lib_simple`) need the Wigner small-d transforms and are out of scope.
+`get_qes` and the response-leg helpers build the list of `utils_qe.qe` terms consumed by `utils_qe.qe_eval` (the
+SHT hot path); `get_response` evaluates the estimator normalisations with the Wigner small-d transforms of
+libplk_b200 (`utils_spin.wignerc`) where the reference calls its Fortran extension.
+`resp_lib_simple` (sqlite cache of the same numbers) is not mirrored.
 """
 import numpy as np
 
+from . import utils as ut
 from . import utils_qe as uqe
 from . import utils_spin as uspin
 
@@ -84,3 +86,74 @@ def get_qes(qe_key, lmax, cls_weight, lmax2=None, transf=None):
         legb = uqe.qeleg(0, 0, 0.5 * _clinv(transf[:lmax + 1]))
         return uqe.qe_simplify([uqe.qe(lega, legb, lambda L: np.ones(len(L)))])
     assert 0, qe_key + ' not implemented'
+
+
+def get_response(qe_key, lmax_ivf, source, cls_weight, cls_cmb, fal, fal_leg2=None, lmax_ivf2=None, lmax_qlm=None,
+                 transf=None):
+    r"""QE response (normalisation) :math:`R_L` of estimator `qe_key` to anisotropy `source` (reference:
+    qresp.py:269-311).  Returns (GG, CC, GC, CG).  Not symmetrised in the two filters if they differ."""
+    if lmax_ivf2 is None:
+        lmax_ivf2 = lmax_ivf
+    if lmax_qlm is None:
+        lmax_qlm = lmax_ivf + lmax_ivf2
+    if '_bh_' in qe_key:     # bias-hardened estimators (reference: qresp.py:289-307)
+        k, hsource = qe_key.split('_bh_')
+        assert len(hsource) == 1, hsource
+        h = hsource[0]
+        kw = dict(fal_leg2=fal_leg2, lmax_ivf2=lmax_ivf2, lmax_qlm=lmax_qlm, transf=transf)
+        GG_ks, CC_ks, GC_ks, CG_ks = get_response(k, lmax_ivf, source, cls_weight, cls_cmb, fal, **kw)
+        GG_hs, CC_hs, GC_hs, CG_hs = get_response(h + k[1:], lmax_ivf, source, cls_weight, cls_cmb, fal, **kw)
+        GG_kh, CC_kh, GC_kh, CG_kh = get_response(k, lmax_ivf, h, cls_weight, cls_cmb, fal, **kw)
+        GG_hh, CC_hh, GC_hh, CG_hh = get_response(h + k[1:], lmax_ivf, h, cls_weight, cls_cmb, fal, **kw)
+        iG, iC = ut.cli(GG_hh), ut.cli(CC_hh)
+        return (GG_ks - (GG_kh * GG_hs * iG + GC_kh * CG_hs * iC), CC_ks - (CG_kh * GC_hs * iG + CC_kh * CC_hs * iC),
+                GC_ks - (GG_kh * GC_hs * iG + GC_kh * CC_hs * iC), CG_ks - (CG_kh * GG_hs * iG + CC_kh * CG_hs * iC))
+    assert source not in ['n', 'ntt'], 'point-source / noise-inhomogeneity responses are not mirrored'
+    qes = get_qes(qe_key, lmax_ivf, cls_weight, lmax2=lmax_ivf2, transf=transf)
+    return _get_response(qes, source, cls_cmb, fal, lmax_qlm, fal_leg2=fal_leg2)
+
+
+def _get_response(qes, source, cls_cmb, fal_leg1, lmax_qlm, fal_leg2=None):
+    """reference: qresp.py:376-417 (same loops, same order of accumulation)"""
+    fal_leg2 = fal_leg1 if fal_leg2 is None else fal_leg2
+    RGG = np.zeros(lmax_qlm + 1, dtype=float)
+    RCC = np.zeros(lmax_qlm + 1, dtype=float)
+    RGC = np.zeros(lmax_qlm + 1, dtype=float)
+    RCG = np.zeros(lmax_qlm + 1, dtype=float)
+    Ls = np.arange(lmax_qlm + 1, dtype=int)
+    for qe in qes:
+        si, ti = (qe.leg_a.spin_in, qe.leg_b.spin_in)
+        so, to = (qe.leg_a.spin_ou, qe.leg_b.spin_ou)
+        for s2 in [0, -2, 2]:
+            FA = uspin.get_spin_matrix(si, s2, fal_leg1)
+            if not np.any(FA):
+                continue
+            for t2 in [0, -2, 2]:
+                FB = uspin.get_spin_matrix(ti, t2, fal_leg2)
+                if not np.any(FB):
+                    continue
+                rW_st, prW_st, mrW_st, s_cL_st = get_covresp(source, -s2, t2, cls_cmb, len(FB) - 1)
+                clA = ut.joincls([qe.leg_a.cl, FA])
+                clB = ut.joincls([qe.leg_b.cl, FB, mrW_st.conj()])
+                Rpr_st = uspin.wignerc(clA, clB, so, s2, to, -s2 + rW_st, lmax_out=lmax_qlm) * s_cL_st(Ls)
+
+                rW_ts, prW_ts, mrW_ts, s_cL_ts = get_covresp(source, -t2, s2, cls_cmb, len(FA) - 1)
+                clA = ut.joincls([qe.leg_a.cl, FA, mrW_ts.conj()])
+                clB = ut.joincls([qe.leg_b.cl, FB])
+                Rpr_st = Rpr_st + uspin.wignerc(clA, clB, so, -t2 + rW_ts, to, t2, lmax_out=lmax_qlm) * s_cL_ts(Ls)
+                assert rW_st == rW_ts and rW_st >= 0, (rW_st, rW_ts)
+                if rW_st > 0:
+                    clA = ut.joincls([qe.leg_a.cl, FA])
+                    clB = ut.joincls([qe.leg_b.cl, FB, prW_st.conj()])
+                    Rmr_st = uspin.wignerc(clA, clB, so, s2, to, -s2 - rW_st, lmax_out=lmax_qlm) * s_cL_st(Ls)
+                    clA = ut.joincls([qe.leg_a.cl, FA, prW_ts.conj()])
+                    clB = ut.joincls([qe.leg_b.cl, FB])
+                    Rmr_st = Rmr_st + uspin.wignerc(clA, clB, so, -t2 - rW_ts, to, t2, lmax_out=lmax_qlm) * s_cL_ts(Ls)
+                else:
+                    Rmr_st = Rpr_st
+                prefac = qe.cL(Ls)
+                RGG += prefac * (Rpr_st.real + Rmr_st.real * (-1) ** rW_st)
+                RCC += prefac * (Rpr_st.real - Rmr_st.real * (-1) ** rW_st)
+                RGC += prefac * (-Rpr_st.imag + Rmr_st.imag * (-1) ** rW_st)
+                RCG += prefac * (Rpr_st.imag + Rmr_st.imag * (-1) ** rW_st)
+    return RGG, RCC, RGC, RCG

@@ -115,3 +115,23 @@ def synthetic_cls(lmax):
     for c in (tt, ee, bb, te):
         c[:2] = 0.0
     return {'tt': tt, 'ee': ee, 'bb': bb, 'te': te}
+
+
+def cl_inverse(cls):
+    """Inverse of the T, E, B spectral matrices; dictionaries in and out (reference: utils.py:336-366)."""
+    def ext(cl, lmax):
+        ret = np.zeros(lmax + 1, dtype=float)
+        n = min(len(cl), lmax + 1)
+        ret[:n] = np.asarray(cl)[:n]
+        return ret
+    lmax = np.max([len(cl) for cl in cls.values()]) - 1
+    m = np.zeros((lmax + 1, 3, 3))
+    for k, (i, j) in zip(['tt', 'ee', 'bb', 'te', 'tb', 'eb'], [[0, 0], [1, 1], [2, 2], [0, 1], [0, 2], [1, 2]]):
+        m[:, i, j] = m[:, j, i] = ext(cls.get(k, [0.]), lmax)
+    mi = np.linalg.pinv(m)
+    out = {}
+    for k, (i, j) in zip(['tt', 'ee', 'bb', 'te', 'tb', 'eb'], [[0, 0], [1, 1], [2, 2], [0, 1], [0, 2], [1, 2]]):
+        arr = mi[:, i, j].copy()
+        if np.any(arr):
+            out[k] = arr
+    return out

@@ -1,0 +1,110 @@
+"""Wigner small-d transforms: oracle against the Jacobi closed form and known answers
+on the CPU; CUDA kernels against the oracle and the reference's own test identity (tests/test_w.py) on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import rel_l2
+
+
+def test_oracle_recurrence_matches_jacobi_closed_form():
+    from oracle import ref_wigner as rw
+    x = np.cos(np.linspace(0.05, np.pi - 0.05, 41))
+    for s1, s2 in [(0, 0), (1, 0), (0, 1), (2, 0), (2, 2), (2, -2), (-2, 2), (1, -1), (3, 1), (-3, 2), (4, -2), (3, -3)]:
+        d = rw.wigner_d_all(120, s1, s2, x)
+        for l in (max(abs(s1), abs(s2)), 7, 30, 120):
+            if l >= max(abs(s1), abs(s2)):
+                ref = rw.wigner_d_jacobi(l, s1, s2, x)
+                assert np.max(np.abs(d[l] - ref)) < 1e-11 * max(1.0, np.max(np.abs(ref))), (s1, s2, l)
+
+
+def test_oracle_known_answers():
+    from oracle import ref_wigner as rw
+    x, w = rw.get_xgwg(64)
+    assert abs(w.sum() - 2.0) < 1e-13 and abs((w * x ** 2).sum() - 2.0 / 3.0) < 1e-13
+    # d^l_00 = P_l ; d^1_11 = (1 + x)/2 ; d^1_10 = -sin(theta)/sqrt(2) ; d^2_22 = ((1+x)/2)^2
+    d = rw.wigner_d_all(3, 0, 0, x)
+    assert np.allclose(d[2], 0.5 * (3 * x ** 2 - 1), atol=1e-14)
+    assert np.allclose(rw.wigner_d_all(1, 1, 1, x)[1], 0.5 * (1 + x), atol=1e-14)
+    assert np.allclose(rw.wigner_d_all(1, 1, 0, x)[1], -np.sqrt(1 - x ** 2) / np.sqrt(2.), atol=1e-14)
+    assert np.allclose(rw.wigner_d_all(2, 2, 2, x)[2], (0.5 * (1 + x)) ** 2, atol=1e-14)
+    # orthogonality = round trip: wignercoeff(wignerpos(cl) w) = cl
+    rng = np.random.default_rng(0)
+    cl = rng.standard_normal(40)
+    cl[:2] = 0
+    back = rw.wignercoeff(rw.wignerpos(cl, x, 2, -2) * w, x, 2, -2, 39)
+    assert rel_l2(back, cl) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("s1,s2", [(0, 0), (1, 0), (2, 2), (2, -2), (-1, 3), (0, -2), (3, 1), (4, -2)])
+def test_gpu_wigner_transforms_match_oracle(s1, s2):
+    from oracle import ref_wigner as rw
+    from plancklens_b200 import wigners
+    rng = np.random.default_rng(abs(s1) * 10 + abs(s2))
+    lmax, n = 700, 1100
+    xg, wg = wigners.get_xgwg(-1., 1., n)
+    xr, wr = rw.get_xgwg(n)
+    assert np.max(np.abs(xg - xr)) < 1e-14 and np.max(np.abs(wg - wr)) < 1e-15
+    cl = rng.standard_normal(lmax + 1) / (1.0 + np.arange(lmax + 1)) ** 2
+    xi = wigners.wignerpos(cl, xg, s1, s2)
+    assert rel_l2(xi, rw.wignerpos(cl, xg, s1, s2)) < 1e-11
+    f = rng.standard_normal(n) * wg
+    assert rel_l2(wigners.wignercoeff(f, xg, s1, s2, lmax), rw.wignercoeff(f, xg, s1, s2, lmax)) < 1e-11
+
+
+@pytest.mark.gpu
+def test_gpu_wignerc_matches_oracle():
+    from oracle import ref_wigner as rw
+    from plancklens_b200 import utils_spin as us
+    rng = np.random.default_rng(3)
+    cl1 = rng.standard_normal(301) / (1.0 + np.arange(301)) ** 1.5
+    cl2 = (rng.standard_normal(257) + 1j * rng.standard_normal(257)) / (1.0 + np.arange(257)) ** 1.5
+    for args in [(0, 0, 0, 0), (1, 0, -1, 2), (2, -2, 1, 1), (-3, 2, 1, 0)]:
+        got = us.wignerc(cl1, cl2, *args, lmax_out=400)
+        assert rel_l2(got, rw.wignerc(cl1, cl2, *args, lmax_out=400)) < 1e-10
+
+
+@pytest.mark.gpu
+def test_w():
+    """Port of the reference's own (and only) test, tests/test_w.py: for optimally filtered maps the analytical N0
+    (nhl.get_nhl) equals the response (qresp.get_response), for the lensing ('p') and modulation ('f') estimators,
+    separately and jointly filtered.  Same inputs, same tolerances (rtol 1e-6)."""
+    from plancklens_b200 import hp, nhl, qresp, utils
+    cls_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'plancklens_b200', 'data', 'cls')
+    lmax_ivf, lmin_ivf = 500, 100
+    nlev_t, nlev_p, beam_fwhm = 35., 35. * np.sqrt(2.), 6.
+    lmax_qlm = lmax_ivf
+    for ksource in ['p', 'f']:
+        qe_keys = [ksource + 'tt', ksource + '_p', ksource]
+        transf = hp.gauss_beam(beam_fwhm / 60. / 180. * np.pi, lmax=lmax_ivf)
+        cls_len = utils.camb_clfile(os.path.join(cls_path, 'FFP10_wdipole_lensedCls.dat'))
+        cls_weight = utils.camb_clfile(os.path.join(cls_path, 'FFP10_wdipole_lensedCls.dat'))
+        nl = lambda nlev: (nlev / 60. / 180. * np.pi) ** 2 / transf ** 2
+        fal_sepTP = {'tt': utils.cli(cls_len['tt'][:lmax_ivf + 1] + nl(nlev_t)),
+                     'ee': utils.cli(cls_len['ee'][:lmax_ivf + 1] + nl(nlev_p)),
+                     'bb': utils.cli(cls_len['bb'][:lmax_ivf + 1] + nl(nlev_p))}
+        cls_ivfs_sepTP = {'tt': fal_sepTP['tt'].copy(), 'ee': fal_sepTP['ee'].copy(), 'bb': fal_sepTP['bb'].copy(),
+                          'te': cls_len['te'][:lmax_ivf + 1] * fal_sepTP['tt'] * fal_sepTP['ee']}
+        cls_dat = {'tt': cls_len['tt'][:lmax_ivf + 1] + nl(nlev_t), 'ee': cls_len['ee'][:lmax_ivf + 1] + nl(nlev_p),
+                   'bb': cls_len['bb'][:lmax_ivf + 1] + nl(nlev_p), 'te': np.copy(cls_len['te'][:lmax_ivf + 1])}
+        fal_jtTP = utils.cl_inverse(cls_dat)
+        cls_ivfs_jtTP = utils.cl_inverse(cls_dat)
+        for cls in [fal_sepTP, fal_jtTP, cls_ivfs_sepTP, cls_ivfs_jtTP]:
+            for cl in cls.values():
+                cl[:max(1, lmin_ivf)] *= 0.
+        for qe_key in qe_keys:
+            NG, NC, NGC, NCG = nhl.get_nhl(qe_key, qe_key, cls_weight, cls_ivfs_sepTP, lmax_ivf, lmax_ivf, lmax_out=lmax_qlm)
+            RG, RC, RGC, RCG = qresp.get_response(qe_key, lmax_ivf, ksource, cls_weight, cls_len, fal_sepTP, lmax_qlm=lmax_qlm)
+            if qe_key[1:] in ['tt', '_p']:
+                assert np.allclose(NG[1:], RG[1:], rtol=1e-6), qe_key
+                assert np.allclose(NC[2:], RC[2:], rtol=1e-6), qe_key
+            assert np.all(NCG == 0.) and np.all(NGC == 0.)
+            assert np.all(RCG == 0.) and np.all(RGC == 0.)
+        NG, NC, NGC, NCG = nhl.get_nhl(ksource, ksource, cls_weight, cls_ivfs_jtTP, lmax_ivf, lmax_ivf, lmax_out=lmax_qlm)
+        RG, RC, RGC, RCG = qresp.get_response(ksource, lmax_ivf, ksource, cls_weight, cls_len, fal_jtTP, lmax_qlm=lmax_qlm)
+        assert np.allclose(NG[1:], RG[1:], rtol=1e-6), ksource
+        assert np.allclose(NC[2:], RC[2:], rtol=1e-6), ksource
+        assert np.all(NCG == 0.) and np.all(NGC == 0.)
+        assert np.all(RCG == 0.) and np.all(RGC == 0.)
