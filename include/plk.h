@@ -95,6 +95,8 @@ int plk_alm_dot2_dev(int lmax, int lmin, const void *a1, const void *b1, const v
 /* n <= 4 components (opfilt_tp.py:46-58: T, E and B summed, all from lmin), host arrays of device pointers */
 int plk_alm_dotn_dev(int lmax, int lmin, int n, const void *const *a, const void *const *b, double *result_dev,
                      void *stream);
+/* cl[l] = 1/(2l+1) sum_m a_lm conj(b_lm) over m = -l..l for real fields (hp.alm2cl; qecl.py:148, nhl.py:175-189) */
+int plk_alm2cl_dev(int lmax, const void *a, const void *b, double *cl, void *stream);
 /* out_dev[0] = scale * num_dev[0] / den_dev[0]: CG step lengths (cd_solve.py:69-71, :95-99) kept on the device so that
  * the fixed-iteration multigrid stages (multigrid.py:185-215) run without host synchronisation (CUDA-graph capturable) */
 int plk_scalar_ratio_dev(const double *num, const double *den, double scale, double *out, void *stream);

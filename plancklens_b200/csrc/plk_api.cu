@@ -899,6 +899,12 @@ extern "C" int plk_alm_dotn_dev(int lmax, int lmin, int n, const void *const *a,
   LAUNCHED();
   return PLK_OK;
 }
+extern "C" int plk_alm2cl_dev(int lmax, const void *a, const void *b, double *cl, void *stream) {
+  if (!a || !b || !cl || lmax < 0) return fail(PLK_EINVAL, "bad argument");
+  alm2cl_kernel<<<(lmax + 128) / 128, 128, 0, (cudaStream_t)stream>>>(lmax, (const cplx *)a, (const cplx *)b, cl);
+  LAUNCHED();
+  return PLK_OK;
+}
 extern "C" int plk_scalar_ratio_dev(const double *num, const double *den, double scale, double *out, void *stream) {
   if (!num || !den || !out) return fail(PLK_EINVAL, "NULL buffer");
   scalar_ratio_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(num, den, scale, out);

@@ -139,6 +139,20 @@ __global__ void final_sum_kernel(const double *__restrict__ partial, int n, int 
   }
 }
 
+// cl[l] = 1/(2l+1) sum_m w_m Re(a_lm conj b_lm), w_0 = 1, w_{m>0} = 2 (hp.alm2cl); one thread per l, coalesced over l
+__global__ void alm2cl_kernel(int lmax, const cplx *__restrict__ a, const cplx *__restrict__ b, double *__restrict__ cl) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > lmax) return;
+  double acc = 0.0;
+  for (int m = 0; m <= l; ++m) {
+    const int64_t i = alm_idx(lmax, l, m);
+    const cplx x = a[i], y = b[i];
+    const double t = fma(x.x, y.x, x.y * y.y);
+    acc += m == 0 ? t : 2.0 * t;
+  }
+  cl[l] = acc / (2.0 * l + 1.0);
+}
+
 // out[0] = scale * num[0] / den[0]: the CG step lengths (cd_solve.py:69-71, :95-99) without a host round trip
 __global__ void scalar_ratio_kernel(const double *__restrict__ num, const double *__restrict__ den, double scale,
                                     double *__restrict__ out) {

@@ -1,0 +1,114 @@
+"""QE (cross-)power spectra library (reference: plancklens/qecl.py:12-148).
+
+Combines two `qest.library` instances and a set of mean-field simulations into raw spectra
+:math:`\\frac{1}{(2L+1) f_{sky}} \\sum_M \\hat\\phi^A_{LM} \\hat\\phi^{B\\dagger}_{LM}` after mean-field subtraction.  The
+subtraction and `alm2cl` run on the GPU (`plk_alm_axpy_dev`, `plk_alm2cl_dev`); spectra are cached as `.npy` files
+under the reference's names (the reference keeps them in a sqlite `npdb`).  `qecl.average` is not mirrored.
+"""
+import os
+import pickle as pk
+
+import numpy as np
+
+from . import sht, utils
+from .helpers import mpi
+
+
+class library(object):
+    def __init__(self, lib_dir, qeA, qeB, mc_sims_mf):
+        self.lib_dir = lib_dir
+        self.prefix = lib_dir
+        self.qeA = qeA
+        self.qeB = qeB
+        self.mc_sims_mf = np.asarray(mc_sims_mf, dtype=int)
+        fsname = os.path.join(lib_dir, 'fskies.dat')
+        hname = os.path.join(self.lib_dir, 'qcl_sim_hash.pk')
+        if mpi.rank == 0:
+            if not os.path.exists(lib_dir):
+                os.makedirs(lib_dir)
+            if not os.path.exists(fsname):
+                ms = {1: self.qeA.get_mask(1), 2: self.qeA.get_mask(2), 3: self.qeB.get_mask(1), 4: self.qeB.get_mask(2)}
+                assert np.all([m.shape == ms[1].shape for m in ms.values()])
+                fskies = {}
+                for i in [1, 2, 3, 4]:
+                    for j in [1, 2, 3, 4][i - 1:]:
+                        fskies[10 * i + j] = np.mean(ms[i] * ms[j])
+                fskies[1234] = np.mean(ms[1] * ms[2] * ms[3] * ms[4])
+                with open(fsname, 'w') as f:
+                    for lab in np.sort(list(fskies.keys())):
+                        f.write('%4s %.5f \n' % (lab, fskies[lab]))
+            if not os.path.exists(hname):
+                with open(hname, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+        mpi.barrier()
+        with open(hname, 'rb') as f:
+            utils.hash_check(pk.load(f), self.hashdict(), fn=hname)
+        fskies = {}
+        with open(fsname) as f:
+            for line in f:
+                key, val = line.split()
+                fskies[int(key)] = float(val)
+        self.fskies = fskies
+        self.fsky1234, self.fsky11, self.fsky12, self.fsky22 = fskies[1234], fskies[11], fskies[12], fskies[22]
+
+    def hashdict(self):
+        return {'qeA': self.qeA.hashdict(), 'qeB': self.qeB.hashdict(), 'mc_sims_mf': self._mcmf_hash()}
+
+    def _mcmf_hash(self):
+        return utils.mchash(self.mc_sims_mf)
+
+    def get_lmaxqcl(self, k1, k2):
+        return min(self.qeA.get_lmax_qlm(k1), self.qeB.get_lmax_qlm(k2))
+
+    def load_sim_qcl(self, k1, idx, k2=None, lmax=None):
+        """Same as get_sim_qcl without triggering its calculation"""
+        return self.get_sim_qcl(k1, idx, k2=k2, lmax=lmax, calc=False)
+
+    def get_sim_qcl(self, k1, idx, k2=None, lmax=None, recache=False, calc=True):
+        """QE (cross-)power spectrum of simulation idx (idx = -1: data), mean field subtracted, / fsky."""
+        if k2 is None:
+            k2 = k1
+        assert k1 in self.qeA.keys and k2 in self.qeB.keys, (k1, k2)
+        assert idx not in self.mc_sims_mf, idx
+        lmax_qcl = self.get_lmaxqcl(k1, k2)
+        lmax_out = lmax or lmax_qcl
+        assert lmax_out <= lmax_qcl
+        tag = '%04d' % idx if idx >= 0 else 'dat'
+        assert idx >= -1
+        fname = os.path.join(self.lib_dir, 'sim_qcl_k1%s_k2%s_lmax%s_%s_%s.npy' % (k1, k2, lmax_qcl, tag, self._mcmf_hash()))
+        if calc and (recache or not os.path.exists(fname)):
+            qlmA = sht.dev_alm(self.qeA.get_sim_qlm(k1, idx, lmax=lmax_qcl))
+            if (k1 == k2) and (self.qeA is self.qeB):
+                qlmB = qlmA.clone()
+            else:
+                qlmB = sht.dev_alm(self.qeB.get_sim_qlm(k2, idx, lmax=lmax_qcl))
+            sht.alm_axpy(qlmA, sht.dev_alm(self.qeA.get_sim_qlm_mf(k1, self.mc_sims_mf[0::2], lmax=lmax_qcl)), -1.0)
+            sht.alm_axpy(qlmB, sht.dev_alm(self.qeB.get_sim_qlm_mf(k2, self.mc_sims_mf[1::2], lmax=lmax_qcl)), -1.0)
+            np.save(fname, self._alm2clfsky1234(qlmA, qlmB, k1, k2))
+        return np.load(fname)[:lmax_out + 1] / self.fskies[1234]
+
+    def get_sim_stats_qcl(self, k1, mc_sims, k2=None, recache=False):
+        """Mean and scatter of the QE spectra over mc_sims: object with `.mean()`, `.sigmas()`, `.N`
+        (the part of plancklens.utils.stats the spectra pipeline uses)."""
+        if k2 is None:
+            k2 = k1
+        cls = np.array([self.get_sim_qcl(k1, idx, k2=k2) for idx in mc_sims])
+        return _stats(cls)
+
+    def _alm2clfsky1234(self, qlm1, qlm2, k1, k2):
+        return sht.alm2cl(qlm1, qlm2).cpu().numpy()
+
+
+class _stats:
+    def __init__(self, rows):
+        self.rows = np.atleast_2d(rows)
+        self.N = self.rows.shape[0]
+
+    def mean(self):
+        return np.mean(self.rows, axis=0)
+
+    def sigmas(self):
+        return np.std(self.rows, axis=0, ddof=1) if self.N > 1 else np.zeros(self.rows.shape[1])
+
+    def sigmas_on_mean(self):
+        return self.sigmas() / np.sqrt(self.N)

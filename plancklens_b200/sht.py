@@ -248,6 +248,15 @@ def alm_dotn(avec, bvec, lmin=0, out=None):
     return out
 
 
+def alm2cl(a, b=None):
+    """hp.alm2cl on device alms -> device float64[lmax + 1]"""
+    b = a if b is None else b
+    lmax = alm_lmax(a.numel())
+    out = torch.empty(lmax + 1, dtype=torch.float64, device='cuda')
+    check(_lib.load().plk_alm2cl_dev(lmax, _ptr(a), _ptr(b), _ptr(out), _stream()))
+    return out
+
+
 def scalar_ratio(num, den, scale=1.0, out=None):
     """scale * num / den on 1-element device tensors (no host synchronisation)"""
     out = torch.empty(1, dtype=torch.float64, device='cuda') if out is None else out

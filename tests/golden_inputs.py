@@ -104,3 +104,31 @@ def chain_descr_tp(cd_solve):
     """Two-level version of the reference's default joint T+P chain (filt_cinv.py:398-405), sized for nside 32."""
     return [[1, ["split(dense, 8, diag_cl)"], 32, 16, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
             [0, ["split(stage(1), 32, diag_cl)"], 64, 32, np.inf, 1.0e-6, cd_solve.tr_cg, cd_solve.cache_mem()]]
+
+
+class idx_ivfs:
+    """In-memory filtering library whose simulations differ by index (deterministic mixes of the two seeded sets of
+    qe_case); `hp` is the healpy-shaped module providing almxfl (the shim on the reference side, plancklens_b200.hp
+    on the product side)."""
+    lib_dir = None
+
+    def __init__(self, q, hp):
+        self.q, self.hp = q, hp
+        self.cl = q['cls']
+
+    def hashdict(self):
+        return {'idx_ivfs': 1}
+
+    def get_fmask(self):
+        return np.ones(12 * self.q['nside'] ** 2)
+
+    def _mix(self, a, idx):
+        i = idx if idx >= 0 else 7
+        return self.q[a + 'lm1'] * (1.0 + 0.3 * i) + self.q[a + 'lm2'] * (0.2 * i - 0.1)
+
+    def get_sim_tlm(self, idx): return self._mix('t', idx)
+    def get_sim_elm(self, idx): return self._mix('e', idx)
+    def get_sim_blm(self, idx): return self._mix('b', idx)
+    def get_sim_tmliklm(self, idx): return self.hp.almxfl(self.get_sim_tlm(idx), self.q['cls']['tt'])
+    def get_sim_emliklm(self, idx): return self.hp.almxfl(self.get_sim_elm(idx), self.q['cls']['ee'])
+    def get_sim_bmliklm(self, idx): return self.hp.almxfl(self.get_sim_blm(idx), self.q['cls']['bb'])

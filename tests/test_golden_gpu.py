@@ -325,3 +325,23 @@ def test_qe_term_lists_match_reference_structure():
     assert n['ptt'] == 1 and n['p_p'] == 4 and n['p'] == 9, n
     for q in qresp.get_qes('p', 20, cls):
         assert q.leg_a.spin_ou + q.leg_b.spin_ou == 1
+
+
+def test_qecl_spectra_match_reference():
+    """qecl.library (mean-field subtracted QE spectra) against the unmodified reference:
+    auto- and cross-spectra within 1e-8 (north_star tolerance for qlm auto-spectra)."""
+    from plancklens_b200 import hp, qecl, qest
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_qecl.npz'))
+    q = gi.qe_case()
+    with tempfile.TemporaryDirectory() as tmp:
+        iv = gi.idx_ivfs(q, hp)
+        lib = qest.library_sepTP(os.path.join(tmp, 'dd'), iv, iv, q['cls']['te'], q['nside'], lmax_qlm=q['lmax_qlm'])
+        qcl = qecl.library(os.path.join(tmp, 'qcl'), lib, lib, np.array([1, 2, 3, 4]))
+        for k1, k2 in (('ptt', 'ptt'), ('p', 'p'), ('p_p', 'ptt'), ('x', 'x')):
+            ref = g['qcl_%s_%s' % (k1, k2)]
+            got = qcl.get_sim_qcl(k1, 0, k2=k2)
+            assert np.max(np.abs(got - ref)) < 1e-8 * np.max(np.abs(ref)), (k1, k2)
+        ref = g['qcl_p_dat']
+        assert np.max(np.abs(qcl.get_sim_qcl('p', -1) - ref)) < 1e-8 * np.max(np.abs(ref))
+        st = qcl.get_sim_stats_qcl('ptt', [0, 5, 6])
+        assert st.N == 3 and st.mean().shape == ref.shape
