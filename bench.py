@@ -190,6 +190,9 @@ def run_reference(args):
     """--impl reference: the CPU port of the step (healpy is not installable here), rank 0 only."""
     if int(os.environ.get('RANK', 0)) != 0:
         return
+    if int(os.environ.get('WORLD_SIZE', 1)) > 1:
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and gets all host cores
+        os.environ['OMP_NUM_THREADS'] = str(os.cpu_count())
     from oracle import ref_sht
     ref_sht.build()
     cls, transf, ftl, fel, fbl = fiducial(LMAX_IVF)
