@@ -243,10 +243,27 @@ PLK_HD void synth_input2(const cplx *X, int mmax, int n, int q, int kp, int shif
   // e^{i pi (k'+qc)/n} = g * e^{i pi c/4}
   const double r2 = 0.70710678118654752440;
   const cplx c8[4] = {mk(1.0, 0.0), mk(r2, r2), mk(0.0, 1.0), mk(-r2, r2)};
+  if (mmax <= q) {
+    // No aliasing beyond the first mirror image (every ring with n >= 4 mmax: the equatorial belt and most of the
+    // caps): the four folded bins reduce to X[k'], X[q] (k' = 0 only) and conj X[q - k'] -- two independent loads
+    // issued back to back instead of eight data-dependent loops.
+    const cplx zero = mk(0.0, 0.0);
+    const int mm = q - kp;                                     // 1 .. q
+    const cplx x0 = kp <= mmax ? X[kp] : zero;
+    const cplx xm = mm <= mmax ? X[mm] : zero;
+    const cplx D0 = kp == 0 ? mk(x0.x, 0.0) : x0;
+    const cplx D1 = (kp == 0 && q <= mmax) ? xm : zero;        // k = q exists only for k' = 0 (then mm = q)
+    const cplx D3 = shifted ? mk(-xm.x, xm.y) : conj(xm);      // sg * conj(X[q - k'])
+    d[0] = shifted ? (g * c8[0]) * D0 : D0;
+    d[1] = shifted ? (g * c8[1]) * D1 : D1;
+    d[2] = zero;
+    d[3] = shifted ? (g * c8[3]) * D3 : D3;
+  } else {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    cplx D = fold_bin(X, mmax, n, kp + q * c, shifted);
-    d[c] = shifted ? (g * c8[c]) * D : D;
+    for (int c = 0; c < 4; ++c) {
+      cplx D = fold_bin(X, mmax, n, kp + q * c, shifted);
+      d[c] = shifted ? (g * c8[c]) * D : D;
+    }
   }
   const cplx s02 = d[0] + d[2], s13 = d[1] + d[3], m02 = d[0] - d[2], m13 = mul_i(d[1] - d[3]);
   const cplx g4 = g2 * g2, g6 = g4 * g2;

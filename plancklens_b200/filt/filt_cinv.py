@@ -157,7 +157,8 @@ class cinv_t(cinv):
         else:
             talm = util_alm.dalm.from_numpy(soltn)
         self.chain.solve(talm, tmap)
-        return hp.almxfl(talm.numpy(), self.rescal_cl)
+        from .. import sht
+        return talm.almxfl(sht.dev_fl(self.rescal_cl, self.lmax), inplace=True).numpy()
 
 
 class cinv_p(cinv):

@@ -308,8 +308,8 @@ class alm_filter_ninv(object):
 
 def calc_prep(maps, s_cls, n_inv_filt):
     """b = B^t N^{-1} d for d = (Q, U)  (reference: opfilt_pp.py:306-317)."""
-    qmap = sht.dev_map(np.array(util.read_map(maps[0]), dtype=float)) if not isinstance(maps[0], torch.Tensor) else maps[0].clone()
-    umap = sht.dev_map(np.array(util.read_map(maps[1]), dtype=float)) if not isinstance(maps[1], torch.Tensor) else maps[1].clone()
+    qmap = sht.dev_map(util.read_map(maps[0])) if not isinstance(maps[0], torch.Tensor) else maps[0].clone()
+    umap = sht.dev_map(util.read_map(maps[1])) if not isinstance(maps[1], torch.Tensor) else maps[1].clone()
     assert qmap.numel() == umap.numel()
     lmax = len(n_inv_filt.b_transf) - 1
     n_inv_filt.apply_map([qmap, umap])

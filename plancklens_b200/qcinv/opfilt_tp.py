@@ -267,7 +267,7 @@ class alm_filter_ninv(object):
 
 def calc_prep(maps, s_cls, n_inv_filt):
     """b = B^t N^{-1} d for d = (T, Q, U)  (reference: opfilt_tp.py:14-31)."""
-    ms = [m.clone() if isinstance(m, torch.Tensor) else sht.dev_map(np.array(util.read_map(m), dtype=float)) for m in maps]
+    ms = [m.clone() if isinstance(m, torch.Tensor) else sht.dev_map(util.read_map(m)) for m in maps]
     assert ms[0].numel() == ms[1].numel() == ms[2].numel()
     n_inv_filt.apply_map(ms)
     lmax = len(n_inv_filt.b_transf) - 1

@@ -37,7 +37,7 @@ def _as_dalm(alm):
 
 def calc_prep(m, s_cls, n_inv_filt):
     """b = B^t N^{-1} d  (reference: opfilt_tt.py:30-36)."""
-    tmap = sht.dev_map(m).clone() if isinstance(m, torch.Tensor) else sht.dev_map(np.array(m, dtype=float))
+    tmap = sht.dev_map(m).clone() if isinstance(m, torch.Tensor) else sht.dev_map(m)
     n_inv_filt.apply_map(tmap)
     lmax = len(n_inv_filt.b_transf) - 1
     plan = sht.get_plan(n_inv_filt.nside, lmax)

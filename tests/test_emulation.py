@@ -26,7 +26,7 @@ def emul():
 
 
 @pytest.mark.parametrize("nbatch", [1, 2, 4])
-@pytest.mark.parametrize("nside,lmax", [(4, 11), (8, 23), (16, 40), (32, 70), (64, 100)])
+@pytest.mark.parametrize("nside,lmax", [(4, 11), (8, 23), (16, 40), (32, 70), (64, 100), (16, 16), (32, 20), (64, 64), (64, 63)])
 def test_ring_fft_stage(emul, oracle_sht, nside, lmax, nbatch):
     rng = np.random.default_rng(nside)
     nring, pitch = 4 * nside - 1, (lmax + 2) & ~1

@@ -11,7 +11,7 @@ from helpers import alm_dot, alm_size, rand_alm, rel_l2
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
 
-CASES = [(4, 11), (8, 23), (16, 40), (32, 95), (64, 128), (128, 300)]
+CASES = [(4, 11), (8, 23), (16, 40), (32, 95), (64, 128), (128, 300), (64, 64), (128, 100)]   # last two: lmax <= nside (no-alias ring path)
 
 
 @pytest.fixture(scope="module")
