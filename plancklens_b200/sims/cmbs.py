@@ -41,10 +41,20 @@ class sims_cmb_unl:
         ret['phas'] = self.lib_pha.hashdict()
         return ret
 
+    def _phases(self, idx):
+        """unit phases of all fields of simulation idx; the last simulation drawn is kept (T, E and B of one sky are
+        asked for one after the other, and each needs every phase field)"""
+        if getattr(self, '_pha_idx', None) != idx:
+            self._pha = [self.lib_pha.get_sim(idx, idf=i) for i in range(len(self.fields))]
+            self._pha_idx = idx
+        return self._pha
+
     def _get_sim_alm(self, idx, idf):
-        ret = hp.almxfl(self.lib_pha.get_sim(idx, idf=0), self.rmat[:, idf, 0])
+        pha = self._phases(idx)
+        ret = hp.almxfl(pha[0], self.rmat[:, idf, 0])
         for i in range(1, len(self.fields)):
-            ret += hp.almxfl(self.lib_pha.get_sim(idx, idf=i), self.rmat[:, idf, i])
+            if np.any(self.rmat[:, idf, i]):
+                ret += hp.almxfl(pha[i], self.rmat[:, idf, i])
         return ret
 
     def get_sim_alm(self, idx, field):

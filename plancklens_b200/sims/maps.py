@@ -29,7 +29,7 @@ class cmb_maps(object):
         if self.device_maps:
             from .. import sht
             t = sht.get_plan(self.nside, hp.Alm.getlmax(tlm.size)).alm2map(sht.dev_alm(tlm))
-            return sht.map_axpy(t, sht.dev_map(self.get_sim_tnoise(idx)), 1.0)
+            return self._add_noise_dev(t, idx, 't')
         return hp.alm2map(tlm, self.nside) + self.get_sim_tnoise(idx)
 
     def get_sim_pmap(self, idx):
@@ -38,11 +38,15 @@ class cmb_maps(object):
         if self.device_maps:
             from .. import sht
             Q, U = sht.get_plan(self.nside, hp.Alm.getlmax(elm.size)).alm2map_spin(sht.dev_alm(elm), sht.dev_alm(blm), 2)
-            sht.map_axpy(Q, sht.dev_map(self.get_sim_qnoise(idx)), 1.0)
-            sht.map_axpy(U, sht.dev_map(self.get_sim_unoise(idx)), 1.0)
-            return Q, U
+            return self._add_noise_dev(Q, idx, 'q'), self._add_noise_dev(U, idx, 'u')
         Q, U = hp.alm2map_spin([elm, blm], self.nside, 2, hp.Alm.getlmax(elm.size))
         return Q + self.get_sim_qnoise(idx), U + self.get_sim_unoise(idx)
+
+    def _add_noise_dev(self, m, idx, field):
+        """m += noise map of `field` in ('t', 'q', 'u') on the device"""
+        from .. import sht
+        noise = {'t': self.get_sim_tnoise, 'q': self.get_sim_qnoise, 'u': self.get_sim_unoise}[field](idx)
+        return sht.map_axpy(m, sht.dev_map(noise), 1.0)
 
     def get_sim_tnoise(self, idx):
         assert 0, 'subclass this'
@@ -82,6 +86,12 @@ class cmb_maps_nlev(cmb_maps):
 
     def _vamin(self):
         return np.sqrt(hp.nside2pixarea(self.nside, degrees=True)) * 60
+
+    def _add_noise_dev(self, m, idx, field):
+        # unit-variance phases go to the device as drawn; the nlev / vamin scaling is the axpy coefficient
+        from .. import sht
+        idf, nlev = {'t': (0, self.nlev_t), 'q': (1, self.nlev_p), 'u': (2, self.nlev_p)}[field]
+        return sht.map_axpy(m, sht.dev_map(self.pix_lib_phas.get_sim(idx, idf=idf)), nlev / self._vamin())
 
     def get_sim_tnoise(self, idx):
         return self.nlev_t / self._vamin() * self.pix_lib_phas.get_sim(idx, idf=0)
