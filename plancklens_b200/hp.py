@@ -201,28 +201,87 @@ def ud_grade(map_in, nside_out, pess=False, order_in='RING', order_out=None, pow
 
 
 # ------------------------------------------------------------------ file I/O (.npy container)
-def write_alm(filename, alms, overwrite=True, **kw):
+def _is_fits_name(filename):
+    """FITS for `.fits` names (what a stock plancklens / healpy expects to find); PLK_CACHE_FORMAT=npy keeps the
+    `.npy` containers of the throughput runs (60 x faster to write for an lmax-2048 alm)."""
+    import os
+    if os.environ.get('PLK_CACHE_FORMAT', 'fits').lower() == 'npy':
+        return False
+    f = str(filename)
+    return f.endswith('.fits') or f.endswith('.fits.gz') or f.endswith('.fit')
+
+
+def _is_npy(filename):
+    import gzip
+    op = gzip.open if str(filename).endswith('.gz') else open
+    try:
+        with op(filename, 'rb') as f:
+            return f.read(6) == b'\x93NUMPY'
+    except OSError:
+        with open(filename, 'rb') as f:          # '.gz' name holding a plain .npy (caches of earlier versions)
+            return f.read(6) == b'\x93NUMPY'
+
+
+def write_alm(filename, alms, out_dtype=None, lmax=-1, mmax=-1, mmax_in=-1, overwrite=True, **kw):
+    """healpy.write_alm: FITS binary table (index, real, imag) for `.fits` names -- the files a stock plancklens /
+    healpy reads (`fitsio.py`) -- a `.npy` container otherwise."""
+    import os
+    if not overwrite and os.path.exists(filename):
+        raise OSError('File exists: %s' % filename)
+    if _is_fits_name(filename):
+        from . import fitsio
+        return fitsio.write_alm(filename, alms, lmax=lmax, mmax=mmax, out_dtype=np.float64 if out_dtype is None else out_dtype)
     with open(filename, 'wb') as f:
         np.save(f, np.asarray(alms))
 
 
 def read_alm(filename, hdu=1, return_mmax=False):
-    with open(filename, 'rb') as f:
-        a = np.load(f)
-    return (a, Alm.getlmax(a.size)) if return_mmax else a
+    if _is_npy(filename):
+        with open(filename, 'rb') as f:
+            a = np.load(f)
+        return (a, Alm.getlmax(a.size)) if return_mmax else a
+    from . import fitsio
+    return fitsio.read_alm(filename, hdu=hdu, return_mmax=return_mmax)
 
 
-def write_map(filename, m, overwrite=True, **kw):
+def write_map(filename, m, nest=False, dtype=None, coord=None, overwrite=True, **kw):
+    """healpy.write_map: FITS binary table (1024 pixels per row) for `.fits` / `.fits.gz` names, `.npy` otherwise."""
+    import os
+    if not overwrite and os.path.exists(filename):
+        raise OSError('File exists: %s' % filename)
+    if _is_fits_name(filename):
+        from . import fitsio
+        return fitsio.write_map(filename, m, nest=nest, dtype=np.float64 if dtype is None else dtype, coord=coord)
     with open(filename, 'wb') as f:
         np.save(f, np.asarray(m))
 
 
-def read_map(filename, field=0, **kw):
-    with open(filename, 'rb') as f:
-        m = np.load(f)
-    if m.ndim == 2:
-        return m[field] if np.isscalar(field) else m[list(field)]
-    return m
+def read_map(filename, field=0, nest=False, hdu=1, **kw):
+    """healpy.read_map: returns RING-ordered map(s) unless nest=True (or nest=None: as stored)."""
+    if _is_npy(filename):
+        with open(filename, 'rb') as f:
+            m = np.load(f)
+        if m.ndim == 2:
+            return m[field] if np.isscalar(field) else m[list(field)]
+        return m
+    from . import fitsio
+    m, hdr = fitsio.read_map(filename, field=field, hdu=hdu, return_header=True)
+    stored_nest = str(hdr.get('ORDERING', 'RING')).strip().upper().startswith('NEST')
+    if nest is None or stored_nest == bool(nest):
+        return m
+    maps = [m] if np.isscalar(field) else m
+    nside = npix2nside(maps[0].size)
+    r2n = ring2nest(nside, np.arange(maps[0].size))
+    if stored_nest:                       # NEST on disk -> RING
+        maps = [x[r2n] for x in maps]
+    else:                                 # RING on disk -> NEST
+        out = []
+        for x in maps:
+            y = np.empty_like(x)
+            y[r2n] = x
+            out.append(y)
+        maps = out
+    return maps[0] if np.isscalar(field) else maps
 
 
 # ------------------------------------------------------------------ transforms (GPU)

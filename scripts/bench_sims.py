@@ -38,6 +38,7 @@ rank, size = mpi.init('nccl') if int(os.environ.get('WORLD_SIZE', 1)) > 1 else (
 if size == 1:
     torch.cuda.set_device(0)
 
+os.environ.setdefault('PLK_CACHE_FORMAT', 'npy')     # .npy caches under the reference's file names (FITS: +0.15 s per alm)
 os.environ['PLENS'] = os.path.join('/tmp', 'plk_cfg4_%s_%d' % (os.environ.get('MASTER_PORT', 'single'), os.getppid() if size > 1 else os.getpid()))
 os.environ.update({'PLK_NSIDE': str(a.nside), 'PLK_LMAX_IVF': str(a.lmax), 'PLK_LMAX_QLM': str(a.lmax), 'PLK_NSIMS': '320'})
 spec = importlib.util.spec_from_file_location('anisofilt_example', os.path.join(ROOT, 'params', 'anisofilt_example.py'))
