@@ -132,3 +132,42 @@ class idx_ivfs:
     def get_sim_tmliklm(self, idx): return self.hp.almxfl(self.get_sim_tlm(idx), self.q['cls']['tt'])
     def get_sim_emliklm(self, idx): return self.hp.almxfl(self.get_sim_elm(idx), self.q['cls']['ee'])
     def get_sim_bmliklm(self, idx): return self.hp.almxfl(self.get_sim_blm(idx), self.q['cls']['bb'])
+
+
+def resp_case(lmax=60, lmax_qlm=70):
+    """Spectra, filters and filtered-map spectra for the response / N0 tests (toy spectra, 30' beam, lmin 10):
+    separately filtered, jointly filtered, and a joint set with TB / EB correlations (complex spin matrices)."""
+    cls = toy_cls(lmax)
+    l = np.arange(lmax + 1, dtype=float)
+    transf = np.exp(-0.5 * l * (l + 1) * (0.01 ** 2))
+    nlt, nlp = 2e-3 / transf ** 2, 4e-3 / transf ** 2
+
+    def cli(c):
+        r = np.zeros_like(c)
+        r[c != 0] = 1. / c[c != 0]
+        return r
+    fal_sep = {'tt': cli(cls['tt'] + nlt), 'ee': cli(cls['ee'] + nlp), 'bb': cli(cls['bb'] + nlp)}
+    cls_ivfs_sep = {'tt': fal_sep['tt'].copy(), 'ee': fal_sep['ee'].copy(), 'bb': fal_sep['bb'].copy(),
+                    'te': cls['te'] * fal_sep['tt'] * fal_sep['ee']}
+    cls_dat = {'tt': cls['tt'] + nlt, 'ee': cls['ee'] + nlp, 'bb': cls['bb'] + nlp, 'te': cls['te'].copy()}
+
+    def inv3(d):
+        m = np.zeros((lmax + 1, 3, 3))
+        for k, (i, j) in zip(['tt', 'ee', 'bb', 'te', 'tb', 'eb'], [[0, 0], [1, 1], [2, 2], [0, 1], [0, 2], [1, 2]]):
+            if k in d:
+                m[:, i, j] = m[:, j, i] = d[k]
+        mi = np.linalg.pinv(m)
+        return {k: mi[:, i, j].copy() for k, (i, j) in zip(['tt', 'ee', 'bb', 'te', 'tb', 'eb'],
+                                                          [[0, 0], [1, 1], [2, 2], [0, 1], [0, 2], [1, 2]]) if np.any(mi[:, i, j])}
+    fal_jt = inv3(cls_dat)
+    dat_tb = dict(cls_dat)
+    dat_tb['tb'] = 0.1 * np.sqrt(cls['tt'] * cls['bb'])
+    dat_tb['eb'] = 0.05 * np.sqrt(cls['ee'] * cls['bb'])
+    fal_tb = inv3(dat_tb)
+    out = {'lmax': lmax, 'lmax_qlm': lmax_qlm, 'cls_weight': cls, 'cls_len': cls, 'cls_dat': cls_dat,
+           'fal_sep': fal_sep, 'fal_jt': fal_jt, 'fal_tb': fal_tb,
+           'cls_ivfs_sep': cls_ivfs_sep, 'cls_ivfs_jt': inv3(cls_dat), 'cls_ivfs_tb': inv3(dat_tb)}
+    for d in (fal_sep, fal_jt, fal_tb, cls_ivfs_sep, out['cls_ivfs_jt'], out['cls_ivfs_tb']):
+        for v in d.values():
+            v[:10] = 0.
+    return out

@@ -108,3 +108,72 @@ def test_w():
         assert np.allclose(NC[2:], RC[2:], rtol=1e-6), ksource
         assert np.all(NCG == 0.) and np.all(NGC == 0.)
         assert np.all(RCG == 0.) and np.all(RGC == 0.)
+
+
+# ------------------------------------------------------------------------------------------------ responses and N0
+RESP_KEYS = [('ptt', 'p', 'fal_sep'), ('p_p', 'p', 'fal_sep'), ('p', 'p', 'fal_jt'), ('x', 'x', 'fal_jt'),
+             ('ftt', 'f', 'fal_sep'), ('ptt', 'f', 'fal_sep'), ('p', 'p', 'fal_tb'), ('ptt_bh_f', 'p', 'fal_sep')]
+NHL_KEYS = [('ptt', 'ptt', 'cls_ivfs_sep'), ('p_p', 'p_p', 'cls_ivfs_sep'), ('p', 'p', 'cls_ivfs_jt'),
+            ('ptt', 'p_p', 'cls_ivfs_sep'), ('p', 'p', 'cls_ivfs_tb'), ('x', 'p', 'cls_ivfs_tb')]
+
+
+def _resp_gold():
+    return np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_resp.npz'))
+
+
+def _close(a, b, tol):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b)) <= tol * max(np.max(np.abs(b)), 1e-300)
+
+
+def test_host_helpers_match_reference():
+    """utils_spin.get_spin_matrix / spin_cls, utils.cl_inverse and qresp.get_qes against the unmodified reference
+    (tests/golden/make_golden_resp.py), including TB / EB spectra (complex spin matrices)."""
+    import golden_inputs as gi
+    from plancklens_b200 import qresp, utils
+    from plancklens_b200 import utils_spin as us
+    g, r = _resp_gold(), gi.resp_case()
+    for s1, s2 in [(0, 0), (0, 2), (2, 0), (2, 2), (2, -2), (-2, 2), (-2, 0), (0, -2)]:
+        assert _close(us.get_spin_matrix(s1, s2, r['fal_tb']), g['spinmat_%d_%d' % (s1, s2)], 1e-15)
+        assert _close(us.spin_cls(s1, s2, r['cls_ivfs_tb']), g['spincls_%d_%d' % (s1, s2)], 1e-15)
+    inv = utils.cl_inverse(r['cls_dat'])
+    assert set('clinv_' + k for k in inv) == set(k for k in g.files if k.startswith('clinv_'))
+    for k, v in inv.items():
+        assert _close(v, g['clinv_' + k], 1e-13)
+    for key in ['ptt', 'p_p', 'p', 'x', 'ftt', 'pee', 'p_te', 'a_p']:
+        qes = qresp.get_qes(key, r['lmax'], r['cls_weight'])
+        assert len(qes) == int(g['qes_%s_n' % key][0]), key
+        for i, q in enumerate(qes):
+            assert [q.leg_a.spin_in, q.leg_a.spin_ou, q.leg_b.spin_in, q.leg_b.spin_ou] == list(g['qes_%s_%d_spins' % (key, i)])
+            assert _close(q.leg_a.cl, g['qes_%s_%d_cla' % (key, i)], 1e-15) and _close(q.leg_b.cl, g['qes_%s_%d_clb' % (key, i)], 1e-15)
+            assert _close(q.cL(np.arange(r['lmax_qlm'] + 1)), g['qes_%s_%d_cL' % (key, i)], 1e-15)
+
+
+def _check_resp_and_nhl(tol):
+    import golden_inputs as gi
+    from plancklens_b200 import nhl, qresp
+    g, r = _resp_gold(), gi.resp_case()
+    for key, src, fal in RESP_KEYS:
+        R = qresp.get_response(key, r['lmax'], src, r['cls_weight'], r['cls_len'], r[fal], lmax_qlm=r['lmax_qlm'])
+        ref = g['resp_%s_%s_%s' % (key, src, fal)]
+        scale = np.max(np.abs(ref))
+        assert np.max(np.abs(np.array(R) - ref)) <= tol * scale, (key, src, fal)
+    for k1, k2, ivf in NHL_KEYS:
+        N = nhl.get_nhl(k1, k2, r['cls_weight'], r[ivf], r['lmax'], r['lmax'], lmax_out=r['lmax_qlm'])
+        ref = g['nhl_%s_%s_%s' % (k1, k2, ivf)]
+        assert np.max(np.abs(np.array(N) - ref)) <= tol * np.max(np.abs(ref)), (k1, k2, ivf)
+
+
+def test_response_and_n0_assembly_matches_reference_on_cpu(monkeypatch):
+    """qresp.get_response / nhl.get_nhl host logic with the Wigner seam served by the CPU oracle on both sides: the
+    port of the assembly code is checked without a GPU."""
+    from oracle import ref_wigner
+    from plancklens_b200 import utils_spin as us
+    monkeypatch.setattr(us, 'wignerc', ref_wigner.wignerc)
+    _check_resp_and_nhl(1e-12)
+
+
+@pytest.mark.gpu
+def test_response_and_n0_match_reference_on_gpu():
+    """the same numbers with the Wigner transforms on the GPU"""
+    _check_resp_and_nhl(1e-9)
