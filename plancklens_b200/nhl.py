@@ -2,12 +2,17 @@
 
 `get_nhl` is a sum of Wigner-d correlation functions of the estimator weights and the filtered-map spectra; the
 transforms run on the GPU (`utils_spin.wignerc` -> libplk_b200) where the reference calls its Fortran extension.
-The simulation-based `nhl_lib_simple` (sqlite cache around the same function) is not mirrored.
+`nhl_lib_simple` evaluates it on the spectra of the filtered simulations and caches the result in the reference's
+sqlite layout (`helpers/sql.py`).
 """
+import os
+import pickle as pk
+
 import numpy as np
 
-from . import qresp, utils
+from . import hp, qresp, utils
 from . import utils_spin as uspin
+from .helpers import mpi, sql
 
 
 def get_nhl(qe_key1, qe_key2, cls_weights, cls_ivfs, lmax_ivf1, lmax_ivf2, lmax_out=None, lmax_ivf12=None,
@@ -70,3 +75,84 @@ def _get_nhl(qes1, qes2, cls_ivfs, lmax_out, cls_ivfs_bb=None, cls_ivfs_ab=None,
             GC_N0 -= 0.5 * R_sutv.imag + 0.5 * sg * R_msmtuv.imag
             CG_N0 += 0.5 * R_sutv.imag - 0.5 * sg * R_msmtuv.imag
     return GG_N0, CC_N0, GC_N0, CG_N0
+
+
+class nhl_lib_simple:
+    """Semi-analytical unnormalised N0 library for four identical legs and the 1 / fsky spectrum estimator
+    (reference: nhl.py:98-189)."""
+
+    def __init__(self, lib_dir, ivfs, cls_weight, lmax_qlm, resplib=None):
+        self.lmax_qlm = lmax_qlm
+        self.cls_weight = cls_weight
+        self.ivfs = ivfs
+        fn_hash = os.path.join(lib_dir, 'nhl_hash.pk')
+        if mpi.rank == 0:
+            if not os.path.exists(lib_dir):
+                os.makedirs(lib_dir)
+            if not os.path.exists(fn_hash):
+                with open(fn_hash, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+        mpi.barrier()
+        with open(fn_hash, 'rb') as f:
+            utils.hash_check(pk.load(f), self.hashdict(), fn=fn_hash)
+        self.lib_dir = lib_dir
+        self.npdb = sql.npdb(os.path.join(lib_dir, 'npdb.db'))
+        self.fsky = np.mean(self.ivfs.get_fmask())
+        self.resplib = resplib
+
+    def hashdict(self):
+        ret = {k: utils.clhash(self.cls_weight[k]) for k in self.cls_weight.keys()}
+        ret['ivfs'] = self.ivfs.hashdict()
+        ret['lmax_qlm'] = self.lmax_qlm
+        return ret
+
+    def _get_qe_derived(self, k):
+        if '_bh_' in k:
+            kQE, ksource = k.split('_bh_')
+            assert len(ksource) == 1
+            wL = self.resplib.get_response(kQE, ksource) * utils.cli(self.resplib.get_response(ksource + kQE[1:], ksource))
+            return [(kQE, 1.), (ksource + kQE[1:], -wL)]
+        return [(k, 1.)]
+
+    def get_sim_nhl(self, idx, k1, k2, recache=False):
+        """N0 of the (k1, k2) spectrum from the empirical spectra of the filtered maps of simulation idx (-1: data)."""
+        assert idx == -1 or idx >= 0, idx
+        ret = np.zeros(self.lmax_qlm + 1)
+        for k1_, w1 in self._get_qe_derived(k1):
+            for k2_, w2 in self._get_qe_derived(k2):
+                s1, GC1, s1ins, ksp1 = qresp.qe_spin_data(k1_)
+                s2, GC2, s2ins, ksp2 = qresp.qe_spin_data(k2_)
+                base = 'anhl_qe_' + ksp1 + k1_[1:] + '_qe_' + ksp2 + k2_[1:]
+                suf = ('sim%04d' % idx) * (int(idx) >= 0) + 'dat' * (idx == -1)
+                fn = base + GC1 + GC2
+                if self.npdb.get(fn + suf) is None or recache:
+                    assert s1 >= 0 and s2 >= 0, (s1, s2)
+                    cls_ivfs, lmax_ivf = self._get_cls(idx, np.unique(np.concatenate([s1ins, s2ins])))
+                    GG, CC, GC, CG = get_nhl(k1_, k2_, self.cls_weight, cls_ivfs, lmax_ivf, lmax_ivf, lmax_out=self.lmax_qlm)
+                    fns = [('G', 'G', GG)] + [('C', 'G', CG)] * (s1 > 0) + [('G', 'C', GC)] * (s2 > 0) \
+                        + [('C', 'C', CC)] * (s1 > 0) * (s2 > 0)
+                    if recache and self.npdb.get(fn + suf) is not None:
+                        for a, b, _ in fns:
+                            self.npdb.remove(base + a + b + suf)
+                    for a, b, N0 in fns:
+                        self.npdb.add(base + a + b + suf, N0)
+                ret += w1 * w2 * self.npdb.get(fn + suf)
+        return ret
+
+    def _get_cls(self, idx, spins):
+        """empirical spectra of the filtered alms / fsky, and the length the reference passes on as lmax (nhl.py:175-189)"""
+        assert np.all(spins >= 0), spins
+        ret = {}
+        iv = self.ivfs
+        if 0 in spins:
+            ret['tt'] = hp.alm2cl(iv.get_sim_tlm(idx)) / self.fsky
+        if 2 in spins:
+            ret['ee'] = hp.alm2cl(iv.get_sim_elm(idx)) / self.fsky
+            ret['bb'] = hp.alm2cl(iv.get_sim_blm(idx)) / self.fsky
+            ret['eb'] = hp.alm2cl(iv.get_sim_elm(idx), alms2=iv.get_sim_blm(idx)) / self.fsky
+        if 0 in spins and 2 in spins:
+            ret['te'] = hp.alm2cl(iv.get_sim_tlm(idx), alms2=iv.get_sim_elm(idx)) / self.fsky
+            ret['tb'] = hp.alm2cl(iv.get_sim_tlm(idx), alms2=iv.get_sim_blm(idx)) / self.fsky
+        lmaxs = [len(cl) for cl in ret.values()]
+        assert len(np.unique(lmaxs)) == 1, lmaxs
+        return ret, lmaxs[0]

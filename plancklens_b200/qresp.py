@@ -3,13 +3,17 @@
 `get_qes` and the response-leg helpers build the list of `utils_qe.qe` terms consumed by `utils_qe.qe_eval` (the
 SHT hot path); `get_response` evaluates the estimator normalisations with the Wigner small-d transforms of
 libplk_b200 (`utils_spin.wignerc`) where the reference calls its Fortran extension.
-`resp_lib_simple` (sqlite cache of the same numbers) is not mirrored.
+`resp_lib_simple` caches the same numbers in the reference's sqlite layout (`helpers/sql.py`).
 """
 import numpy as np
+
+import os
+import pickle as pk
 
 from . import utils as ut
 from . import utils_qe as uqe
 from . import utils_spin as uspin
+from .helpers import mpi, sql
 
 
 def _clinv(cl):
@@ -157,3 +161,83 @@ def _get_response(qes, source, cls_cmb, fal_leg1, lmax_qlm, fal_leg2=None):
                 RGC += prefac * (-Rpr_st.imag + Rmr_st.imag * (-1) ** rW_st)
                 RCG += prefac * (Rpr_st.imag + Rmr_st.imag * (-1) ** rW_st)
     return RGG, RCC, RGC, RCG
+
+
+def qe_spin_data(qe_key):
+    """(spin of the estimator output, 'G' or 'C', unique input spins >= 0, spin-1 key) (reference: qresp.py:164-179)."""
+    if qe_key in ['ntt']:
+        return 0, 'G', [0], 'n'
+    qes = get_qes(qe_key, 10, {k: np.ones(11 + 4, dtype=float) for k in ['tt', 'te', 'ee', 'bb']})
+    spins_out = [qe.leg_a.spin_ou + qe.leg_b.spin_ou for qe in qes]
+    spins_in = np.unique(np.abs([qe.leg_a.spin_in for qe in qes] + [qe.leg_b.spin_in for qe in qes]))
+    assert len(np.unique(spins_out)) == 1, spins_out
+    assert spins_out[0] >= 0, spins_out[0]
+    if spins_out[0] > 0:
+        assert qe_key[0] in ['x', 'p'], 'non-zero spin anisotropy ' + qe_key + ' not implemented ?'
+    return spins_out[0], 'C' if qe_key[0] == 'x' else 'G', spins_in, 'p' if qe_key[0] == 'x' else qe_key[0]
+
+
+class resp_lib_simple:
+    """Cached QE responses (reference: qresp.py:182-266): wraps `get_response`, results in `npdb.db`."""
+
+    def __init__(self, lib_dir, lmax_ivf, cls_weight, cls_cmb, fal, lmax_qlm, transf=None):
+        self.lmax_qe = lmax_ivf
+        self.lmax_qlm = lmax_qlm
+        self.cls_weight = cls_weight
+        self.cls_cmb = cls_cmb
+        self.fal = fal
+        self.transf = transf
+        self.lib_dir = lib_dir
+        fn_hash = os.path.join(lib_dir, 'resp_hash.pk')
+        if mpi.rank == 0:
+            if not os.path.exists(lib_dir):
+                os.makedirs(lib_dir)
+            if not os.path.exists(fn_hash):
+                with open(fn_hash, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+        mpi.barrier()
+        with open(fn_hash, 'rb') as f:
+            ut.hash_check(pk.load(f), self.hashdict(), fn=fn_hash)
+        self.npdb = sql.npdb(os.path.join(lib_dir, 'npdb.db'))
+
+    def hashdict(self):
+        ret = {'lmaxqe': self.lmax_qe, 'lmax_qlm': self.lmax_qlm}
+        for k in self.cls_weight.keys():
+            ret['clsweight ' + k] = ut.clhash(self.cls_weight[k])
+        for k in self.cls_cmb.keys():
+            ret['clscmb ' + k] = ut.clhash(self.cls_cmb[k])
+        for k in self.fal.keys():
+            ret['fal' + k] = ut.clhash(self.fal[k])
+        return ret
+
+    def get_response(self, k, ksource, recache=False):
+        """Response of estimator key k to anisotropy source ksource (GG part for gradient keys, CC for curl keys)."""
+        if '_bh_' in k:      # bias-hardened estimator
+            kQE, bhksource = k.split('_bh_')
+            assert len(ksource) == 1, (kQE, ksource)
+            wL = self.get_response(kQE, bhksource, recache=recache)
+            wL = wL * ut.cli(self.get_response(bhksource + kQE[1:], bhksource, recache=recache))
+            ret = np.copy(self.get_response(kQE, ksource, recache=recache))
+            ret -= wL * self.get_response(bhksource + kQE[1:], ksource, recache=recache)
+            return ret
+        if k in ['xmtt', 'pmtt']:
+            return self.get_response(k[0], ksource, recache=recache) - self.get_response(k[0] + 'tt', ksource, recache=recache)
+        s, GorC, sins, ksp = qe_spin_data(k)
+        assert s >= 0, s
+        if s == 0:
+            assert GorC == 'G', (s, GorC)
+        base = 'qe_' + ksp + k[1:] + '_source_%s' % ksource
+        fn = base + '_' + GorC + GorC
+        if self.npdb.get(fn) is None or recache:
+            GG, CC, GC, CG = get_response(k, self.lmax_qe, ksource, self.cls_weight, self.cls_cmb, self.fal,
+                                          lmax_qlm=self.lmax_qlm, transf=self.transf)
+            if np.any(CG) or np.any(GC):
+                print("Warning: C-G or G-C responses non-zero but not returned")
+            if recache and self.npdb.get(fn) is not None:
+                self.npdb.remove(base + '_GG')
+                if s > 0:
+                    self.npdb.remove(base + '_CC')
+            self.npdb.add(base + '_GG', GG)
+            if s > 0:
+                self.npdb.add(base + '_CC', CC)
+        return self.npdb.get(fn)

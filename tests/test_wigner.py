@@ -177,3 +177,41 @@ def test_response_and_n0_assembly_matches_reference_on_cpu(monkeypatch):
 def test_response_and_n0_match_reference_on_gpu():
     """the same numbers with the Wigner transforms on the GPU"""
     _check_resp_and_nhl(1e-9)
+
+
+def test_resp_and_nhl_libraries_cache_in_sqlite(tmp_path, monkeypatch):
+    """resp_lib_simple / nhl_lib_simple: same numbers as the bare functions, cached in the reference's npdb layout
+    (Wigner seam served by the oracle: runs on the CPU)."""
+    import golden_inputs as gi
+    from oracle import ref_wigner
+    from plancklens_b200 import hp, nhl, qresp
+    from plancklens_b200 import utils_spin as us
+    calls = []
+
+    def counted(*a, **k):
+        calls.append(1)
+        return ref_wigner.wignerc(*a, **k)
+    monkeypatch.setattr(us, 'wignerc', counted)
+    r = gi.resp_case()
+    lib = qresp.resp_lib_simple(str(tmp_path / 'resp'), r['lmax'], r['cls_weight'], r['cls_len'], r['fal_sep'], r['lmax_qlm'])
+    RG = lib.get_response('ptt', 'p')
+    ref = qresp.get_response('ptt', r['lmax'], 'p', r['cls_weight'], r['cls_len'], r['fal_sep'], lmax_qlm=r['lmax_qlm'])[0]
+    assert np.array_equal(RG, ref)
+    n = len(calls)
+    assert np.array_equal(lib.get_response('ptt', 'p'), ref) and len(calls) == n          # second call served by sqlite
+    xc = lib.get_response('x_p', 'x')
+    assert np.array_equal(xc, qresp.get_response('x_p', r['lmax'], 'x', r['cls_weight'], r['cls_len'], r['fal_sep'],
+                                                 lmax_qlm=r['lmax_qlm'])[1])
+    assert qresp.qe_spin_data('ptt')[:2] == (1, 'G') and qresp.qe_spin_data('x_p')[:2] == (1, 'C')
+    assert qresp.qe_spin_data('ftt')[:2] == (0, 'G')
+    # N0 from the empirical spectra of an in-memory filtering library
+    q = gi.qe_case()
+    iv = gi.idx_ivfs(q, hp)
+    cls_w = gi.toy_cls(80)      # weights reach beyond lmax_ivf, as the CAMB tables the reference is used with
+    nl = nhl.nhl_lib_simple(str(tmp_path / 'nhl'), iv, cls_w, 40)
+    n0 = nl.get_sim_nhl(0, 'ptt', 'ptt')
+    cls_emp = {'tt': hp.alm2cl(iv.get_sim_tlm(0))}
+    ref = nhl.get_nhl('ptt', 'ptt', cls_w, cls_emp, len(cls_emp['tt']), len(cls_emp['tt']), lmax_out=40)[0]
+    assert np.array_equal(n0, ref) and n0.shape == (41,) and np.all(n0[2:] > 0)
+    n = len(calls)
+    assert np.array_equal(nl.get_sim_nhl(0, 'ptt', 'ptt'), ref) and len(calls) == n
