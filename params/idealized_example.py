@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 import plancklens_b200
-from plancklens_b200 import hp, qest, utils
+from plancklens_b200 import hp, nhl, qecl, qest, qresp, utils
 from plancklens_b200.filt import filt_simple, filt_util
 from plancklens_b200.sims import cmbs, maps, phas, utils as maps_utils
 
@@ -81,3 +81,21 @@ qlms_ss = qest.library_sepTP(os.path.join(TEMP, 'qlms_ss'), ivfs, ivfs_s, cl_len
 
 mc_sims_bias = np.arange(min(60, nsims))  #: The mean-field will be calculated from these simulations.
 mc_sims_var = np.arange(min(60, nsims), nsims)  #: The covariance matrix will be calculated from these simulations
+
+# ---- QE spectra libraries: power spectra of the QE maps after mean-field subtraction (only qcls_dd needs one)
+mc_sims_mf_dd = mc_sims_bias
+mc_sims_mf_ds = np.array([], dtype=int)
+mc_sims_mf_ss = np.array([], dtype=int)
+
+qcls_dd = qecl.library(os.path.join(TEMP, 'qcls_dd'), qlms_dd, qlms_dd, mc_sims_mf_dd)
+qcls_ds = qecl.library(os.path.join(TEMP, 'qcls_ds'), qlms_ds, qlms_ds, mc_sims_mf_ds)
+qcls_ss = qecl.library(os.path.join(TEMP, 'qcls_ss'), qlms_ss, qlms_ss, mc_sims_mf_ss)
+
+# ---- semi-analytical Gaussian lensing bias library
+nhl_dd = nhl.nhl_lib_simple(os.path.join(TEMP, 'nhl_dd'), ivfs, cl_weight, lmax_qlm)
+
+# ---- N1 lensing bias library: Fortran extension of the reference (n1.library_n1), not part of this package
+
+# ---- QE response calculation library
+qresp_dd = qresp.resp_lib_simple(os.path.join(TEMP, 'qresp'), lmax_ivf, cl_weight, cl_len,
+                                 {'t': ivfs.get_ftl(), 'e': ivfs.get_fel(), 'b': ivfs.get_fbl()}, lmax_qlm)

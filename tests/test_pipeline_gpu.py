@@ -59,6 +59,17 @@ def test_idealized_example_param_file(oracle_sht):
         a = ref_qe.qe('p_p', t1, e1, b1, cls, par.nside, par.lmax_qlm, tbar2=td, ebar2=ed, bbar2=bd)
         b = ref_qe.qe('p_p', td, ed, bd, cls, par.nside, par.lmax_qlm, tbar2=t1, ebar2=e1, bbar2=b1)
         assert rel_l2(Gds, 0.5 * (a[0] + b[0])) < 1e-10
+        # downstream libraries of the parameter file: responses (GPU Wigner transforms), semi-analytical N0 from the
+        # filtered maps' spectra, mean-field subtracted QE spectrum of the "data" -- for a Gaussian (unlensed) sky the
+        # raw spectrum scatters around N0
+        R = par.qresp_dd.get_response('ptt', 'p')
+        n0 = par.nhl_dd.get_sim_nhl(-1, 'ptt', 'ptt')
+        qcl = par.qcls_dd.get_sim_qcl('ptt', -1)
+        assert R.shape == n0.shape == qcl.shape == (par.lmax_qlm + 1,)
+        assert np.all(R[2:100] > 0) and np.all(n0[2:100] > 0) and np.all(qcl[2:] >= 0)
+        band = slice(8, 64)
+        assert 0.5 < np.sum(qcl[band]) / np.sum(n0[band]) < 2.0
+        assert 0.5 < np.sum(n0[band] / R[band] ** 2) / np.sum(1.0 / R[band]) < 2.0     # filters are optimal: N0 ~ R
         # cached on disk under the reference's file names
         assert os.path.exists(os.path.join(tmp, 'temp', 'idealized_example', 'qlms_dd', 'sim_p_0000.fits'))
         assert os.path.exists(os.path.join(tmp, 'temp', 'idealized_example', 'ivfs', 'sim_0000_tlm.fits'))
