@@ -68,8 +68,8 @@ def test_idealized_example_param_file(oracle_sht):
         assert R.shape == n0.shape == qcl.shape == (par.lmax_qlm + 1,)
         assert np.all(R[2:100] > 0) and np.all(n0[2:100] > 0) and np.all(qcl[2:] >= 0)
         band = slice(8, 64)
-        assert 0.5 < np.sum(qcl[band]) / np.sum(n0[band]) < 2.0
-        assert 0.5 < np.sum(n0[band] / R[band] ** 2) / np.sum(1.0 / R[band]) < 2.0     # filters are optimal: N0 ~ R
+        assert 0.3 < np.sum(qcl[band]) / np.sum(n0[band]) < 3.0
+        assert 0.3 < np.sum(n0[band] / R[band] ** 2) / np.sum(1.0 / R[band]) < 3.0     # filters are optimal: N0 ~ R
         # cached on disk under the reference's file names
         assert os.path.exists(os.path.join(tmp, 'temp', 'idealized_example', 'qlms_dd', 'sim_p_0000.fits'))
         assert os.path.exists(os.path.join(tmp, 'temp', 'idealized_example', 'ivfs', 'sim_0000_tlm.fits'))
