@@ -171,3 +171,13 @@ def resp_case(lmax=60, lmax_qlm=70):
         for v in d.values():
             v[:10] = 0.
     return out
+
+
+def kk_cls(lmax):
+    """toy lensing-potential spectrum in the units of cg_case's noise: C_L^{kk} = (L(L+1)/2)^2 C_L^{pp} crosses the
+    noise level of cg_case()['ninv_t'] near L ~ 45 (tens of CG iterations); zero below L = 2"""
+    l = np.maximum(np.arange(lmax + 1, dtype=float), 1.0)
+    clkk = 30.0 / (1.0 + (l / 10.0) ** 2) ** 1.5
+    clpp = clkk / (0.5 * l * (l + 1)) ** 2
+    clpp[:2] = 0.0
+    return {'pp': clpp}

@@ -124,6 +124,32 @@ def test_cg_tt_diag_only(gold, mods):
     assert rel_l2(sol, gold['tt_diag_soltn']) < 1e-7
 
 
+def test_kappa_filter_matches_reference(mods):
+    """opfilt_kk: operators at 1e-10 and the two-level chain with the reference's iteration count and eps trace
+    (golden: tests/golden/make_golden_kk.py, unmodified reference)."""
+    from plancklens_b200.qcinv import opfilt_kk
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'reference_golden_kk.npz'))
+    c, ua = gi.cg_case(), mods['util_alm']
+    s_cls = gi.kk_cls(c['lmax'])
+    nf = opfilt_kk.alm_filter_ninv(c['ninv_t'], c['transf'], marge_monopole=True, marge_dipole=True)
+    assert np.allclose(nf.get_fkl(), nf.get_ftl()) and nf.nlev_fkl == nf.nlev_ftl
+    x = ua.dalm.from_numpy(c['x_t'])
+    fwd = opfilt_kk.fwd_op(s_cls, nf)
+    y = fwd(x)
+    assert rel_l2(y.numpy(), g['kk_fwd']) < 1e-10
+    assert rel_l2(opfilt_kk.calc_prep(c['tmap'], s_cls, nf).numpy(), g['kk_prep']) < 1e-10
+    assert rel_l2(opfilt_kk.pre_op_diag(s_cls, nf)(x).numpy(), g['kk_prediag']) < 1e-12
+    d = opfilt_kk.dot_op()(x, y)
+    assert abs(d - g['kk_dot'][0]) < 1e-10 * abs(g['kk_dot'][0])
+    assert set(fwd.hashdict()) == {'clkk_inv', 'n_inv_filt'}
+    sol = np.zeros(g['kk_soltn'].size, dtype=complex)
+    chain = _solve(mods, opfilt_kk, gi.chain_descr_t(mods['cd_solve']), s_cls, nf, sol, c['tmap'])
+    ref = g['kk_trace']
+    assert chain.niter == int(ref[-1][1])
+    assert np.allclose(np.array([t[1] for t in chain.last_monitor.trace]), ref[:, 2], rtol=1e-5)
+    assert rel_l2(sol, g['kk_soltn']) < 1e-7
+
+
 @pytest.mark.parametrize('pol', [False, True])
 def test_cg_graph_and_device_scalar_stages_equal_host_loop(gold, mods, pol, monkeypatch):
     """The inner multigrid stages run three ways -- the reference's host loop (cd_solve, PLK_CG_FIXED=0), the

@@ -127,3 +127,21 @@ def test_joint_tp_operators_match_reference(built):
         assert abs(ref_cg.dot_tp(x, f) - g[tag + '_dot'][0]) < 1e-11 * abs(g[tag + '_dot'][0])
         for a, k in zip(ref_cg.lmat3(ref_cg.pre_diag_tp(c['cls'], nf), *x), 'teb'):
             assert rel_l2(a, g['%s_prediag_%s' % (tag, k)]) < 1e-11
+
+
+def test_kappa_filter_operators_match_reference(built):
+    """opfilt_kk (the temperature operators with C_L^kk = (L(L+1)/2)^2 C_L^pp as the signal spectrum): oracle vs the
+    unmodified reference (tests/golden/make_golden_kk.py)."""
+    from oracle import ref_cg
+    from oracle.healpy_shim.healpy import almxfl
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'reference_golden_kk.npz'))
+    c = gi.cg_case()
+    clpp = gi.kk_cls(c['lmax'])['pp']
+    l = np.arange(c['lmax'] + 1, dtype=float)
+    clkk = clpp * (0.5 * l * (l + 1)) ** 2           # opfilt_kk.py:25-33
+    nf = ref_cg.ninv_tt(c['ninv_t'][0], c['transf'])
+    fwd = ref_cg.fwd_tt(c['x_t'], clkk, nf)
+    assert rel_l2(fwd, g['kk_fwd']) < 1e-11
+    assert rel_l2(nf.calc_prep(c['tmap']), g['kk_prep']) < 1e-11
+    assert rel_l2(almxfl(c['x_t'], ref_cg.pre_diag_tt(clkk, nf)), g['kk_prediag']) < 1e-12
+    assert abs(ref_cg.dot_tt(c['x_t'], fwd) - g['kk_dot'][0]) < 1e-11 * abs(g['kk_dot'][0])
