@@ -135,3 +135,34 @@ def cl_inverse(cls):
         if np.any(arr):
             out[k] = arr
     return out
+
+
+_TEB = ('t', 'e', 'b')
+
+
+def _cldict2arr(cls_dict):
+    """{'tt': ..., 'te': ...} -> symmetric (3, 3, lmax + 1) array in T, E, B order (reference: utils.py:375-381)."""
+    n = max(len(cl) for cl in cls_dict.values())
+    out = np.zeros((3, 3, n), dtype=float)
+    for i, x in enumerate(_TEB):
+        for j, y in enumerate(_TEB):
+            cl = cls_dict.get(x + y, cls_dict.get(y + x, None))
+            if cl is not None:
+                out[i, j] = extcl(n - 1, np.asarray(cl, dtype=float))
+    return out
+
+
+def cls_dot(cls_list, ret_dict=False):
+    """Product, per multipole, of T E B spectral matrices given as dictionaries or (3, 3, lmax + 1) arrays
+    (reference: utils.py:383-410).  With `ret_dict` the non-zero entries of the upper triangle come back as a dict."""
+    mats = [_cldict2arr(c) if isinstance(c, dict) else np.asarray(c) for c in cls_list]
+    ret = mats[-1]
+    for m in mats[-2::-1]:
+        ret = np.einsum('ikl,kjl->ijl', m, ret)
+    if not ret_dict or len(mats) == 1:
+        return ret
+    out = {}
+    for k, (i, j) in zip(['tt', 'ee', 'bb', 'te', 'tb', 'eb'], [[0, 0], [1, 1], [2, 2], [0, 1], [0, 2], [1, 2]]):
+        if np.any(ret[i, j]):
+            out[k] = ret[i, j].copy()
+    return out

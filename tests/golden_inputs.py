@@ -181,3 +181,18 @@ def kk_cls(lmax):
     clpp = clkk / (0.5 * l * (l + 1)) ** 2
     clpp[:2] = 0.0
     return {'pp': clpp}
+
+
+def n0s_cases(lmax=60, lmax_out=70):
+    """Keyword arguments of n0s.get_N0: toy spectra (response spectra differing from the weights), 80' beam."""
+    cls = toy_cls(lmax)
+    cls_len = {k: v * (1.0 + 0.05 * np.cos(np.arange(lmax + 1) / 7.0)) for k, v in cls.items()}
+    cls_sky = {k: v * 1.02 for k, v in cls.items()}
+    base = dict(beam_fwhm=80., nlev_t=150., lmax_CMB=lmax, lmin_CMB=2, lmax_out=lmax_out, cls_filt=cls,
+                cls_len=cls_len, cls_weight=cls, cls_sky=cls_sky)
+    l = np.arange(lmax + 1, dtype=float)
+    return {'gmv': dict(base, nlev_p=210., joint_TP=True),
+            'sep': dict(base, joint_TP=False, lmax_CMB={'t': 50, 'e': lmax, 'b': lmax},
+                        nlev_p=np.array([200. + l, 230. + 0.5 * l])),
+            'tcut': dict(base, nlev_p=210., joint_TP=True, wfleg_Tcut=40, ksource='p'),
+            'curl': dict(base, nlev_p=[210. * np.ones(lmax + 1)], joint_TP=True, ksource='x', lmin_CMB={'t': 5, 'e': 3, 'b': 3})}

@@ -215,3 +215,55 @@ def test_resp_and_nhl_libraries_cache_in_sqlite(tmp_path, monkeypatch):
     assert np.array_equal(n0, ref) and n0.shape == (41,) and np.all(n0[2:] > 0)
     n = len(calls)
     assert np.array_equal(nl.get_sim_nhl(0, 'ptt', 'ptt'), ref) and len(calls) == n
+
+
+def _n0s_gold():
+    return np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_n0s.npz'))
+
+
+def _check_n0s(tol):
+    import golden_inputs as gi
+    from plancklens_b200 import n0s
+    g = _n0s_gold()
+    expected = {'gmv': {'ptt', 'p_p', 'p'}, 'sep': {'ptt', 'p_p', 'p'}, 'tcut': {'ptt', 'p_p', 'p'}, 'curl': {'xtt', 'x_p', 'x'}}
+    for name, kw in gi.n0s_cases().items():
+        N0, N0c = n0s.get_N0(**kw)
+        assert set(N0) == set(N0c) == expected[name]
+        for k in N0:
+            for tag, mine in (('G', N0[k]), ('C', N0c[k])):
+                ref = g['%s_%s_%s' % (name, tag, k)]
+                assert mine.shape == ref.shape
+                assert np.max(np.abs(mine - ref)) <= tol * np.max(np.abs(ref)), (name, tag, k)
+
+
+def test_n0s_match_reference_on_cpu(monkeypatch):
+    """n0s.get_N0 (filters, filtered-map spectra with per-field multipole cuts, the Wiener-leg T cut, N0 = nhl / R^2)
+    against the unmodified reference (tests/golden/make_golden_n0s.py), Wigner seam served by the oracle."""
+    from oracle import ref_wigner
+    from plancklens_b200 import utils_spin as us
+    monkeypatch.setattr(us, 'wignerc', ref_wigner.wignerc)
+    _check_n0s(1e-11)
+
+
+@pytest.mark.gpu
+def test_n0s_match_reference_on_gpu():
+    _check_n0s(1e-8)
+
+
+def test_cls_dot_and_dls_conversions_match_reference():
+    from plancklens_b200 import n0s, utils
+    g = _n0s_gold()
+    a = {'tt': np.arange(5.) + 1, 'ee': np.arange(7.) + 2, 'te': 0.1 * np.arange(6.), 'bb': 0.5 * np.ones(4)}
+    b = {'tt': np.ones(7), 'ee': 2 * np.ones(7), 'bb': 3 * np.ones(7), 'tb': 0.2 * np.ones(7)}
+    assert np.allclose(utils.cls_dot([a, b]), g['clsdot_ab'], rtol=1e-15, atol=0)
+    assert np.allclose(utils.cls_dot([a, b, a]), g['clsdot_aba'], rtol=1e-14, atol=0)
+    d = utils.cls_dot([a, b, a], ret_dict=True)
+    assert set('clsdot_aba_' + k for k in d) == set(k for k in g.files if k.startswith('clsdot_aba_'))
+    for k, v in d.items():
+        assert np.allclose(v, g['clsdot_aba_' + k], rtol=1e-14, atol=0)
+    dls, cldd = n0s.cls2dls({'tt': a['tt'], 'te': a['te'], 'pp': np.arange(8.) * 1e-3})
+    assert np.allclose(dls, g['cls2dls'], rtol=1e-15, atol=0) and np.allclose(cldd, g['cls2dls_dd'], rtol=1e-15, atol=0)
+    back = n0s.dls2cls(dls)
+    assert np.allclose(back['tt'][1:5], a['tt'][1:5]) and np.allclose(back['te'][1:6], a['te'][1:6])
+    with pytest.raises(NotImplementedError):
+        n0s.get_N0_iter('p', 1., 1., 1., {}, 2, 10, 1)
