@@ -29,6 +29,8 @@ from . import utils as ut
 from .helpers import mpi
 
 _write_alm = lambda fn, alm: hp.write_alm(fn, alm, overwrite=True)
+_XY_PAIRS = ['te', 'et', 'tb', 'bt', 'ee', 'eb', 'be', 'bb']            # single-pair lensing keys 'pte', 'xeb', ...
+_SYM_PAIR_KEYS = ['p_te', 'p_tb', 'p_eb', 'x_te', 'x_tb', 'x_eb']
 
 
 def eval_qe(qe_key, lmax_ivf, cls_weight, get_alm, nside, lmax_qlm, verbose=True, get_alm2=None, transf=None):
@@ -213,9 +215,11 @@ class library:
                 self.fskies[int(key)] = float(val)
         self.fsky11, self.fsky12, self.fsky22 = self.fskies[11], self.fskies[12], self.fskies[22]
         self.resplib = resplib
-        self.keys_fund = ['ptt', 'xtt', 'p_p', 'x_p', 'p', 'x']
-        self.keys = self.keys_fund + ['p_tp', 'x_tp']
-        self.keys_remaps = {}
+        self.keys_fund = ['ptt', 'xtt', 'p_p', 'x_p', 'p', 'x', 'stt', 's', 'ftt', 'f_p', 'f', 'dtt', 'ntt', 'a_p'] \
+                         + [s + xy for s in 'px' for xy in _XY_PAIRS]
+        self.keys = self.keys_fund + ['p_tp', 'x_tp', 'p_te', 'p_tb', 'p_eb', 'x_te', 'x_tb', 'x_eb', 'ptt_bh_n',
+                                      'ptt_bh_s', 'ptt_bh_f', 'ptt_bh_d', 'dtt_bh_p', 'stt_bh_p', 'ftt_bh_d', 'p_bh_s']
+        self.keys_remaps = {'s': 'stt'}      # equivalent keys (reference: qest.py:118)
         self._qe = None
 
     def hashdict(self):
@@ -229,6 +233,11 @@ class library:
                 ret.append(k)
             elif '_tp' in k:
                 ret += [k[0] + 'tt', k[0] + '_p']
+            elif 'tt_bh_' in k:
+                kqe, src = k.split('_bh_')
+                ret += [kqe, src + 'tt']
+            elif k in _SYM_PAIR_KEYS:
+                ret += [k[0] + k[2] + k[3], k[0] + k[3] + k[2]]
         return list(collections.OrderedDict.fromkeys(ret))
 
     def get_fsky(self, id):
@@ -249,8 +258,14 @@ class library:
         if lmax is None:
             lmax = self.get_lmax_qlm(k)
         assert lmax <= self.get_lmax_qlm(k)
-        if k in ['p_tp', 'x_tp']:
+        if k in ['p_tp', 'x_tp', 'f_tp', 's_tp']:
             return self.get_sim_qlm('%stt' % k[0], idx, lmax=lmax) + self.get_sim_qlm('%s_p' % k[0], idx, lmax=lmax)
+        if k in _SYM_PAIR_KEYS:             # e.g. 'p_eb' = 'peb' + 'pbe'
+            return self.get_sim_qlm(k[0] + k[2] + k[3], idx, lmax=lmax) + self.get_sim_qlm(k[0] + k[3] + k[2], idx, lmax=lmax)
+        if '_bh_' in k:
+            kQE, kS, wL = self._bh_split(k)
+            lmax = self.get_lmax_qlm(kQE)
+            return self.get_sim_qlm(kQE, idx, lmax=lmax) - hp.almxfl(self.get_sim_qlm(kS, idx, lmax=lmax), wL)
         assert k in self.keys_fund, (k, self.keys_fund)
         fname = os.path.join(self.lib_dir, 'sim_%s_%04d.fits' % (k, idx) if idx != -1 else 'dat_%s.fits' % k)
         if not os.path.exists(fname):
@@ -260,18 +275,41 @@ class library:
                 self._build_sim_Pgclm(idx)
             elif k in ['p', 'x']:
                 self._build_sim_MVgclm(idx)
+            elif k in ['f', 'stt', 'ftt', 'f_p', 'ntt', 'a_p']:
+                getattr(self, '_build_sim_' + k)(idx)
+            elif k[1:] in _XY_PAIRS:
+                self._build_sim_xfiltMVgclm(idx, k)
+            else:
+                assert 0, k
         return ut.alm_copy(hp.read_alm(fname), lmax=lmax)
 
     def get_dat_qlm(self, k, **kwargs):
         return self.get_sim_qlm(k, -1, **kwargs)
 
+    def _bh_split(self, k):
+        """'ptt_bh_s' -> ('ptt', 'stt', w_L): the estimator hardened against source s is
+        qlm(ptt) - w_L qlm(stt) with w_L = R^{ptt,s}_L / R^{stt,s}_L from the response library (reference: qest.py:170-177)."""
+        assert self.resplib is not None, 'resplib arg necessary for this'
+        kQE, src = k.split('_bh_')
+        assert len(src) == 1, (src, kQE)
+        kS = src + kQE[1:]
+        assert self.get_lmax_qlm(kQE) == self.get_lmax_qlm(kS), (kQE, kS)
+        return kQE, kS, self.resplib.get_response(kQE, src) * ut.cli(self.resplib.get_response(kS, src))
+
     def get_sim_qlm_mf(self, k, mc_sims, lmax=None):
         """Mean-field estimate: average of the QE over mc_sims (reference: qest.py:206-246)."""
+        k = self.keys_remaps.get(k, k)
         if lmax is None:
             lmax = self.get_lmax_qlm(k)
         assert lmax <= self.get_lmax_qlm(k)
         if k in ['p_tp', 'x_tp']:
             return self.get_sim_qlm_mf('%stt' % k[0], mc_sims, lmax=lmax) + self.get_sim_qlm_mf('%s_p' % k[0], mc_sims, lmax=lmax)
+        if k in _SYM_PAIR_KEYS:
+            return self.get_sim_qlm_mf(k[0] + k[2] + k[3], mc_sims, lmax=lmax) + self.get_sim_qlm_mf(k[0] + k[3] + k[2], mc_sims, lmax=lmax)
+        if '_bh_' in k:
+            kQE, kS, wL = self._bh_split(k)
+            lmax = self.get_lmax_qlm(kQE)
+            return self.get_sim_qlm_mf(kQE, mc_sims, lmax=lmax) - hp.almxfl(self.get_sim_qlm_mf(kS, mc_sims, lmax=lmax), wL)
         assert k in self.keys_fund, (k, self.keys_fund)
         fname = os.path.join(self.lib_dir, 'simMF_k1%s_%s.fits' % (k, ut.mchash(mc_sims)))
         if not os.path.exists(fname):
@@ -436,6 +474,161 @@ class library:
     def _build_sim_MVgclm(self, idx):
         self._save('p', 'x', idx, *self._symmetrised(self._get_sim_MVgclm, idx, 'p'))
 
+    # ---- scalar-source estimators: products of two spin-0 / spin-2 real-space legs, one spin-0 analysis
+    def _plans(self, lmax_ivf):
+        return sht.get_plan(self.nside, lmax_ivf), sht.get_plan(self.nside, self.lmax_qlm['T'])
+
+    def _scalar_qlm(self, prod, fac, lmax_ivf):
+        fl = _dfl(fac * np.ones(self.lmax_qlm['T'] + 1))
+        return self._plans(lmax_ivf)[1].map2alm(prod, fl=fl).cpu().numpy()
+
+    def _t_res_map(self, f, idx, wl=None):
+        """alm2map(w_l T_bar) on the device"""
+        tlm = f.ivfs.get_sim_tlm(idx)
+        lmax = hp.Alm.getlmax(tlm.size)
+        return self._plans(lmax)[0].alm2map(sht.dev_alm(tlm), fl=None if wl is None else sht.dev_fl(wl, lmax)), lmax
+
+    def _p_res_maps(self, f, idx):
+        """alm2map_spin(E_bar / 2, B_bar / 2, 2)"""
+        elm, blm = f.ivfs.get_sim_elm(idx), f.ivfs.get_sim_blm(idx)
+        lmax = hp.Alm.getlmax(elm.size)
+        half = _dfl(0.5 * np.ones(lmax + 1))
+        return self._plans(lmax)[0].alm2map_spin(sht.dev_alm(elm), sht.dev_alm(blm), 2, flg=half, flc=half), lmax
+
+    def _t_wf_map(self, f, idx, joint):
+        tlm = f.ivfs.get_sim_tmliklm(idx)
+        if joint:
+            tlm = tlm + hp.almxfl(f.ivfs.get_sim_elm(idx), f.clte)
+        lmax = hp.Alm.getlmax(tlm.size)
+        return self._plans(lmax)[0].alm2map(sht.dev_alm(tlm))
+
+    def _p_wf_maps(self, f, idx, joint):
+        elm, blm = f.ivfs.get_sim_emliklm(idx), f.ivfs.get_sim_bmliklm(idx)
+        if joint:
+            elm = elm + hp.almxfl(f.ivfs.get_sim_tlm(idx), f.clte)
+        lmax = hp.Alm.getlmax(elm.size)
+        return self._plans(lmax)[0].alm2map_spin(sht.dev_alm(elm), sht.dev_alm(blm), 2)
+
+    def _get_sim_stt(self, idx, swapped=False):
+        """Point-source estimator -1/2 (T_bar_1 T_bar_2)_LM (reference: qest.py:286-290)."""
+        f1, f2 = self._legs(idx, 'stt', swapped)
+        t1, lmax = self._t_res_map(f1, idx)
+        t2, _ = self._t_res_map(f2, idx)
+        return self._scalar_qlm(t1.mul_(t2), -0.5, lmax)
+
+    def _get_sim_ntt(self, idx, swapped=False):
+        """Noise-inhomogeneity estimator: the same on beam-deconvolved maps (reference: qest.py:292-297)."""
+        f1, f2 = self._legs(idx, 'ntt', swapped)
+        t1, lmax = self._t_res_map(f1, idx, f1.ivfs.get_tal('t')[:])
+        t2, _ = self._t_res_map(f2, idx, f2.ivfs.get_tal('t')[:])
+        return self._scalar_qlm(t1.mul_(t2), -0.5, lmax)
+
+    def _get_sim_ftt(self, idx, joint=False, swapped=False):
+        """Modulation estimator, temperature: -(T_bar_1 T^WF_2)_LM (reference: qest.py:299-303)."""
+        f1, f2 = self._legs(idx, 'ftt', swapped)
+        t1, lmax = self._t_res_map(f1, idx)
+        return self._scalar_qlm(t1.mul_(self._t_wf_map(f2, idx, joint)), -1.0, lmax)
+
+    def _get_sim_f_p(self, idx, joint=False, swapped=False):
+        """Modulation estimator, polarization: -2 (Q_1 Q_2 + U_1 U_2)_LM (reference: qest.py:305-309)."""
+        f1, f2 = self._legs(idx, 'f_p', swapped)
+        (Q1, U1), lmax = self._p_res_maps(f1, idx)
+        Q2, U2 = self._p_wf_maps(f2, idx, joint)
+        return self._scalar_qlm(Q1.mul_(Q2).add_(U1.mul_(U2)), -2.0, lmax)
+
+    def _get_sim_a_p(self, idx, joint=False, swapped=False):
+        """Polarization-rotation estimator: -4 (Q_1 U_2 - U_1 Q_2)_LM (reference: qest.py:311-315)."""
+        f1, f2 = self._legs(idx, 'a_p', swapped)
+        (Q1, U1), lmax = self._p_res_maps(f1, idx)
+        Q2, U2 = self._p_wf_maps(f2, idx, joint)
+        return self._scalar_qlm(Q1.mul_(U2).sub_(U1.mul_(Q2)), -4.0, lmax)
+
+    def _two_legs(self):
+        return not self.f2map1.ivfs == self.f2map2.ivfs
+
+    def _save1(self, k, idx, qlm):
+        _write_alm(os.path.join(self.lib_dir, 'sim_%s_%04d.fits' % (k, idx) if idx != -1 else 'dat_%s.fits' % k), qlm)
+
+    def _build_sim_stt(self, idx):
+        self._save1('stt', idx, self._get_sim_stt(idx))          # symmetric in the two legs: no swap needed
+
+    def _build_sim_ntt(self, idx):
+        self._save1('ntt', idx, self._get_sim_ntt(idx))
+
+    def _build_sim_ftt(self, idx):
+        f = self._get_sim_ftt(idx)
+        if self._two_legs():
+            f = 0.5 * (f + self._get_sim_ftt(idx, swapped=True))
+        self._save1('ftt', idx, f)
+
+    def _build_sim_f_p(self, idx):
+        f = self._get_sim_f_p(idx)
+        if self._two_legs():
+            f = 0.5 * (f + self._get_sim_f_p(idx, swapped=True))
+        self._save1('f_p', idx, f)
+
+    def _build_sim_a_p(self, idx):
+        a = self._get_sim_a_p(idx)
+        if self._two_legs():
+            # the reference averages with the swapped-leg *f_p* estimate here (qest.py:433); kept for parity
+            a = 0.5 * (a + self._get_sim_f_p(idx, swapped=True))
+        self._save1('a_p', idx, a)
+
+    def _build_sim_f(self, idx):
+        """MV modulation estimator: P and T pieces with the C^TE cross terms in the Wiener legs (reference: qest.py:359-367)."""
+        fp = self._get_sim_f_p(idx, joint=True)
+        ft = self._get_sim_ftt(idx, joint=True)
+        if self._two_legs():
+            fp = 0.5 * (fp + self._get_sim_f_p(idx, joint=True, swapped=True))
+            ft = 0.5 * (ft + self._get_sim_ftt(idx, joint=True, swapped=True))
+        self._save1('f', idx, fp + ft)
+
+    # ---- single-pair lensing estimators 'pte', 'peb', ...: the MV estimator with one field kept on each leg
+    def _get_sim_xfilt_gclm(self, idx, x1, x2, swapped=False):
+        """MV lensing estimator keeping field x1 ('t', 'e' or 'b') on the inverse-variance leg and x2 on the
+        Wiener-filtered gradient leg (reference: qest.py:369-399 with the xfilt branches of qest.py:506-638).
+        Separately filtered libraries only, as in the reference."""
+        f1, f2 = self._legs(idx, 'p', swapped)
+        if swapped:
+            x1, x2 = x2, x1
+        assert isinstance(f2, lib_filt2map_sepTP), 'not implemented'
+        bars = {'t': f1.ivfs.get_sim_tlm, 'e': f1.ivfs.get_sim_elm, 'b': f1.ivfs.get_sim_blm}
+        bar = bars[x1](idx)
+        lmax = hp.Alm.getlmax(bar.size)
+        qe = self._engine(lmax)
+        zero = torch.zeros(bar.size, dtype=torch.complex128, device='cuda')
+        dbar = sht.dev_alm(bar)
+        # Wiener legs sourced by x2 alone: T^WF = C^TT T_bar [x2 = t] + C^TE E_bar [x2 = e],
+        #                                   E^WF = C^EE E_bar [x2 = e] + C^TE T_bar [x2 = t],  B^WF = C^BB B_bar [x2 = b]
+        twf = ewf = bwf = None
+        if x2 == 't':
+            twf = sht.dev_alm(f2.ivfs.get_sim_tmliklm(idx))
+            ewf = sht.dev_alm(hp.almxfl(f2.ivfs.get_sim_tlm(idx), f2.clte))
+        elif x2 == 'e':
+            twf = sht.dev_alm(hp.almxfl(f2.ivfs.get_sim_elm(idx), f2.clte))
+            ewf = sht.dev_alm(f2.ivfs.get_sim_emliklm(idx))
+        else:
+            bwf = sht.dev_alm(f2.ivfs.get_sim_bmliklm(idx))
+        re = im = None
+        if x1 == 't' and twf is not None:
+            G, C = qe.t_products(dbar, twf)
+            re, im = G, C
+        elif x1 in 'eb' and (ewf is not None or bwf is not None):
+            re, im = qe.p_products(dbar if x1 == 'e' else zero, dbar if x1 == 'b' else zero,
+                                   zero if ewf is None else ewf, zero if bwf is None else bwf)
+        if re is None:
+            n = hp.Alm.getsize(self.lmax_qlm['T'])
+            return np.zeros(n, dtype=complex), np.zeros(n, dtype=complex)
+        return qe.to_host(*qe.analyse(re, im))
+
+    def _build_sim_xfiltMVgclm(self, idx, k):
+        assert k[0] in 'px' and k[1:] in _XY_PAIRS + ['tt'], k
+        G, C = self._get_sim_xfilt_gclm(idx, k[-2], k[-1])
+        if self._two_legs():
+            _G, _C = self._get_sim_xfilt_gclm(idx, k[-2], k[-1], swapped=True)
+            G, C = 0.5 * (G + _G), 0.5 * (C + _C)
+        self._save('p' + k[1:], 'x' + k[1:], idx, G, C)
+
 
 class lib_filt2map(object):
     """Filtered alms -> real-space legs, jointly filtered T and P (reference: qest.py:441-530).
@@ -475,6 +668,11 @@ class lib_filt2map(object):
     def get_pmap(self, idx):
         Glm, Clm = self.ivfs.get_sim_emliklm(idx), self.ivfs.get_sim_bmliklm(idx)
         return hp.alm2map_spin([Glm, Clm], self.nside, 2, hp.Alm.getlmax(Glm.size))
+
+    def get_wirestmap(self, idx, wl):
+        """weighted residual map alm2map(w_l T_bar) (reference: qest.py:516-519)"""
+        reslm = self.ivfs.get_sim_tlm(idx)
+        return hp.alm2map(hp.almxfl(reslm, wl), self.nside, lmax=hp.Alm.getlmax(reslm.size))
 
     def get_gpmap(self, idx, spin, k=None, xfilt=None):
         r"""\sum_{lm} (Elm +- iBlm) sqrt((l+2)(l-1)) _1 Ylm(n) or sqrt((l-2)(l+3)) _3 Ylm(n) (reference: qest.py:481-504)."""

@@ -112,18 +112,22 @@ class idx_ivfs:
     on the product side)."""
     lib_dir = None
 
-    def __init__(self, q, hp):
-        self.q, self.hp = q, hp
+    def __init__(self, q, hp, shift=0):
+        self.q, self.hp, self.shift = q, hp, shift
         self.cl = q['cls']
 
     def hashdict(self):
-        return {'idx_ivfs': 1}
+        return {'idx_ivfs': 1, 'shift': self.shift}
+
+    def get_tal(self, a):
+        l = np.arange(self.q['lmax'] + 1, dtype=float)
+        return np.exp(0.5 * l * (l + 1) * 0.01 ** 2)          # inverse of a Gaussian transfer function
 
     def get_fmask(self):
         return np.ones(12 * self.q['nside'] ** 2)
 
     def _mix(self, a, idx):
-        i = idx if idx >= 0 else 7
+        i = (idx if idx >= 0 else 7) + self.shift
         return self.q[a + 'lm1'] * (1.0 + 0.3 * i) + self.q[a + 'lm2'] * (0.2 * i - 0.1)
 
     def get_sim_tlm(self, idx): return self._mix('t', idx)
@@ -196,3 +200,20 @@ def n0s_cases(lmax=60, lmax_out=70):
                         nlev_p=np.array([200. + l, 230. + 0.5 * l])),
             'tcut': dict(base, nlev_p=210., joint_TP=True, wfleg_Tcut=40, ksource='p'),
             'curl': dict(base, nlev_p=[210. * np.ones(lmax + 1)], joint_TP=True, ksource='x', lmin_CMB={'t': 5, 'e': 3, 'b': 3})}
+
+
+QEST_EXTRA_KEYS = ['stt', 'ntt', 'ftt', 'f_p', 'f', 'a_p', 'pte', 'pet', 'xbt', 'peb', 'pbe', 'xee', 'ptb', 'p_eb', 'x_te',
+                   'f_tp', 'ptt_bh_s', 's']
+
+
+class toy_resplib:
+    """deterministic stand-in for qresp.resp_lib_simple: enough for the bias-hardening combination of qest.library"""
+
+    def __init__(self, lmax_qlm):
+        self.L = np.arange(lmax_qlm + 1, dtype=float)
+
+    def get_response(self, k, ksource):
+        seed = sum(ord(c) for c in k + ksource)
+        r = 1.0 + 0.01 * seed + 0.3 * np.cos(self.L / (3.0 + seed % 5))
+        r[:2] = 0.0
+        return r
