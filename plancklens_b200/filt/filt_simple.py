@@ -253,6 +253,25 @@ class library_fullsky_sepTP(library_sepTP):
         return elm, blm
 
 
+class library_fullsky_alms_sepTP(library_fullsky_sepTP):
+    """The same isotropic filter for a simulation library that hands out harmonic coefficients: its `get_sim_tmap`
+    returns tlm and `get_sim_pmap` returns (elm, blm), so no transform is involved (reference: filt_simple.py:409-470)."""
+
+    def __init__(self, lib_dir, sim_lib, transf, cl_len, ftl, fel, fbl, cache=False):
+        super(library_fullsky_alms_sepTP, self).__init__(lib_dir, sim_lib, None, transf, cl_len, ftl, fel, fbl, cache=cache)
+
+    def get_fmask(self):
+        return np.array([1.])       # for compatibility only
+
+    def _apply_ivf_t(self, tlm, soltn=None):
+        return hp.almxfl(tlm, self.get_ftl() * utils.cli(self.transf['t'][:len(self.ftl)]))
+
+    def _apply_ivf_p(self, eblm, soltn=None):
+        elm = hp.almxfl(eblm[0], self.get_fel() * utils.cli(self.transf['e'][:len(self.fel)]))
+        blm = hp.almxfl(eblm[1], self.get_fbl() * utils.cli(self.transf['b'][:len(self.fbl)]))
+        return elm, blm
+
+
 class library_apo_sepTP(library_sepTP):
     """Apodised-mask + isotropic filter (reference: filt_simple.py:473-534)."""
 

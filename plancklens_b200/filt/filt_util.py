@@ -66,6 +66,88 @@ class library_ftl:
         return self._cut(self.ivfs.get_sim_bmliklm(idx), self.lfilt_b)
 
 
+class library_fml:
+    """Rescales the filtered alms of another library by functions of m, alm -> f_m alm (reference: filt_util.py:106-182).
+
+    The isotropic filters reported by get_ftl / get_fel / get_fbl carry the square root of the m-averaged weight
+    (2 sum_{m <= l} f_m - f_0) / (2 l + 1)."""
+
+    def __init__(self, ivfs, lmax, mfilt_t, mfilt_e, mfilt_b):
+        assert len(mfilt_t) > lmax and len(mfilt_e) > lmax and len(mfilt_b) > lmax
+        self.ivfs = ivfs
+        self.lmax = lmax
+        self.mfilt_t, self.mfilt_e, self.mfilt_b = mfilt_t, mfilt_e, mfilt_b
+        self.lib_dir = ivfs.lib_dir
+
+    def hashdict(self):
+        return {'ivfs': self.ivfs.hashdict(), 'filt_t': utils.clhash(self.mfilt_t[:self.lmax + 1]),
+                'filt_e': utils.clhash(self.mfilt_e[:self.lmax + 1]), 'filt_b': utils.clhash(self.mfilt_b[:self.lmax + 1])}
+
+    def get_fmask(self):
+        return self.ivfs.get_fmask()
+
+    def get_tal(self, a):
+        return self.ivfs.get_tal(a)
+
+    @staticmethod
+    def almxfm(alm, fm, lmax):
+        """alm truncated / padded to lmax with every m column scaled by fm[m]"""
+        ret = utils.alm_copy(alm, lmax=lmax)
+        start = 0
+        for m in range(lmax + 1):           # healpy order: m-major blocks of lmax + 1 - m entries
+            ret[start:start + lmax + 1 - m] *= fm[m]
+            start += lmax + 1 - m
+        return ret
+
+    def _l_rescal(self, fm):
+        w = 2 * np.cumsum(fm[:self.lmax + 1]) - fm[0]
+        return np.sqrt(w / (2 * np.arange(self.lmax + 1) + 1))
+
+    def get_ftl(self):
+        return self.ivfs.get_ftl()[:self.lmax + 1] * self._l_rescal(self.mfilt_t)
+
+    def get_fel(self):
+        return self.ivfs.get_fel()[:self.lmax + 1] * self._l_rescal(self.mfilt_e)
+
+    def get_fbl(self):
+        return self.ivfs.get_fbl()[:self.lmax + 1] * self._l_rescal(self.mfilt_b)
+
+    def get_sim_tlm(self, idx):
+        return self.almxfm(self.ivfs.get_sim_tlm(idx), self.mfilt_t, self.lmax)
+
+    # the reference scales the inverse-variance filtered E and B with the *temperature* weights (filt_util.py:169-173)
+    def get_sim_elm(self, idx):
+        return self.almxfm(self.ivfs.get_sim_elm(idx), self.mfilt_t, self.lmax)
+
+    def get_sim_blm(self, idx):
+        return self.almxfm(self.ivfs.get_sim_blm(idx), self.mfilt_t, self.lmax)
+
+    def get_sim_tmliklm(self, idx):
+        return self.almxfm(self.ivfs.get_sim_tmliklm(idx), self.mfilt_t, self.lmax)
+
+    def get_sim_emliklm(self, idx):
+        return self.almxfm(self.ivfs.get_sim_emliklm(idx), self.mfilt_e, self.lmax)
+
+    def get_sim_bmliklm(self, idx):
+        return self.almxfm(self.ivfs.get_sim_bmliklm(idx), self.mfilt_b, self.lmax)
+
+
+def _alm_copy(alm, mmaxin, lmaxout, mmaxout):
+    """Copy of a healpy alm array with new lmax and mmax (reference: filt_util.py:10-37)."""
+    lmaxin = hp.Alm.getlmax(alm.size, mmaxin)
+    if mmaxin is None or mmaxin < 0:
+        mmaxin = lmaxin
+    if lmaxin == lmaxout and mmaxin == mmaxout:
+        return np.copy(alm)
+    ret = np.zeros(hp.Alm.getsize(lmaxout, mmaxout), dtype=complex)
+    n = min(lmaxout, lmaxin) + 1
+    for m in range(min(mmaxout, mmaxin) + 1):
+        i = m * (2 * lmaxin + 1 - m) // 2 + m
+        o = m * (2 * lmaxout + 1 - m) // 2 + m
+        ret[o:o + n - m] = alm[i:i + n - m]
+    return ret
+
+
 class library_shuffle:
     """Filtering library with remapped simulation indices (reference: filt_util.py:186-236)."""
 

@@ -3,7 +3,7 @@
 Combines two `qest.library` instances and a set of mean-field simulations into raw spectra
 :math:`\\frac{1}{(2L+1) f_{sky}} \\sum_M \\hat\\phi^A_{LM} \\hat\\phi^{B\\dagger}_{LM}` after mean-field subtraction.  The
 subtraction and `alm2cl` run on the GPU (`plk_alm_axpy_dev`, `plk_alm2cl_dev`); spectra are cached as `.npy` files
-under the reference's names (the reference keeps them in a sqlite `npdb`).  `qecl.average` is not mirrored.
+under the reference's names (the reference keeps them in a sqlite `npdb`).
 """
 import os
 import pickle as pk
@@ -87,28 +87,81 @@ class library(object):
             np.save(fname, self._alm2clfsky1234(qlmA, qlmB, k1, k2))
         return np.load(fname)[:lmax_out + 1] / self.fskies[1234]
 
+    def get_dat_qcl(self, k1, k2=None, lmax=None, recache=False):
+        """QE (cross-)power spectrum of the data maps (index -1); `qecl.average.get_dat_qcl` calls it, although the
+        reference's `library` does not define it (qecl.py:199 raises AttributeError there)"""
+        return self.get_sim_qcl(k1, -1, k2=k2, lmax=lmax, recache=recache)
+
     def get_sim_stats_qcl(self, k1, mc_sims, k2=None, recache=False):
-        """Mean and scatter of the QE spectra over mc_sims: object with `.mean()`, `.sigmas()`, `.N`
-        (the part of plancklens.utils.stats the spectra pipeline uses)."""
+        """Mean and scatter of the QE spectra over mc_sims, as a cached `utils.stats` instance (reference: qecl.py:126-145)."""
         if k2 is None:
             k2 = k1
-        cls = np.array([self.get_sim_qcl(k1, idx, k2=k2) for idx in mc_sims])
-        return _stats(cls)
+        tfname = os.path.join(self.lib_dir, 'sim_qcl_stats_%s_%s_%s.pk' % (k1, k2, utils.mchash(mc_sims)))
+        if not os.path.exists(tfname) or recache:
+            st = utils.stats(self.get_lmaxqcl(k1, k2) + 1, docov=False)
+            for idx in mc_sims:
+                st.add(self.get_sim_qcl(k1, idx, k2=k2))
+            with open(tfname, 'wb') as f:
+                pk.dump(st, f, protocol=2)
+        with open(tfname, 'rb') as f:
+            return pk.load(f)
 
     def _alm2clfsky1234(self, qlm1, qlm2, k1, k2):
         return sht.alm2cl(qlm1, qlm2).cpu().numpy()
 
 
-class _stats:
-    def __init__(self, rows):
-        self.rows = np.atleast_2d(rows)
-        self.N = self.rows.shape[0]
+class average:
+    """Average of several QE spectra libraries (reference: qecl.py:151-223).
 
-    def mean(self):
-        return np.mean(self.rows, axis=0)
+        Args:
+            lib_dir: the statistics are cached there
+            qcls_lib: list of `qecl.library` instances
+    """
 
-    def sigmas(self):
-        return np.std(self.rows, axis=0, ddof=1) if self.N > 1 else np.zeros(self.rows.shape[1])
+    def __init__(self, lib_dir, qcls_lib):
+        self.lib_dir = lib_dir
+        self.qclibs = qcls_lib
+        hname = os.path.join(lib_dir, 'qeclav_hash.pk')
+        if mpi.rank == 0:
+            os.makedirs(lib_dir, exist_ok=True)
+            if not os.path.exists(hname):
+                with open(hname, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+        mpi.barrier()
+        with open(hname, 'rb') as f:
+            utils.hash_check(pk.load(f), self.hashdict(), fn=hname)
+        self.mc_sims_mf = np.sort(np.unique(np.concatenate([q.mc_sims_mf for q in self.qclibs])))
 
-    def sigmas_on_mean(self):
-        return self.sigmas() / np.sqrt(self.N)
+    def hashdict(self):
+        return {'qcl_lib %s' % i: q.hashdict() for i, q in enumerate(self.qclibs)}
+
+    def get_lmaxqcl(self, k1, k2):
+        return np.min([q.get_lmaxqcl(k1, k2) for q in self.qclibs])
+
+    def _mean(self, get):
+        return sum(get(q) for q in self.qclibs) / len(self.qclibs)
+
+    def get_sim_qcl(self, k1, idx, k2=None, lmax=None):
+        if lmax is None:
+            lmax = self.get_lmaxqcl(k1, k2)
+        return self._mean(lambda q: q.get_sim_qcl(k1, idx, k2=k2, lmax=lmax))
+
+    def get_dat_qcl(self, k1, k2=None, lmax=None):
+        if lmax is None:
+            lmax = self.get_lmaxqcl(k1, k2)
+        return self._mean(lambda q: q.get_dat_qcl(k1, k2=k2, lmax=lmax))
+
+    def get_sim_stats_qcl(self, k1, mc_sims, k2=None, recache=False, lmax=None):
+        if k2 is None:
+            k2 = k1
+        if lmax is None:
+            lmax = self.get_lmaxqcl(k1, k2)
+        tfname = os.path.join(self.lib_dir, 'sim_qcl_stats_%s_%s_%s_%s.pk' % (k1, k2, lmax, utils.mchash(mc_sims)))
+        if not os.path.exists(tfname) or recache:
+            st = utils.stats(lmax + 1, docov=False)
+            for idx in mc_sims:
+                st.add(self.get_sim_qcl(k1, idx, k2=k2, lmax=lmax))
+            with open(tfname, 'wb') as f:
+                pk.dump(st, f, protocol=2)
+        with open(tfname, 'rb') as f:
+            return pk.load(f)

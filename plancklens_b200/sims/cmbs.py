@@ -69,3 +69,16 @@ class sims_cmb_unl:
 
     def get_sim_blm(self, idx):
         return self.get_sim_alm(idx, 'b')
+
+    def get_sim_plm(self, idx):
+        """lensing potential (field 'p' of the input spectra, e.g. from 'pp', 'pt', 'pe')"""
+        return self.get_sim_alm(idx, 'p')
+
+    def get_sim_olm(self, idx):
+        """lensing curl potential (field 'o')"""
+        return self.get_sim_alm(idx, 'o')
+
+    def get_sim_alms(self, idx):
+        """all fields of one simulation, in the order of `self.fields` (the reference's version, cmbs.py:95-101,
+        builds the same array but forgets to return it)"""
+        return np.array([self._get_sim_alm(idx, i) for i in range(len(self.fields))])

@@ -101,3 +101,71 @@ class cmb_maps_nlev(cmb_maps):
 
     def get_sim_unoise(self, idx):
         return self.nlev_p / self._vamin() * self.pix_lib_phas.get_sim(idx, idf=2)
+
+
+class cmb_maps_harmonicspace(object):
+    r"""Simulations made directly in harmonic space: transfer function times the lensed CMB alms plus statistically
+    isotropic (possibly non-white) noise drawn from a harmonic phase library (reference: maps.py:176-275).
+
+        Args:
+            sims_cmb_len: lensed CMB library
+            cls_transf: transfer functions for 't', 'e', 'b'
+            cls_noise: noise spectra for 't', 'e', 'b'
+            noise_phas: `phas.lib_phas` with at least three fields, same lmax as the CMB library
+            lib_dir (optional): the hash is checked against a cached copy there
+            nside (optional): maps are returned in pixel space at this resolution instead of as alms
+    """
+
+    def __init__(self, sims_cmb_len, cls_transf, cls_noise, noise_phas, lib_dir=None, nside=None):
+        import os
+        import pickle as pk
+        from ..helpers import mpi
+        from ..utils import hash_check
+        assert noise_phas.nfields >= 3, noise_phas.nfields
+        self.sims_cmb_len, self.cls_transf, self.cls_noise = sims_cmb_len, cls_transf, cls_noise
+        self.phas, self.nside = noise_phas, nside
+        if hasattr(sims_cmb_len, 'lmax'):
+            assert sims_cmb_len.lmax == noise_phas.lmax, (sims_cmb_len.lmax, noise_phas.lmax)
+        if lib_dir is not None:
+            fn_hash = os.path.join(lib_dir, 'sim_hash.pk')
+            if mpi.rank == 0 and not os.path.exists(fn_hash):
+                os.makedirs(lib_dir, exist_ok=True)
+                with open(fn_hash, 'wb') as f:
+                    pk.dump(self.hashdict(), f, protocol=2)
+            mpi.barrier()
+            with open(fn_hash, 'rb') as f:
+                hash_check(self.hashdict(), pk.load(f))
+
+    def hashdict(self):
+        ret = {'sims_cmb_len': self.sims_cmb_len.hashdict(), 'phas': self.phas.hashdict()}
+        ret.update({'noise' + k: clhash(v) for k, v in self.cls_noise.items()})
+        ret.update({'transf' + k: clhash(v) for k, v in self.cls_transf.items()})
+        return ret
+
+    def _noise(self, idx, a):
+        assert a in self.cls_noise, a
+        return hp.almxfl(self.phas.get_sim(idx, 'teb'.index(a)), np.sqrt(self.cls_noise[a]))
+
+    def get_sim_tnoise(self, idx):
+        return self._noise(idx, 't')
+
+    def get_sim_enoise(self, idx):
+        return self._noise(idx, 'e')
+
+    def get_sim_bnoise(self, idx):
+        return self._noise(idx, 'b')
+
+    def get_sim_tmap(self, idx):
+        """temperature alms, or the map if nside was given"""
+        assert 't' in self.cls_transf
+        tlm = hp.almxfl(self.sims_cmb_len.get_sim_tlm(idx), self.cls_transf['t']) + self.get_sim_tnoise(idx)
+        return hp.alm2map(tlm, self.nside) if self.nside else tlm
+
+    def get_sim_pmap(self, idx):
+        """(elm, blm), or the (Q, U) maps if nside was given"""
+        assert 'e' in self.cls_transf and 'b' in self.cls_transf
+        elm = hp.almxfl(self.sims_cmb_len.get_sim_elm(idx), self.cls_transf['e']) + self.get_sim_enoise(idx)
+        blm = hp.almxfl(self.sims_cmb_len.get_sim_blm(idx), self.cls_transf['b']) + self.get_sim_bnoise(idx)
+        if self.nside is not None:
+            return hp.alm2map_spin([elm, blm], self.nside, 2, hp.Alm.getlmax(elm.size))
+        return elm, blm

@@ -166,3 +166,106 @@ def cls_dot(cls_list, ret_dict=False):
         if np.any(ret[i, j]):
             out[k] = ret[i, j].copy()
     return out
+
+
+def alm2rlm(alm):
+    """complex alm -> 'real harmonic' coefficients (reference: utils.py:37-51)"""
+    from .qcinv.dense import alm2rlm as f
+    return f(alm)
+
+
+def rlm2alm(rlm):
+    """inverse of alm2rlm (reference: utils.py:54-69)"""
+    from .qcinv.dense import rlm2alm as f
+    return f(rlm)
+
+
+class stats:
+    """Running mean and covariance of data vectors (reference: utils.py:178-267).
+
+    `sum`, `mom` (second-moment matrix, only with docov) and `N` are the accumulators; unlike the reference the diagonal
+    second moments are always kept, so `sigmas()` also works with docov=False."""
+
+    def __init__(self, size, xcoord=None, docov=True):
+        self.N = 0
+        self.size = size
+        self.sum = np.zeros(size)
+        self.sum2 = np.zeros(size)
+        if docov:
+            self.mom = np.zeros((size, size))
+        self.xcoord = xcoord
+        self.docov = docov
+
+    def add(self, v):
+        assert v.shape == (self.size,), "input not understood"
+        self.sum += v
+        self.sum2 += v * v
+        if self.docov:
+            self.mom += np.outer(v, v)
+        self.N += 1
+
+    def mean(self):
+        assert self.N > 0
+        return self.sum / float(self.N)
+
+    avg = mean
+
+    def cov(self):
+        assert self.docov and self.N > 0
+        if self.N == 1:
+            return np.zeros((self.size, self.size))
+        m = self.mean()
+        return (self.mom - self.N * np.outer(m, m)) / (self.N - 1.)
+
+    def sigmas(self):
+        if self.docov:
+            return np.sqrt(np.diagonal(self.cov()))
+        assert self.N > 0
+        if self.N == 1:
+            return np.zeros(self.size)
+        return np.sqrt(np.maximum(self.sum2 - self.N * self.mean() ** 2, 0.) / (self.N - 1.))
+
+    def corrcoeffs(self):
+        sig = self.sigmas()
+        return self.cov() / np.outer(sig, sig)
+
+    def sigmas_on_mean(self):
+        assert self.N > 0
+        return self.sigmas() / np.sqrt(self.N)
+
+    def inverse(self, bias_p=None):
+        """inverse covariance, by default with the (N - size - 2) / (N - 1) de-biasing factor"""
+        assert self.N > self.size, "Non invertible cov.matrix"
+        if bias_p is None:
+            bias_p = (self.N - self.size - 2.) / (self.N - 1)
+        return bias_p * np.linalg.inv(self.cov())
+
+    def get_chisq(self, data):
+        assert data.size == self.size, (data.size, self.size)
+        dx = data - self.mean()
+        return float(dx @ self.inverse() @ dx)
+
+    def get_chisq_pte(self, data):
+        from scipy.stats import chi2
+        return chi2.sf(self.get_chisq(data), self.N - 1)
+
+    def rebin_that_nooverlap(self, orig_coord, lmins, lmaxs, weights=None):
+        """New instance with the data vector averaged (weights) inside the non-overlapping bins [lmin, lmax]."""
+        lmins, lmaxs = np.asarray(lmins), np.asarray(lmaxs)
+        assert orig_coord.size == self.size and lmins.size == lmaxs.size, "Incompatible input"
+        assert np.all(np.diff(lmins) > 0.) and np.all(np.diff(lmaxs) > 0.), "This only for non overlapping bins."
+        if weights is None:
+            weights = np.ones(self.size)
+        assert weights.size == self.size and self.size > len(lmaxs), "incompatible input"
+        T = np.zeros((len(lmaxs), self.size))
+        for k, (lo, hi) in enumerate(zip(lmins, lmaxs)):
+            sel = (orig_coord >= lo) & (orig_coord <= hi)
+            if np.any(sel):
+                T[k, sel] = weights[sel] / np.sum(weights[sel])
+        new = stats(len(lmaxs), xcoord=0.5 * (lmins[:-1] + lmaxs[1:]), docov=self.docov)
+        new.sum = T @ self.sum
+        if self.docov:
+            new.mom = T @ self.mom @ T.T
+            new.sum2 = np.diagonal(new.mom).copy()
+        new.N = self.N
+        return new

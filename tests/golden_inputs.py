@@ -217,3 +217,64 @@ class toy_resplib:
         r = 1.0 + 0.01 * seed + 0.3 * np.cos(self.L / (3.0 + seed % 5))
         r[:2] = 0.0
         return r
+
+
+def wrapper_case(q):
+    """filters and spectra for the host-side wrapper goldens (make_golden_wrappers.py)"""
+    lmax = q['lmax']
+    l = np.arange(lmax + 1, dtype=float)
+    transf = np.exp(-0.5 * l * (l + 1) * 0.02 ** 2)
+    return {'lmax_cut': lmax - 6, 'transf': transf,
+            'ftl': 1.0 / (1.0 + 0.01 * l), 'fel': 2.0 / (1.0 + 0.02 * l), 'fbl': 3.0 / (1.0 + 0.03 * l),
+            'fm_t': 1.0 - 0.5 * np.exp(-l / 4.0), 'fm_e': 1.0 - 0.3 * np.exp(-l / 6.0), 'fm_b': np.where(l < 3, 0.0, 1.0),
+            'nl_t': 1e-4 * (1 + 30.0 / (l + 1)), 'nl_p': 3e-4 * np.ones(lmax + 1)}
+
+
+class alm_sims:
+    """simulation library handing out harmonic coefficients (what library_fullsky_alms_sepTP and
+    cmb_maps_harmonicspace consume), deterministic mixes of qe_case's alms"""
+
+    def __init__(self, q):
+        self.q, self.lmax = q, q['lmax']
+
+    def hashdict(self):
+        return {'alm_sims': 1}
+
+    def _mix(self, a, idx):
+        return self.q[a + 'lm1'] * (1.0 + 0.5 * idx) - self.q[a + 'lm2'] * 0.25 * idx
+
+    def get_sim_tlm(self, idx): return self._mix('t', idx)
+    def get_sim_elm(self, idx): return self._mix('e', idx)
+    def get_sim_blm(self, idx): return self._mix('b', idx)
+    def get_sim_tmap(self, idx): return self._mix('t', idx)
+    def get_sim_pmap(self, idx): return self._mix('e', idx), self._mix('b', idx)
+
+
+class map_sims:
+    """tiny map-valued simulation library (12 pixels), value = scale * f(idx, pixel)"""
+
+    def __init__(self, q, scale):
+        self.scale = scale
+
+    def hashdict(self):
+        return {'map_sims': self.scale}
+
+    def get_sim_tmap(self, idx):
+        return self.scale * (np.arange(12.) + idx)
+
+    def get_sim_pmap(self, idx):
+        return self.scale * np.cos(np.arange(12.) + idx), self.scale * np.sin(np.arange(12.) * idx)
+
+
+class fixed_phas:
+    """harmonic phase library with three deterministic fields (stand-in for sims.phas.lib_phas)"""
+    nfields = 3
+
+    def __init__(self, q):
+        self.q, self.lmax = q, q['lmax']
+
+    def hashdict(self):
+        return {'fixed_phas': 1}
+
+    def get_sim(self, idx, idf=None):
+        return [self.q['tlm2'], self.q['elm2'], self.q['blm2']][idf] * (1.0 + idx)
