@@ -156,3 +156,19 @@ class nhl_lib_simple:
         lmaxs = [len(cl) for cl in ret.values()]
         assert len(np.unique(lmaxs)) == 1, lmaxs
         return ret, lmaxs[0]
+
+
+def cls2dls(cls):
+    """see n0s.cls2dls (the reference keeps a second copy here, nhl.py:191-203)"""
+    from . import n0s
+    return n0s.cls2dls(cls)
+
+
+def dls2cls(dls):
+    from . import n0s
+    return n0s.dls2cls(dls)
+
+
+def get_N0_iter(*args, **kwargs):
+    from . import n0s
+    return n0s.get_N0_iter(*args, **kwargs)

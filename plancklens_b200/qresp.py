@@ -112,9 +112,118 @@ def get_response(qe_key, lmax_ivf, source, cls_weight, cls_cmb, fal, fal_leg2=No
         iG, iC = ut.cli(GG_hh), ut.cli(CC_hh)
         return (GG_ks - (GG_kh * GG_hs * iG + GC_kh * CG_hs * iC), CC_ks - (CG_kh * GC_hs * iG + CC_kh * CC_hs * iC),
                 GC_ks - (GG_kh * GC_hs * iG + GC_kh * CC_hs * iC), CG_ks - (CG_kh * GG_hs * iG + CC_kh * CG_hs * iC))
-    assert source not in ['n', 'ntt'], 'point-source / noise-inhomogeneity responses are not mirrored'
     qes = get_qes(qe_key, lmax_ivf, cls_weight, lmax2=lmax_ivf2, transf=transf)
+    custom = _get_response_custom(qe_key, qes, source, fal, lmax_qlm, fal_leg2=fal_leg2, transf=transf)
+    if custom is not None:
+        return custom
     return _get_response(qes, source, cls_cmb, fal, lmax_qlm, fal_leg2=fal_leg2)
+
+
+def _get_response_custom(qe_key, qes, source, fal_leg1, lmax_qlm, fal_leg2=None, transf=None):
+    """Responses that do not fit the (source spin, covariance response) scheme of `get_covresp`: temperature
+    estimators responding to a noise-variance map ('n' / 'ntt'), a spin-0 source acting on the beam-deconvolved
+    temperature (reference: qresp.py:315-361).  None for every other combination."""
+    if not ('tt' in qe_key and source in ['n', 'ntt']):
+        return None
+    assert transf is not None
+    fal_leg2 = fal_leg1 if fal_leg2 is None else fal_leg2
+    Ls = np.arange(lmax_qlm + 1, dtype=int)
+    R = np.zeros((4, lmax_qlm + 1), dtype=float)          # GG, CC, GC, CG
+    bi = _clinv(transf)
+    for qe in qes:
+        si, ti, so, to = qe.leg_a.spin_in, qe.leg_b.spin_in, qe.leg_a.spin_ou, qe.leg_b.spin_ou
+        assert (si, ti) == (0, 0)
+        spin_qe = abs(so + to)
+
+        def term(sgn):
+            FA = uspin.get_spin_matrix(sgn * si, 0, fal_leg1)
+            FB = uspin.get_spin_matrix(sgn * ti, 0, fal_leg2)
+            cla, clb = (qe.leg_a.cl, qe.leg_b.cl) if sgn > 0 else (qe.leg_a.cl.conj(), qe.leg_b.cl.conj())
+            return FB, uspin.wignerc(ut.joincls([cla, FA, bi]), ut.joincls([clb, FB, bi]), sgn * so, 0, sgn * to, 0,
+                                     lmax_out=lmax_qlm)
+        FB, Rp = term(+1)
+        if not np.any(FB):
+            continue
+        Rm = (-1) ** (so + si + to + ti) * term(-1)[1] if spin_qe > 0 else Rp
+        w, sg = 0.5 * qe.cL(Ls), (-1) ** spin_qe
+        R[0] += w * (Rp.real + sg * Rm.real)
+        R[1] += w * (Rp.real - sg * Rm.real)
+        R[2] += w * (-Rp.imag + sg * Rm.imag)
+        R[3] += w * (Rp.imag + sg * Rm.imag)
+    return R[0], R[1], R[2], R[3]
+
+
+def get_dresponse_dlncl(qe_key, l, cl_key, lmax_ivf, source, cls_weight, cls_cmb, fal_leg1, fal_leg2=None, lmax_ivf2=None,
+                        lmax_out=None):
+    r"""Derivative :math:`dR_L / d\ln C_\ell` of the isotropic response with respect to one multipole of one CMB
+    spectrum (reference: qresp.py:364-374): the response to a spectrum that is zero except for `cls_cmb[cl_key][l]`."""
+    if lmax_ivf2 is None:
+        lmax_ivf2 = lmax_ivf
+    if lmax_out is None:
+        lmax_out = lmax_ivf + lmax_ivf2
+    dcls = {k: np.zeros_like(cls_cmb[k]) for k in cls_cmb}
+    dcls[cl_key][l] = cls_cmb[cl_key][l]
+    qes = get_qes(qe_key, lmax_ivf, cls_weight, lmax2=lmax_ivf2)
+    return _get_response(qes, source, dcls, fal_leg1, lmax_out, fal_leg2=fal_leg2)
+
+
+def get_mf_resp(qe_key, cls_cmb, cls_ivfs, lmax_qe, lmax_out, retterms=False):
+    """Deflection-induced mean-field response of the lensing estimators 'ptt' and 'p_p' (reference: qresp.py:421-500).
+
+    Two groups of Wigner correlation functions: (xi K xi - xi)(K)-like terms, built from the filtered-map spectra and
+    the CMB spectra minus their filtered part, and (xi K)(xi K)-like terms; the L = 1 value of the curl part, which must
+    vanish, is subtracted from both.  Returns (gradient, curl) responses, with the three terms if `retterms`."""
+    assert qe_key in ['p_p', 'ptt'], qe_key
+    if qe_key == 'ptt':
+        lmax_cmb, spins, keys = len(cls_cmb['tt']) - 1, [0], ['tt']
+    else:
+        lmax_cmb, spins, keys = min(len(cls_cmb['ee']) - 1, len(cls_cmb['bb'] - 1)), [-2, 2], ['ee', 'bb']
+    assert lmax_qe <= lmax_cmb
+    n = lmax_qe + 1
+    cl_cic = {k: cls_cmb[k][:n] ** 2 * cls_ivfs[k][:n] for k in keys}      # C F C
+    cl_ci = {k: cls_cmb[k][:n] * cls_ivfs[k][:n] for k in keys}            # C F
+    half = lambda sp: 0.5 if sp != 0 else 1.0     # each B in B Cov^-1 B^dagger maps spin fields to T E B with a factor 1/2
+
+    def ladder(a, sp, lmax):
+        return uspin.get_spin_lower(sp, lmax) if a == -1 else uspin.get_spin_raise(sp, lmax)
+
+    G1, C1 = np.zeros(lmax_out + 1), np.zeros(lmax_out + 1)
+    G2, C2 = np.zeros(lmax_out + 1), np.zeros(lmax_out + 1)
+    for s1 in spins:
+        for s2 in spins:
+            sgn = 2 * (-1) ** (s1 + s2)
+            # (xi K xi - xi)(K)
+            cl1 = uspin.spin_cls(s1, s2, cls_ivfs)[:n] * (half(s1) * half(s2))
+            cl2 = np.copy(uspin.spin_cls(s2, s1, cls_cmb)[:lmax_cmb + 1])
+            cl2[:n] -= uspin.spin_cls(s2, s1, cl_cic)[:n]       # subtracted before the transform: unstable otherwise
+            if np.any(cl1) and np.any(cl2):
+                aj = ladder(-1, -s1, lmax_cmb)
+                for a in (-1, 1):                               # the b = -1 terms follow from the a <-> b symmetry
+                    hL = sgn * uspin.wignerc(cl1, cl2 * ladder(a, s2, lmax_cmb) * aj, s2, s1, -s2 - a, -s1 - 1, lmax_out=lmax_out)
+                    G1 -= a * hL
+                    C1 -= hL
+            # (xi K)(xi K)
+            cl1 = uspin.spin_cls(s2, s1, cl_ci)[:n] * half(s1)
+            cl2 = uspin.spin_cls(s1, s2, cl_ci)[:n] * half(s2)
+            if np.any(cl1) and np.any(cl2):
+                aj = ladder(-1, s1, lmax_qe)
+                for a in (-1, 1):
+                    hL = sgn * uspin.wignerc(cl1 * ladder(a, s2, lmax_qe), cl2 * aj, -s2 - a, -s1, s2, s1 - 1, lmax_out=lmax_out)
+                    G2 -= a * hL
+                    C2 -= hL
+    terms = {'GK': G1.copy(), 'GxiK': -G2}
+    GL, CL = G1 - G2, C1 - C2
+    terms['Gcons'] = -np.ones_like(GL) * CL[1]
+    print("CL[1] ", CL[1])
+    print("GL[1] (before subtraction) ", GL[1])
+    print("GL[1] (after subtraction) ", GL[1] - CL[1])
+    GL = GL - CL[1]
+    CL = CL - CL[1]
+    fac = 0.25 * np.arange(lmax_out + 1) * np.arange(1, lmax_out + 2)
+    GL, CL = GL * fac, CL * fac
+    for k in terms:
+        terms[k] = terms[k] * fac
+    return (GL, CL, terms) if retterms else (GL, CL)
 
 
 def _get_response(qes, source, cls_cmb, fal_leg1, lmax_qlm, fal_leg2=None):

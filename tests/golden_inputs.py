@@ -278,3 +278,12 @@ class fixed_phas:
 
     def get_sim(self, idx, idf=None):
         return [self.q['tlm2'], self.q['elm2'], self.q['blm2']][idf] * (1.0 + idx)
+
+
+RESP2_CUSTOM = [('ptt', 'n'), ('ntt', 'n'), ('stt', 'ntt'), ('ftt', 'n')]
+RESP2_DERIV = [('ptt', 30, 'tt', 'p'), ('p_p', 25, 'ee', 'p'), ('p', 40, 'te', 'p')]
+
+
+def resp_transf(lmax):
+    l = np.arange(lmax + 1, dtype=float)
+    return np.exp(-0.5 * l * (l + 1) * (0.01 ** 2))

@@ -270,3 +270,45 @@ def test_cls_dot_and_dls_conversions_match_reference():
     assert np.allclose(back['tt'][1:5], a['tt'][1:5]) and np.allclose(back['te'][1:6], a['te'][1:6])
     with pytest.raises(NotImplementedError):
         n0s.get_N0_iter('p', 1., 1., 1., {}, 2, 10, 1)
+
+
+def _check_resp2(tol):
+    import golden_inputs as gi
+    from plancklens_b200 import qresp
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_resp2.npz'))
+    r = gi.resp_case()
+    transf = gi.resp_transf(r['lmax'])
+
+    def close(a, ref, what):
+        assert np.max(np.abs(np.array(a) - ref)) <= tol * np.max(np.abs(ref)), what
+    for key, src in gi.RESP2_CUSTOM:
+        R = qresp.get_response(key, r['lmax'], src, r['cls_weight'], r['cls_len'], r['fal_sep'], lmax_qlm=r['lmax_qlm'], transf=transf)
+        close(R, g['custom_%s_%s' % (key, src)], (key, src))
+    for key, l, ck, src in gi.RESP2_DERIV:
+        R = qresp.get_dresponse_dlncl(key, l, ck, r['lmax'], src, r['cls_weight'], r['cls_len'], r['fal_sep'], lmax_out=r['lmax_qlm'])
+        close(R, g['dresp_%s_%d_%s_%s' % (key, l, ck, src)], (key, l, ck))
+    for key in ('ptt', 'p_p'):
+        GL, CL, terms = qresp.get_mf_resp(key, r['cls_len'], r['cls_ivfs_sep'], r['lmax'] - 10, r['lmax_qlm'], retterms=True)
+        # the result is a difference of terms ~1e3 times larger: tolerance relative to the terms
+        scale = np.max(np.abs(g['mf_%s_GK' % key]))
+        assert np.max(np.abs(GL - g['mf_%s_G' % key])) <= tol * scale and np.max(np.abs(CL - g['mf_%s_C' % key])) <= tol * scale
+        assert set(terms) == {'GK', 'GxiK', 'Gcons'}
+        for k, v in terms.items():
+            close(v, g['mf_%s_%s' % (key, k)], (key, k))
+    assert len(qresp.get_mf_resp('ptt', r['cls_len'], r['cls_ivfs_sep'], 20, 30)) == 2
+    with pytest.raises(AssertionError):
+        qresp.get_mf_resp('p', r['cls_len'], r['cls_ivfs_sep'], 20, 30)
+
+
+def test_custom_responses_derivatives_and_mf_response_on_cpu(monkeypatch):
+    """qresp._get_response_custom ('n' source), get_dresponse_dlncl and get_mf_resp against the unmodified reference
+    (tests/golden/make_golden_resp2.py), Wigner seam served by the oracle."""
+    from oracle import ref_wigner
+    from plancklens_b200 import utils_spin as us
+    monkeypatch.setattr(us, 'wignerc', ref_wigner.wignerc)
+    _check_resp2(1e-12)
+
+
+@pytest.mark.gpu
+def test_custom_responses_derivatives_and_mf_response_on_gpu():
+    _check_resp2(1e-9)
