@@ -35,6 +35,19 @@ def map2alm(maps, lmax=None, mmax=None, iter=0, pol=True, **kw):
     return _sht.map2alm(maps, lmax=lmax, mmax=mmax, iter=iter, **kw)
 
 
+def smoothing(map_in, fwhm=0.0, sigma=None, iter=3, lmax=None, **kw):
+    """hp.smoothing of a scalar map: map2alm with healpy's default of 3 refinement passes, Gaussian window, alm2map
+    (plancklens/utils.py:296, :301)"""
+    m = np.asarray(map_in, dtype=float)
+    nside = _rg.npix2nside(m.size)
+    lmax = 3 * nside - 1 if lmax is None else lmax
+    if sigma is None:
+        sigma = fwhm / np.sqrt(8.0 * np.log(2.0))
+    ell = np.arange(lmax + 1)
+    alm = _sht.map2alm(m, lmax=lmax, iter=iter)
+    return _sht.alm2map(almxfl(alm, np.exp(-0.5 * ell * (ell + 1) * sigma ** 2)), nside, lmax=lmax)
+
+
 alm2map_spin = _sht.alm2map_spin
 map2alm_spin = _sht.map2alm_spin
 nside2npix = _rg.nside2npix

@@ -171,15 +171,22 @@ def alm2map(alm, nside, lmax=None, mmax=None, **kw):
 
 
 def map2alm(m, lmax=None, mmax=None, iter=0, **kw):
-    assert iter == 0, 'the reference hot path always passes iter=0'
+    """Uniform-weight analysis; the reference hot path always passes iter=0.  iter > 0 restates the published
+    refinement loop of HEALPix C++ `map2alm_iter` (alm_healpix_tools.cc; what healpy.map2alm(iter=k) runs):
+    alm <- alm + map2alm(map - alm2map(alm)), k times.  Parity of this branch is unpinned (healpy absent)."""
     m = np.asarray(m, dtype=float)
     nside = rg.npix2nside(m.size)
     if lmax is None:
         lmax = 3 * nside - 1
     mmax = lmax if mmax is None else mmax
-    X = map2phase(nside, m, mmax)
-    G, _ = legendre_anal(nside, 0, lmax, mmax, X)
-    return G
+
+    def once(x):
+        G, _ = legendre_anal(nside, 0, lmax, mmax, map2phase(nside, x, mmax))
+        return G
+    alm = once(m)
+    for _ in range(iter):
+        alm = alm + once(m - alm2map(alm, nside, lmax=lmax, mmax=mmax))
+    return alm
 
 
 def alm2map_spin(alms, nside, spin, lmax, mmax=None):

@@ -302,17 +302,72 @@ def alm2map(alms, nside, lmax=None, mmax=None, pol=False, **kw):
     return _plan(nside, lmax).alm2map_host(0, alms)
 
 
-def map2alm(maps, lmax=None, mmax=None, iter=0, pol=False, use_weights=False, **kw):
-    """Single-pass scalar analysis with uniform weights.  reference: plancklens/shts.py:35 (always iter=0)."""
-    if iter != 0 or use_weights:
-        raise NotImplementedError("the reference hot path only calls map2alm(iter=0) without ring weights")
+def map2alm(maps, lmax=None, mmax=None, iter=3, pol=True, use_weights=False, **kw):
+    """Scalar analysis with uniform pixel weights 4 pi / npix and `iter` Jacobi refinement passes
+    alm <- alm + map2alm(map - alm2map(alm)), healpy's signature and default (iter=3).  Every call on the reference's
+    hot path passes iter=0 (plancklens/shts.py:35, opfilt_tt.py:34).  A (T, Q, U) triple with pol=True gives
+    [tlm, elm, blm].  Ring-weight files are not shipped: use_weights=True raises."""
+    if use_weights:
+        raise NotImplementedError("map2alm(use_weights=True) needs healpy's ring-weight data files")
+    if isinstance(maps, (list, tuple)) or np.ndim(maps) == 2:
+        assert len(maps) == 3 and pol, "a list of maps is a (T, Q, U) triple with pol=True"
+        tlm = map2alm(maps[0], lmax=lmax, mmax=mmax, iter=iter)
+        elm, blm = _map2alm_spin_iter(maps[1], maps[2], 2, lmax, iter)
+        return [tlm, elm, blm]
     m = np.asarray(maps, dtype=float)
     assert m.ndim == 1
     nside = npix2nside(m.size)
     if lmax is None:
         lmax = 3 * nside - 1
     assert mmax is None or mmax == lmax
-    return _plan(nside, lmax).map2alm_host(0, m)
+    plan = _plan(nside, lmax)
+    if iter == 0:
+        return plan.map2alm_host(0, m)
+    from . import sht
+    md = sht.dev_map(m)
+    alm = plan.map2alm(md)
+    for _ in range(iter):
+        res = plan.alm2map(alm)
+        res = md - res
+        sht.alm_axpy(alm, plan.map2alm(res), 1.0)
+    return alm.cpu().numpy()
+
+
+def _map2alm_spin_iter(m1, m2, spin, lmax, iter):
+    m1, m2 = np.asarray(m1, dtype=float), np.asarray(m2, dtype=float)
+    nside = npix2nside(m1.size)
+    if lmax is None:
+        lmax = 3 * nside - 1
+    plan = _plan(nside, lmax)
+    if iter == 0:
+        return plan.map2alm_host(spin, m1, m2)
+    from . import sht
+    d1, d2 = sht.dev_map(m1), sht.dev_map(m2)
+    g, c = plan.map2alm_spin(d1, d2, spin)
+    for _ in range(iter):
+        r1, r2 = plan.alm2map_spin(g, c, spin)
+        dg, dc = plan.map2alm_spin(d1 - r1, d2 - r2, spin)
+        sht.alm_axpy(g, dg, 1.0)
+        sht.alm_axpy(c, dc, 1.0)
+    return g.cpu().numpy(), c.cpu().numpy()
+
+
+def smoothing(map_in, fwhm=0.0, sigma=None, beam_window=None, pol=False, iter=3, lmax=None, mmax=None,
+              use_weights=False, **kw):
+    """Gaussian (or `beam_window`) smoothing of a scalar map in harmonic space: map2alm (iter refinement passes, healpy's
+    default 3) -> almxfl -> alm2map.  reference use: utils.apodize_mask (utils.py:296, :301)."""
+    m = np.asarray(map_in, dtype=float)
+    assert m.ndim == 1 and not pol, 'scalar maps only'
+    nside = npix2nside(m.size)
+    if lmax is None:
+        lmax = 3 * nside - 1
+    if sigma is None:
+        sigma = fwhm / np.sqrt(8.0 * np.log(2.0))
+    if beam_window is None:
+        l = np.arange(lmax + 1, dtype=float)
+        beam_window = np.exp(-0.5 * l * (l + 1) * sigma ** 2)
+    alm = map2alm(m, lmax=lmax, mmax=mmax, iter=iter, use_weights=use_weights)
+    return alm2map(almxfl(alm, beam_window), nside, lmax=lmax)
 
 
 def alm2map_spin(alms, nside, spin, lmax, mmax=None):

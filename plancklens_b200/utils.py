@@ -269,3 +269,34 @@ class stats:
             new.sum2 = np.diagonal(new.mom).copy()
         new.N = self.N
         return new
+
+
+def apodize_mask(mask, sigma_arcmin=12., lmax=None, method='hybrid', cache_dir='caches/', mult_factor=3, min_factor=0.1):
+    """Apodizes a mask for pseudo-C_l work (reference: utils.py:270-306): Gaussian smoothing, or 'hybrid' -- smooth, scale
+    (1 - mask) by `mult_factor`, clip, smooth again with half the width, which mostly eats into the unmasked side.
+    The smoothing transforms run on the GPU (`hp.smoothing`)."""
+    import hashlib
+    import os
+    from . import hp
+    if not sigma_arcmin:
+        return mask
+    sigma = sigma_arcmin / 180. / 60. * np.pi
+    name = None
+    if cache_dir:
+        tag = '_'.join('%s' % x for x in [sigma_arcmin, method, lmax, mult_factor, min_factor, hashlib.sha1(mask).hexdigest()])
+        name = os.path.join(cache_dir, 'ap_mask_' + tag) + '.fits'
+        if os.path.exists(name):
+            return hp.read_map(name)
+    print('apodizing... (fsky_unapodized=%s)' % (np.sum(mask ** 2) / mask.size))
+    ap = hp.smoothing(mask, sigma=sigma, lmax=lmax)
+    if method == 'gaussian':
+        return ap
+    if method != 'hybrid':
+        raise ValueError('Unknown apodization method')
+    ap = 1 - np.minimum(1., np.maximum(0., mult_factor * (1 - ap) - min_factor))
+    ap = hp.smoothing(ap, sigma=sigma / 2, lmax=lmax)
+    print('fsky=', np.sum(ap ** 2) / ap.size)
+    if name is not None:
+        os.makedirs(cache_dir, exist_ok=True)
+        hp.write_map(name, ap)
+    return ap

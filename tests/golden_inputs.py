@@ -287,3 +287,12 @@ RESP2_DERIV = [('ptt', 30, 'tt', 'p'), ('p_p', 25, 'ee', 'p'), ('p', 40, 'te', '
 def resp_transf(lmax):
     l = np.arange(lmax + 1, dtype=float)
     return np.exp(-0.5 * l * (l + 1) * (0.01 ** 2))
+
+
+def apo_case(nside=16, lmax=40):
+    """binary mask (galactic-like band + a few holes), a seeded map, and a smoothing scale of a few pixels"""
+    rng = np.random.default_rng(99)
+    z = pix_z(nside)
+    mask = (np.abs(z) > 0.3).astype(float)
+    mask[rng.choice(mask.size, 15, replace=False)] = 0.0
+    return {'nside': nside, 'lmax': lmax, 'mask': mask, 'map': rng.standard_normal(mask.size), 'sigma_arcmin': 400.0}

@@ -187,3 +187,30 @@ def test_gradient_only_synthesis(sht, nside, lmax, spin):
     b = plan.alm2map_spin(g, torch.zeros_like(g), spin, flg=fl)
     for x, y in zip(a, b):
         assert float(torch.linalg.norm(x - y) / torch.linalg.norm(y)) < 1e-13
+
+
+def test_map2alm_refinement_smoothing_and_mask_apodization():
+    """healpy-shaped helpers above the transforms: map2alm(iter=k) (HEALPix map2alm_iter: k Jacobi refinement passes),
+    hp.smoothing and the reference's utils.apodize_mask, against the oracle / the unmodified reference run on the
+    oracle (tests/golden/make_golden_apo.py)."""
+    import os
+    import golden_inputs as gi
+    from plancklens_b200 import hp, utils
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_apo.npz'))
+    a = gi.apo_case()
+    for it in (1, 3):
+        got = hp.map2alm(a['map'], lmax=a['lmax'], iter=it)
+        assert rel_l2(got, g['alm_iter%d' % it]) < 1e-11
+    assert rel_l2(hp.map2alm(a['map'], lmax=a['lmax']), g['alm_iter3']) < 1e-11          # healpy's default is iter=3
+    assert rel_l2(hp.map2alm(a['map'], lmax=a['lmax'], iter=0), g['alm_iter3']) > 1e-3   # and it matters
+    for method in ('gaussian', 'hybrid'):
+        got = utils.apodize_mask(a['mask'], sigma_arcmin=a['sigma_arcmin'], lmax=a['lmax'], method=method, cache_dir=None)
+        assert rel_l2(got, g['apo_' + method]) < 1e-10, method
+    with pytest.raises(ValueError):
+        utils.apodize_mask(a['mask'], sigma_arcmin=a['sigma_arcmin'], lmax=a['lmax'], method='tophat', cache_dir=None)
+    with pytest.raises(NotImplementedError):
+        hp.map2alm(a['map'], lmax=a['lmax'], use_weights=True)
+    # (T, Q, U) triple, pol=True: spin-0 and spin-2 analyses
+    t, e, b = hp.map2alm([a['map'], a['mask'], a['map'] * a['mask']], lmax=a['lmax'], iter=0)
+    e0, b0 = hp.map2alm_spin([a['mask'], a['map'] * a['mask']], 2, lmax=a['lmax'])
+    assert np.array_equal(e, e0) and np.array_equal(b, b0) and np.array_equal(t, hp.map2alm(a['map'], lmax=a['lmax'], iter=0))
