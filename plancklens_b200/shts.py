@@ -17,9 +17,9 @@ def alm2map(alm, nside):
 
 
 def map2alm(m, lmax, **kwargs):
-    """Single-pass analysis with uniform weights (the reference always passes iter=0).  reference: shts.py:16."""
-    kwargs.pop('iter', None)
-    return hp.map2alm(m, lmax=lmax, iter=0, **kwargs)
+    """Analysis with uniform weights; keyword arguments go to `hp.map2alm` as in the reference (every call on its hot
+    path passes iter=0: single pass).  reference: shts.py:16."""
+    return hp.map2alm(m, lmax=lmax, **kwargs)
 
 
 def alm2map_spin(gclm, nside, spin, lmax):
