@@ -290,10 +290,17 @@ def _plan(nside, lmax):
     return sht.get_plan(nside, lmax)
 
 
-def alm2map(alms, nside, lmax=None, mmax=None, pol=False, **kw):
+def alm2map(alms, nside, lmax=None, mmax=None, pol=True, **kw):
     """Scalar synthesis (healpy signature).  reference: plancklens/shts.py:35."""
+    if isinstance(alms, (list, tuple)) or np.ndim(alms) == 2:
+        # (tlm, elm, blm) with pol=True -> [T, Q, U]: a spin-0 and a spin-2 synthesis in the HEALPix polarization
+        # convention (reference use: qcinv/opfilt_tp.py:279)
+        assert len(alms) == 3 and pol, "a list of alms is a (tlm, elm, blm) triple with pol=True"
+        L = Alm.getlmax(np.asarray(alms[0]).size) if lmax is None else lmax
+        q, u = alm2map_spin([alms[1], alms[2]], nside, 2, L)
+        return [alm2map(alms[0], nside, lmax=L), q, u]
     alms = np.asarray(alms)
-    assert alms.ndim == 1, 'only scalar alm2map is on the hot path (use alm2map_spin for polarisation)'
+    assert alms.ndim == 1
     if lmax is None:
         lmax = Alm.getlmax(alms.size)
     assert mmax is None or mmax == lmax

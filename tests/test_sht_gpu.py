@@ -210,6 +210,12 @@ def test_map2alm_refinement_smoothing_and_mask_apodization():
         utils.apodize_mask(a['mask'], sigma_arcmin=a['sigma_arcmin'], lmax=a['lmax'], method='tophat', cache_dir=None)
     with pytest.raises(NotImplementedError):
         hp.map2alm(a['map'], lmax=a['lmax'], use_weights=True)
+    # (tlm, elm, blm) triple, pol=True -> (T, Q, U), and back
+    rng = np.random.default_rng(3)
+    tlm, elm, blm = rand_alm(rng, a['lmax']), rand_alm(rng, a['lmax'], 2), rand_alm(rng, a['lmax'], 2)
+    T, Q, U = hp.alm2map([tlm, elm, blm], a['nside'], pol=True)
+    Q0, U0 = hp.alm2map_spin([elm, blm], a['nside'], 2, a['lmax'])
+    assert np.array_equal(T, hp.alm2map(tlm, a['nside'])) and np.array_equal(Q, Q0) and np.array_equal(U, U0)
     # (T, Q, U) triple, pol=True: spin-0 and spin-2 analyses
     t, e, b = hp.map2alm([a['map'], a['mask'], a['map'] * a['mask']], lmax=a['lmax'], iter=0)
     e0, b0 = hp.map2alm_spin([a['mask'], a['map'] * a['mask']], 2, lmax=a['lmax'])
