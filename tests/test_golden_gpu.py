@@ -387,7 +387,7 @@ def test_qe_term_lists_match_reference_structure():
 def test_qecl_spectra_match_reference():
     """qecl.library (mean-field subtracted QE spectra) against the unmodified reference:
     auto- and cross-spectra within 1e-8 (north_star tolerance for qlm auto-spectra)."""
-    from plancklens_b200 import hp, qecl, qest
+    from plancklens_b200 import hp, qecl, qest, utils
     g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_qecl.npz'))
     q = gi.qe_case()
     with tempfile.TemporaryDirectory() as tmp:
@@ -402,3 +402,12 @@ def test_qecl_spectra_match_reference():
         assert np.max(np.abs(qcl.get_sim_qcl('p', -1) - ref)) < 1e-8 * np.max(np.abs(ref))
         st = qcl.get_sim_stats_qcl('ptt', [0, 5, 6])
         assert st.N == 3 and st.mean().shape == ref.shape
+        assert os.path.exists(os.path.join(tmp, 'qcl', 'sim_qcl_stats_ptt_ptt_%s.pk' % utils.mchash([0, 5, 6])))
+        assert np.array_equal(qcl.get_sim_stats_qcl('ptt', [0, 5, 6]).mean(), st.mean())      # second call: from the cache
+        # average of spectra libraries (reference: qecl.py:151-223)
+        av = qecl.average(os.path.join(tmp, 'qclav'), [qcl, qcl])
+        assert np.allclose(av.get_sim_qcl('ptt', 0), qcl.get_sim_qcl('ptt', 0), rtol=1e-15, atol=0)
+        assert np.allclose(av.get_dat_qcl('p'), qcl.get_sim_qcl('p', -1), rtol=1e-15, atol=0)
+        assert list(av.mc_sims_mf) == [1, 2, 3, 4] and av.get_lmaxqcl('ptt', 'ptt') == qcl.get_lmaxqcl('ptt', 'ptt')
+        sa = av.get_sim_stats_qcl('ptt', [0, 5, 6])
+        assert sa.N == 3 and np.allclose(sa.mean(), st.mean(), rtol=1e-14, atol=0) and np.all(sa.sigmas() >= 0)
