@@ -98,3 +98,35 @@ def test_spin0_against_scipy_spherical_harmonics(oracle_sht):
             c = a[rg.alm_getidx(lmax, l, m)] * sph_harm_y(l, m, theta, phi)
             ref += c.real if m == 0 else 2 * c.real
     assert rel_l2(oracle_sht.alm2map(a, nside, lmax=lmax), ref) < 1e-13
+
+
+def test_healpix_ring_geometry_known_answers():
+    """RING pixel centres against the published HEALPix definition (Gorski et al. 2005, eqs. 2-9; ring pixels start at
+    phi = 0 on unshifted rings, as the twelve base-pixel centres of nside 1 fix: 0-3 at z = 2/3, phi = pi/4 + k pi/2;
+    4-7 on the equator at phi = k pi/2; 8-11 at z = -2/3) written out by hand for nside 1 and 2, plus the structural
+    invariants at nside 64: equal-area rings (z spacing), north / south mirror symmetry, ring lengths."""
+    from oracle import ref_geom as rg
+    th, ph = rg.pix2ang(1)
+    z = np.cos(th)
+    assert np.allclose(z, [2 / 3.] * 4 + [0.] * 4 + [-2 / 3.] * 4, atol=1e-15)
+    assert np.allclose(ph[:4], np.pi / 4 + np.pi / 2 * np.arange(4)) and np.allclose(ph[4:8], np.pi / 2 * np.arange(4))
+    assert np.allclose(ph[8:], ph[:4])
+    th, ph = rg.pix2ang(2)
+    z = np.cos(th)
+    rings = [(4, 1 - 1 / 12.), (8, 1 - 4 / 12.), (8, 4 / 3. - 2 * 3 / 6.), (8, 0.), (8, -1 / 3.), (8, -2 / 3.), (4, -11 / 12.)]
+    o = 0
+    for i, (n, zr) in enumerate(rings, start=1):
+        assert np.allclose(z[o:o + n], zr, atol=1e-15), i
+        shifted = (i < 2 or i > 6) or (i - 2 + 1) % 2 == 1        # caps always; belt rings with (i - nside + 1) odd
+        first = np.pi / n if shifted else 0.0
+        assert np.allclose(ph[o:o + n], first + 2 * np.pi * np.arange(n) / n), i
+        o += n
+    nside = 64
+    nphi, start, zr, sth, phi0 = rg.ring_info(nside)
+    assert nphi.sum() == 12 * nside ** 2 and nphi.size == 4 * nside - 1
+    assert np.allclose(zr, -zr[::-1], atol=1e-15) and np.array_equal(nphi, nphi[::-1])
+    belt = slice(nside - 1, 3 * nside)
+    assert np.allclose(np.diff(zr[belt]), -2.0 / (3 * nside)) and np.all(nphi[belt] == 4 * nside)
+    i = np.arange(1, nside)
+    assert np.allclose(zr[:nside - 1], 1 - i ** 2 / (3.0 * nside ** 2)) and np.array_equal(nphi[:nside - 1], 4 * i)
+    assert np.allclose(sth ** 2 + zr ** 2, 1.0, atol=1e-15)
