@@ -10,7 +10,6 @@ import os
 import re
 import sys
 
-import numpy as np
 import torch
 
 from . import cd_monitors, cd_solve, util, util_alm

@@ -9,8 +9,6 @@ import numpy as np
 import torch
 
 from . import hp, sht
-from . import utils as ut
-from . import utils_spin as uspin
 
 
 class qeleg:
