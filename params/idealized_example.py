@@ -6,7 +6,8 @@ Same structure and object names as the reference's params/idealized_example.py: 
 Differences forced by the environment (SURVEY.md, table of discrepancies): the FFP10 lensed CMB sims on NERSC are
 replaced by Gaussian skies drawn from the FFP10 lensed spectra (`cmbs.sims_cmb_unl`), and the transfer function is
 the 5' beam alone (`hp.pixwin` needs the HEALPix data files).  The spectra / response / bias libraries of the
-reference file (qecl, nhl, n1, qresp) are outside the hot path and not instantiated.
+reference file (qecl, nhl, n1, qresp) are instantiated as there; `n1_dd` serves cached N1 curves only (the flat-sky
+integrator is the reference's Fortran extension, see plancklens_b200/n1/n1.py).
 
 Sizes can be scaled down for tests through the environment: PLK_NSIDE, PLK_LMAX_IVF, PLK_LMAX_QLM, PLK_NSIMS.
 """
@@ -17,6 +18,7 @@ import numpy as np
 import plancklens_b200
 from plancklens_b200 import hp, nhl, qecl, qest, qresp, utils
 from plancklens_b200.filt import filt_simple, filt_util
+from plancklens_b200.n1 import n1
 from plancklens_b200.sims import cmbs, maps, phas, utils as maps_utils
 
 assert 'PLENS' in os.environ.keys(), 'Set env. variable PLENS to a writeable folder'
@@ -94,7 +96,9 @@ qcls_ss = qecl.library(os.path.join(TEMP, 'qcls_ss'), qlms_ss, qlms_ss, mc_sims_
 # ---- semi-analytical Gaussian lensing bias library
 nhl_dd = nhl.nhl_lib_simple(os.path.join(TEMP, 'nhl_dd'), ivfs, cl_weight, lmax_qlm)
 
-# ---- N1 lensing bias library: Fortran extension of the reference (n1.library_n1), not part of this package
+# ---- N1 lensing bias library (constructor, hash and sqlite caches as in the reference; no integrator in this package)
+libdir_n1_dd = os.path.join(TEMP, 'n1_ffp10')
+n1_dd = n1.library_n1(libdir_n1_dd, cl_len['tt'], cl_len['te'], cl_len['ee'])
 
 # ---- QE response calculation library
 qresp_dd = qresp.resp_lib_simple(os.path.join(TEMP, 'qresp'), lmax_ivf, cl_weight, cl_len,

@@ -296,3 +296,26 @@ def apo_case(nside=16, lmax=40):
     mask = (np.abs(z) > 0.3).astype(float)
     mask[rng.choice(mask.size, 15, replace=False)] = 0.0
     return {'nside': nside, 'lmax': lmax, 'mask': mask, 'map': rng.standard_normal(mask.size), 'sigma_arcmin': 400.0}
+
+
+N1_PAIRS = [('ptt', 'ptt'), ('pee', 'ptt'), ('ptt', 'pee'), ('p_p', 'p_p'), ('p', 'ptt'), ('ptt', 'p_tp'), ('p_eb', 'p_eb'),
+            ('x_p', 'xtt'), ('stt', 'stt')]
+
+
+def n1_case(lmax=80, lmaxphi=120, Lmax=60):
+    cls = toy_cls(lmax)
+    l = np.arange(lmax + 1, dtype=float)
+    cut = (l >= 5).astype(float)
+    return {'cltt': cls['tt'], 'clte': cls['te'], 'clee': cls['ee'], 'lmaxphi': lmaxphi, 'Lmax': Lmax,
+            'clpp': 1e-7 / (1.0 + np.arange(lmaxphi + 1.0)) ** 2,
+            'ftl': cut / (1.0 + 0.01 * l), 'fel': cut * 2.0 / (1.0 + 0.02 * l), 'fbl': cut * 3.0 / (1.0 + 0.03 * l),
+            'ftlB': np.where(l >= 8, 1.0, 0.0) / (1.0 + 0.015 * l)}
+
+
+def fake_n1l(L, cl_kind, kA, kB, k_ind, cltt, clte, clee, clttfid, cltefid, cleefid, ftlA, felA, fblA, ftlB, felB, fblB,
+             lminA, lminB, dL, lps):
+    """deterministic stand-in for the Fortran n1f.n1l: depends on every argument a wrong call order would change"""
+    code = lambda k: sum((i + 1) * ord(ch) for i, ch in enumerate(k))
+    return (1e-3 * (code(kA) + 0.37 * code(kB) + 0.11 * ord(k_ind)) * (1.0 + np.cos(L / 9.0)) / (L + 3.0)
+            * (1.0 + np.sum(ftlA) + 2 * np.sum(felA) + 3 * np.sum(fblA) + 5 * np.sum(ftlB) + 7 * np.sum(felB) + 11 * np.sum(fblB))
+            * (1.0 + lminA + 0.5 * lminB) * (1.0 + 0.01 * dL + 1e-3 * len(lps)) * (1.0 + 1e3 * cl_kind[min(int(L), len(cl_kind) - 1)]))

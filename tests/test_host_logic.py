@@ -140,3 +140,26 @@ def test_sim_phases_follow_reference_recipe():
     assert np.array_equal(a, lib.get_sim(4, idf=1)) and not np.array_equal(a, lib.get_sim(5, idf=1))
     big = phas.lib_phas(None, 1, 300).get_sim(0, idf=0)
     assert abs(np.mean(np.abs(big[301:]) ** 2) - 1.0) < 0.02 and abs(np.var(big[:301].real) - 1.0) < 0.2
+
+
+def test_idealized_parameter_file_imports_without_a_gpu(tmp_path):
+    """Constructing every library of the reference-shaped parameter file is host work only (SURVEY.md section 8b:
+    mkdir, hash pickles, sqlite, fsky files): it must import on a machine without a GPU, n1 library included."""
+    import importlib.util
+    env = {'PLENS': str(tmp_path), 'PLK_NSIDE': '64', 'PLK_LMAX_IVF': '96', 'PLK_LMAX_QLM': '128', 'PLK_NSIMS': '4'}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        spec = importlib.util.spec_from_file_location('idealized_example_cpu', os.path.join(root, 'params', 'idealized_example.py'))
+        par = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(par)
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    for name in ('ivfs', 'qlms_dd', 'qlms_ds', 'qlms_ss', 'qcls_dd', 'qcls_ds', 'qcls_ss', 'nhl_dd', 'n1_dd', 'qresp_dd'):
+        assert hasattr(par, name), name
+    base = os.path.join(str(tmp_path), 'temp', 'idealized_example')
+    assert sorted(os.listdir(os.path.join(base, 'n1_ffp10'))) == ['fldb.db', 'n1_hash.pk', 'npdb.db']
+    assert os.path.exists(os.path.join(base, 'qlms_dd', 'fskies.dat')) and os.path.exists(os.path.join(base, 'qlms_dd', 'qe_sim_hash.pk'))
+    assert par.qlms_dd.get_fsky(11) == 1.0 and par.n1_dd.lmaxphi == 2500

@@ -142,3 +142,39 @@ def test_unlensed_cmb_extra_fields():
     assert np.array_equal(alms[0], lib.get_sim_plm(3)) and np.array_equal(alms[1], lib.get_sim_tlm(3))
     with pytest.raises(AssertionError):
         lib.get_sim_olm(3)
+
+
+def test_n1_library_surface_matches_reference(tmp_path):
+    """n1.library_n1 around the (absent) flat-sky integrator: default nodes, key ordering, derived-estimator sums, L
+    sampling and splining, both sqlite caches -- against the unmodified reference given the same stand-in integrator
+    (tests/golden/make_golden_n1.py); and the behaviour without one."""
+    from plancklens_b200.n1 import n1
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_n1.npz'))
+    c = gi.n1_case()
+    lib = n1.library_n1(str(tmp_path / 'n1'), c['cltt'], c['clte'], c['clee'], lmaxphi=c['lmaxphi'])
+    assert np.array_equal(lib.lps, g['lps']) and not n1.HASN1F
+    with pytest.raises(NotImplementedError):
+        lib.get_n1('ptt', 'p', c['clpp'], c['ftl'], c['fel'], c['fbl'], c['Lmax'])
+    calls = []
+
+    def backend(*a):
+        calls.append(a[0])
+        return gi.fake_n1l(*a)
+    lib.n1l = backend
+    for kA, kB in gi.N1_PAIRS:
+        got = lib.get_n1(kA, 'p', c['clpp'], c['ftl'], c['fel'], c['fbl'], c['Lmax'], kB=kB, ftlB=c['ftlB'])
+        assert _eq(got, g['n1_%s_%s' % (kA, kB)], 1e-13), (kA, kB)
+    flat = lib.get_n1('ptt', 'p', c['clpp'], c['ftl'], c['fel'], c['fbl'], c['Lmax'] - 10, n1_flat=lambda ell: ell ** 2 * (ell + 1.) ** 2)
+    assert _eq(flat, g['n1_flat'], 1e-12)
+    # a second library on the same directory serves everything from the sqlite caches, without an integrator
+    lib2 = n1.library_n1(str(tmp_path / 'n1'), c['cltt'], c['clte'], c['clee'], lmaxphi=c['lmaxphi'])
+    got = lib2.get_n1('p', 'p', c['clpp'], c['ftl'], c['fel'], c['fbl'], c['Lmax'], kB='ptt', ftlB=c['ftlB'])
+    assert _eq(got, g['n1_p_ptt'], 1e-13)
+    n = len(calls)
+    assert np.all(lib.get_n1('ptt', 'p', c['clpp'], c['ftl'], c['fel'], c['fbl'], c['Lmax'], ftlB=c['ftlB'], remove_only=True) == 0)
+    assert len(calls) == n
+    # remove_only drops the splined curve only; it is rebuilt from the per-multipole cache, still without an integrator
+    again = lib2.get_n1('ptt', 'p', c['clpp'], c['ftl'], c['fel'], c['fbl'], c['Lmax'], ftlB=c['ftlB'])
+    assert _eq(again, g['n1_ptt_ptt'], 1e-13)
+    with pytest.raises(AssertionError):
+        n1.library_n1(str(tmp_path / 'n1'), 2 * c['cltt'], c['clte'], c['clee'], lmaxphi=c['lmaxphi'])  # hash mismatch
