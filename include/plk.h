@@ -59,6 +59,11 @@ int plk_plan_create(plk_plan **plan, int nside, int lmax, int mmax);
 int plk_plan_destroy(plk_plan *plan);
 /* bytes of device memory currently held by the plan (tables + scratch) */
 long long plk_plan_device_bytes(const plk_plan *plan);
+/* Start threshold 2^exp2 of the on-the-fly Legendre recurrences (default 2^-120; libsharp, which healpy / ducc0 wrap
+ * behind plancklens/shts.py:33-35, starts accumulating at 2^-60).  (l, m, ring) contributions below it are skipped
+ * near the poles; results must not depend on it at the 1e-10 level, which the full-size parity tests check by
+ * varying it.  Rebuilds the per-spin seed tables on next use; exp2 in [-900, -20]. */
+int plk_plan_set_seed_threshold(plk_plan *plan, int exp2);
 int plk_plan_nside(const plk_plan *plan);
 int plk_plan_lmax(const plk_plan *plan);
 

@@ -111,12 +111,17 @@ static inline long double logseed_of(const mtab *t, long double logch, long doub
 
 /* ring pair ip: north ring index rn[ip] (row in phase arrays), south rs[ip] (or -1), x = cos(theta_north),
  * chalf/shalf = natural log of cos/sin(theta_north/2) in long double (so that sin^m is exact to ~m*1e-19).  mstep > 1 computes only every mstep-th m (bounded CPU-baseline sample). */
-int csht_synth(int spin, int lmax, int mmax, int npair, const int *rn, const int *rs,
-               const double *cth, const long double *chalf, const long double *shalf,
-               const dcmplx *almG, const dcmplx *almC, dcmplx *X1, dcmplx *X2, int mstep) {
-  const int pitch = mmax + 1;
+/* Common body: m runs over mlist[0..nm) when mlist != NULL, else over 0, mstep, 2 mstep, ... <= mmax. */
+static int synth_body(int spin, int lmax, int mmax, int npair, const int *rn, const int *rs,
+                      const double *cth, const long double *chalf, const long double *shalf,
+                      const dcmplx *almG, const dcmplx *almC, dcmplx *X1, dcmplx *X2, int mstep,
+                      const int *mlist, int nm) {
+  if (!mlist) nm = mmax / mstep + 1;
+  const int pitch = mlist ? nm : mmax + 1;   /* m-list form: compact phase arrays [ring][nm], column = position in mlist */
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int m = 0; m <= mmax; m += mstep) {
+  for (int im = 0; im < nm; ++im) {
+    const int m = mlist ? mlist[im] : im * mstep;
+    const int col = mlist ? im : m;
     mtab t; mtab_init(&t, lmax, m, spin);
     const dcmplx *g = almG + (size_t)m * (2 * lmax + 1 - m) / 2;   /* g[l] valid for l>=m */
     const dcmplx *c = almC ? almC + (size_t)m * (2 * lmax + 1 - m) / 2 : NULL;
@@ -131,8 +136,8 @@ int csht_synth(int spin, int lmax, int mmax, int npair, const int *rn, const int
           double pn = (x * pc - t.E[l] * pm) * t.invE[l + 1];
           pm = pc; pc = pn;
         }
-        X1[(size_t)rn[ip] * pitch + m] = ev + od;
-        if (rs[ip] >= 0) X1[(size_t)rs[ip] * pitch + m] = ev - od;
+        X1[(size_t)rn[ip] * pitch + col] = ev + od;
+        if (rs[ip] >= 0) X1[(size_t)rs[ip] * pitch + col] = ev - od;
       } else {
         double ppm, ppc, mpm, mpc;
         int lp = ramp(&t, lmax, x, +1.0, logseed_of(&t, chalf[ip], shalf[ip], t.pc, t.ps), t.sgn_p, &ppm, &ppc);
@@ -155,11 +160,11 @@ int csht_synth(int spin, int lmax, int mmax, int npair, const int *rn, const int
             mpm = mpc; mpc = pn;
           }
         }
-        size_t in = (size_t)rn[ip] * pitch + m;
+        size_t in = (size_t)rn[ip] * pitch + col;
         X1[in] = 0.5 * (An_p + An_m);
         X2[in] = -0.5 * I * (An_p - An_m);
         if (rs[ip] >= 0) {
-          size_t is = (size_t)rs[ip] * pitch + m;
+          size_t is = (size_t)rs[ip] * pitch + col;
           X1[is] = 0.5 * (As_p + As_m);
           X2[is] = -0.5 * I * (As_p - As_m);
         }
@@ -170,13 +175,30 @@ int csht_synth(int spin, int lmax, int mmax, int npair, const int *rn, const int
   return 0;
 }
 
+int csht_synth(int spin, int lmax, int mmax, int npair, const int *rn, const int *rs,
+               const double *cth, const long double *chalf, const long double *shalf,
+               const dcmplx *almG, const dcmplx *almC, dcmplx *X1, dcmplx *X2, int mstep) {
+  return synth_body(spin, lmax, mmax, npair, rn, rs, cth, chalf, shalf, almG, almC, X1, X2, mstep, NULL, 0);
+}
+/* only the m of mlist[0..nm), with COMPACT phase arrays X[ring][nm] (column = position in mlist): full-size parity
+ * samples that must include m ~ lmax and chosen m in between */
+int csht_synth_mlist(int spin, int lmax, int mmax, int npair, const int *rn, const int *rs,
+                     const double *cth, const long double *chalf, const long double *shalf,
+                     const dcmplx *almG, const dcmplx *almC, dcmplx *X1, dcmplx *X2, const int *mlist, int nm) {
+  return synth_body(spin, lmax, mmax, npair, rn, rs, cth, chalf, shalf, almG, almC, X1, X2, 1, mlist, nm);
+}
+
 /* weight[ip] multiplies both rings of the pair (4 pi / npix for HEALPix). */
-int csht_anal(int spin, int lmax, int mmax, int npair, const int *rn, const int *rs,
-              const double *cth, const long double *chalf, const long double *shalf, const double *weight,
-              const dcmplx *X1, const dcmplx *X2, dcmplx *almG, dcmplx *almC, int mstep) {
-  const int pitch = mmax + 1;
+static int anal_body(int spin, int lmax, int mmax, int npair, const int *rn, const int *rs,
+                     const double *cth, const long double *chalf, const long double *shalf, const double *weight,
+                     const dcmplx *X1, const dcmplx *X2, dcmplx *almG, dcmplx *almC, int mstep,
+                     const int *mlist, int nm) {
+  if (!mlist) nm = mmax / mstep + 1;
+  const int pitch = mlist ? nm : mmax + 1;   /* m-list form: compact phase arrays [ring][nm], column = position in mlist */
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int m = 0; m <= mmax; m += mstep) {
+  for (int im = 0; im < nm; ++im) {
+    const int m = mlist ? mlist[im] : im * mstep;
+    const int col = mlist ? im : m;
     mtab t; mtab_init(&t, lmax, m, spin);
     dcmplx *g = almG + (size_t)m * (2 * lmax + 1 - m) / 2;
     dcmplx *c = almC ? almC + (size_t)m * (2 * lmax + 1 - m) / 2 : NULL;
@@ -184,9 +206,9 @@ int csht_anal(int spin, int lmax, int mmax, int npair, const int *rn, const int 
     dcmplx *am = (dcmplx *)calloc(lmax + 1, sizeof(dcmplx));
     for (int ip = 0; ip < npair; ++ip) {
       double x = cth[ip], w = weight[ip];
-      size_t in = (size_t)rn[ip] * pitch + m;
+      size_t in = (size_t)rn[ip] * pitch + col;
       if (spin == 0) {
-        dcmplx fn = w * X1[in], fs = rs[ip] >= 0 ? w * X1[(size_t)rs[ip] * pitch + m] : 0;
+        dcmplx fn = w * X1[in], fs = rs[ip] >= 0 ? w * X1[(size_t)rs[ip] * pitch + col] : 0;
         dcmplx fe = fn + fs, fo = fn - fs;
         double pm, pc;
         int l = ramp(&t, lmax, x, 0.0, logseed_of(&t, chalf[ip], shalf[ip], t.pc, t.ps), t.sgn_p, &pm, &pc);
@@ -199,7 +221,7 @@ int csht_anal(int spin, int lmax, int mmax, int npair, const int *rn, const int 
         dcmplx pn_ = w * (X1[in] + I * X2[in]), mn_ = w * (X1[in] - I * X2[in]);
         dcmplx ps_ = 0, ms_ = 0;
         if (rs[ip] >= 0) {
-          size_t is = (size_t)rs[ip] * pitch + m;
+          size_t is = (size_t)rs[ip] * pitch + col;
           ps_ = w * (X1[is] + I * X2[is]); ms_ = w * (X1[is] - I * X2[is]);
         }
         double ppm, ppc, mpm, mpc;
@@ -235,6 +257,17 @@ int csht_anal(int spin, int lmax, int mmax, int npair, const int *rn, const int 
     mtab_free(&t);
   }
   return 0;
+}
+
+int csht_anal(int spin, int lmax, int mmax, int npair, const int *rn, const int *rs,
+              const double *cth, const long double *chalf, const long double *shalf, const double *weight,
+              const dcmplx *X1, const dcmplx *X2, dcmplx *almG, dcmplx *almC, int mstep) {
+  return anal_body(spin, lmax, mmax, npair, rn, rs, cth, chalf, shalf, weight, X1, X2, almG, almC, mstep, NULL, 0);
+}
+int csht_anal_mlist(int spin, int lmax, int mmax, int npair, const int *rn, const int *rs,
+                    const double *cth, const long double *chalf, const long double *shalf, const double *weight,
+                    const dcmplx *X1, const dcmplx *X2, dcmplx *almG, dcmplx *almC, const int *mlist, int nm) {
+  return anal_body(spin, lmax, mmax, npair, rn, rs, cth, chalf, shalf, weight, X1, X2, almG, almC, 1, mlist, nm);
 }
 
 int csht_max_threads(void) {

@@ -39,6 +39,8 @@ def _lib():
         ldp = ctypes.POINTER(ctypes.c_longdouble)
         L.csht_synth.argtypes = [ctypes.c_int] * 4 + [ip, ip, dp, ldp, ldp, vp, vp, vp, vp, ctypes.c_int]
         L.csht_anal.argtypes = [ctypes.c_int] * 4 + [ip, ip, dp, ldp, ldp, dp, vp, vp, vp, vp, ctypes.c_int]
+        L.csht_synth_mlist.argtypes = [ctypes.c_int] * 4 + [ip, ip, dp, ldp, ldp, vp, vp, vp, vp, ip, ctypes.c_int]
+        L.csht_anal_mlist.argtypes = [ctypes.c_int] * 4 + [ip, ip, dp, ldp, ldp, dp, vp, vp, vp, vp, ip, ctypes.c_int]
         L.csht_max_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -109,6 +111,42 @@ def legendre_anal(nside, spin, lmax, mmax, X1, X2=None, mstep=1):
                      _p(g.cth, ctypes.c_double), _p(g.lchalf, ctypes.c_longdouble), _p(g.lshalf, ctypes.c_longdouble),
                      _p(g.weight, ctypes.c_double), X1.ctypes.data, X2.ctypes.data if spin > 0 else None,
                      G.ctypes.data, C.ctypes.data if spin > 0 else None, mstep)
+    return G, C
+
+
+def legendre_synth_mlist(nside, spin, lmax, almG, almC, mlist):
+    """Legendre synthesis of the m in `mlist` only -> COMPACT phase arrays X1 (, X2) of shape [nring, len(mlist)]
+    (full-size parity samples: a handful of m, including m ~ lmax, cost seconds where the whole band costs minutes)."""
+    g = _Geom.get(nside)
+    ml = np.ascontiguousarray(mlist, dtype=np.int32)
+    almG = np.ascontiguousarray(almG, dtype=np.complex128)
+    X1 = np.zeros((g.nring, ml.size), dtype=np.complex128)
+    X2 = np.zeros((g.nring, ml.size), dtype=np.complex128) if spin > 0 else None
+    if spin > 0:
+        almC = np.ascontiguousarray(almC, dtype=np.complex128)
+    _lib().csht_synth_mlist(spin, lmax, lmax, g.npair, _p(g.rn, ctypes.c_int), _p(g.rs, ctypes.c_int),
+                            _p(g.cth, ctypes.c_double), _p(g.lchalf, ctypes.c_longdouble), _p(g.lshalf, ctypes.c_longdouble),
+                            almG.ctypes.data, almC.ctypes.data if spin > 0 else None,
+                            X1.ctypes.data, X2.ctypes.data if spin > 0 else None, _p(ml, ctypes.c_int), ml.size)
+    return X1, X2
+
+
+def legendre_anal_mlist(nside, spin, lmax, X1, X2, mlist):
+    """Legendre analysis of the m in `mlist` only, from COMPACT phase arrays [nring, len(mlist)] (weights 4 pi / npix
+    applied here) -> full-size alm arrays, zero at every other m."""
+    g = _Geom.get(nside)
+    ml = np.ascontiguousarray(mlist, dtype=np.int32)
+    nalm = rg.alm_getsize(lmax, lmax)
+    G = np.zeros(nalm, dtype=np.complex128)
+    C = np.zeros(nalm, dtype=np.complex128) if spin > 0 else None
+    X1 = np.ascontiguousarray(X1, dtype=np.complex128)
+    assert X1.shape == (g.nring, ml.size)
+    if spin > 0:
+        X2 = np.ascontiguousarray(X2, dtype=np.complex128)
+    _lib().csht_anal_mlist(spin, lmax, lmax, g.npair, _p(g.rn, ctypes.c_int), _p(g.rs, ctypes.c_int),
+                           _p(g.cth, ctypes.c_double), _p(g.lchalf, ctypes.c_longdouble), _p(g.lshalf, ctypes.c_longdouble),
+                           _p(g.weight, ctypes.c_double), X1.ctypes.data, X2.ctypes.data if spin > 0 else None,
+                           G.ctypes.data, C.ctypes.data if spin > 0 else None, _p(ml, ctypes.c_int), ml.size)
     return G, C
 
 

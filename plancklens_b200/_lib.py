@@ -15,6 +15,7 @@ _SIGS = {
     'plk_plan_create': (c_int, [ctypes.POINTER(vp), c_int, c_int, c_int]),
     'plk_plan_destroy': (c_int, [vp]),
     'plk_plan_device_bytes': (c_ll, [vp]),
+    'plk_plan_set_seed_threshold': (c_int, [vp, c_int]),
     'plk_plan_nside': (c_int, [vp]),
     'plk_plan_lmax': (c_int, [vp]),
     'plk_alm2map_dev': (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, vp]),

@@ -93,6 +93,7 @@ struct plk_plan {
   int *morder = nullptr;
   std::vector<void *> owned;
   SpinDev spins[4];
+  int seed_thr_exp = kSeedThrExp;
   DevBuf X1, X2, rec, part, partial, hostio[4];
   long long table_bytes = 0;
 };
@@ -319,6 +320,21 @@ extern "C" long long plk_plan_device_bytes(const plk_plan *p) {
   for (auto &x : p->hostio) b += (long long)x.bytes;
   return b;
 }
+// Start threshold of the Legendre recurrences (2^exp2): drops the per-spin tables so that they are rebuilt with the
+// new value on next use.  Not to be called while a captured CUDA graph still refers to this plan's tables.
+extern "C" int plk_plan_set_seed_threshold(plk_plan *p, int exp2) {
+  if (!p) return fail(PLK_EINVAL, "plan is NULL");
+  if (exp2 > -20 || exp2 < -900) return fail(PLK_EINVAL, "threshold exponent %d outside [-900, -20]", exp2);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(PLK_ECUDA, "cudaDeviceSynchronize failed: %s", cudaGetErrorString(e));
+  for (auto &s : p->spins) {
+    for (void *q : s.owned) cudaFree(q);
+    s.owned.clear();
+    s.ready = false;
+  }
+  p->seed_thr_exp = exp2;
+  return PLK_OK;
+}
 extern "C" int plk_plan_nside(const plk_plan *p) { return p ? p->nside : 0; }
 extern "C" int plk_plan_lmax(const plk_plan *p) { return p ? p->lmax : 0; }
 
@@ -334,7 +350,7 @@ static int ensure_spin(plk_plan *p, int spin) {
   std::vector<double2> uv(n);
   for (size_t i = 0; i < n; ++i) uv[i] = make_double2(t.U[i], t.V[i]);
   DevSpin &d = sd.d;
-  d.spin = spin; d.lmax = p->lmax; d.mmax = p->mmax;
+  d.spin = spin; d.lmax = p->lmax; d.mmax = p->mmax; d.thr_exp = p->seed_thr_exp;
   int rc;
   double2 *duv; double *dd; int *di; signed char *dc;
 #define UPS(vec, ptr, field) do { rc = upload(p, vec, &ptr, &sd.owned); if (rc) return rc; field = ptr; } while (0)

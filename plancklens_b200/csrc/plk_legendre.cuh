@@ -37,7 +37,8 @@ constexpr int kChunk = PLK_CHUNK;      // l values per TMA stage (even)
 constexpr int kStages = 4;
 constexpr int kNCW = 4;          // compute warps per block
 constexpr int kLegThreads = (kNCW + PLK_PRODUCER_WARP) * 32;
-constexpr int kSeedThrExp = -120;  // accumulation starts once |p_l| >= 2^-120 (libsharp itself uses 2^-60)
+constexpr int kSeedThrExp = -120;  // default start threshold: accumulation starts once |p_l| >= 2^-120 (libsharp itself
+                                   // uses 2^-60); per plan through plk_plan_set_seed_threshold (parity tests vary it)
 
 struct DevGeom {
   int nside, npair, nring;
@@ -48,6 +49,7 @@ struct DevGeom {
 
 struct DevSpin {
   int spin, lmax, mmax;
+  int thr_exp;             // start threshold exponent (kSeedThrExp unless the plan overrides it)
   const double2 *UV;       // [alm_idx]
   const double *alpha;     // [alm_idx]
   const double *k_hi, *k_lo;
@@ -145,8 +147,8 @@ PLK_HD void seed_one(const DevGeom &g, const DevSpin &t, int m, int ip, int &ks_
   for (;;) {
     if ((k & 1) == 0) {
       // true magnitudes: |a_c| * 2^e ; a_c in [2^-129, 2^128] (or 0)
-      bool okp = (ap_c != 0.0) && (ilogb(ap_c) + ep >= kSeedThrExp);
-      bool okm = SPIN && (am_c != 0.0) && (ilogb(am_c) + em >= kSeedThrExp);
+      bool okp = (ap_c != 0.0) && (ilogb(ap_c) + ep >= t.thr_exp);
+      bool okm = SPIN && (am_c != 0.0) && (ilogb(am_c) + em >= t.thr_exp);
       if (okp || okm) break;
     }
     if (k >= K - 1) { ks_out = K; return; }   // never reaches the threshold inside the band: pair skipped for this m

@@ -4,6 +4,11 @@ The reference strides jobs over MPI ranks (`jobs[rank::size]`) and only ever use
 Here one process drives one GPU: when launched under torchrun (RANK / WORLD_SIZE in the environment) rank and
 size come from there and `barrier` maps to torch.distributed (NCCL on GPUs, gloo on CPU-only hosts);
 otherwise the single-rank stubs of the reference apply.
+
+rank, size and barrier always go together, as in the reference (mpi.py:30-36): with WORLD_SIZE > 1 the first
+`barrier` / `bcast` / `allreduce_sum` JOINS the process group torchrun described (lazily, so that importing this
+module stays free), and raises if that is impossible -- a rank != 0 never runs past a dummy barrier into files rank 0
+is still writing (`if mpi.rank == 0: ...; mpi.barrier()` blocks of qest, qecl, filt_*, nhl, qresp, n1, sql).
 """
 import os
 
@@ -13,8 +18,26 @@ ANY_SOURCE = 0
 
 
 def _dist():
+    """torch.distributed once a process group exists; joins it on first use when launched with WORLD_SIZE > 1"""
     import torch.distributed as dist
-    return dist if dist.is_available() and dist.is_initialized() else None
+    if not dist.is_available():
+        if size > 1:
+            raise RuntimeError("WORLD_SIZE = %d but torch.distributed is unavailable: no barrier exists" % size)
+        return None
+    if not dist.is_initialized():
+        if size <= 1:
+            return None
+        init()          # raises if the rendezvous variables are missing
+    return dist
+
+
+def require_group():
+    """Raises unless collectives are real: single process, or a joined process group whose size matches `size`."""
+    d = _dist()
+    if size > 1:
+        if d is None or d.get_world_size() != size:
+            raise RuntimeError("mpi.size = %d but the process group has %s ranks"
+                               % (size, 'no' if d is None else d.get_world_size()))
 
 
 def barrier():
@@ -34,7 +57,7 @@ def bcast(obj, root=0):
 
 
 def allreduce_sum(arr):
-    """Sum of a numpy array over ranks (the mean-field reduction of qest.py:239-243 when simulations are sharded).
+    """Sum of a numpy array over ranks (the sharded mean-field reduction, qest.library.get_sim_qlm_mf_sharded).
     NCCL when a GPU is present (the array is staged on the current device), gloo otherwise; identity on one rank."""
     d = _dist()
     if d is None or d.get_world_size() == 1:
@@ -56,6 +79,10 @@ def init(backend=None):
     import torch
     import torch.distributed as dist
     if int(os.environ.get('WORLD_SIZE', 1)) > 1 and not dist.is_initialized():
+        for var in ('MASTER_ADDR', 'MASTER_PORT', 'RANK'):
+            if var not in os.environ:
+                raise RuntimeError("WORLD_SIZE = %s but %s is not set: cannot join the process group (launch with "
+                                   "torchrun, or unset WORLD_SIZE for a single process)" % (os.environ['WORLD_SIZE'], var))
         if backend is None:
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
         if backend == 'nccl':
@@ -75,7 +102,7 @@ def receive(_, source):
 
 
 def finalize():
-    d = _dist()
-    if d is not None:
-        d.destroy_process_group()
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
     return -1

@@ -401,3 +401,22 @@ def map2alm_spin(maps, spin, lmax=None, mmax=None):
     assert mmax is None or mmax == lmax
     a1, a2 = _plan(nside, lmax).map2alm_host(spin, m1, m2)
     return [a1, a2]
+
+
+def install_as_healpy(force=False):
+    """Registers this module as `healpy` in `sys.modules` when no real healpy can be imported, so that a parameter file
+    written for the reference (`import healpy as hp`, reference params/idealized_example.py:24) runs unchanged on a
+    machine without healpy.  A real healpy is never shadowed unless `force`.  Returns the module now serving `healpy`."""
+    import importlib.util
+    import sys
+    if not force:
+        if 'healpy' in sys.modules:
+            return sys.modules['healpy']
+        try:
+            if importlib.util.find_spec('healpy') is not None:
+                import healpy
+                return healpy
+        except (ImportError, ValueError):
+            pass
+    sys.modules['healpy'] = sys.modules[__name__]
+    return sys.modules['healpy']

@@ -2,8 +2,8 @@
 
 Combines two `qest.library` instances and a set of mean-field simulations into raw spectra
 :math:`\\frac{1}{(2L+1) f_{sky}} \\sum_M \\hat\\phi^A_{LM} \\hat\\phi^{B\\dagger}_{LM}` after mean-field subtraction.  The
-subtraction and `alm2cl` run on the GPU (`plk_alm_axpy_dev`, `plk_alm2cl_dev`); spectra are cached as `.npy` files
-under the reference's names (the reference keeps them in a sqlite `npdb`).
+subtraction and `alm2cl` run on the GPU (`plk_alm_axpy_dev`, `plk_alm2cl_dev`); spectra are cached in the reference's
+sqlite `npdb` (`cldb.db`) under the reference's key strings, so caches are interchangeable.
 """
 import os
 import pickle as pk
@@ -11,7 +11,7 @@ import pickle as pk
 import numpy as np
 
 from . import sht, utils
-from .helpers import mpi
+from .helpers import mpi, sql
 
 
 class library(object):
@@ -43,6 +43,7 @@ class library(object):
         mpi.barrier()
         with open(hname, 'rb') as f:
             utils.hash_check(pk.load(f), self.hashdict(), fn=hname)
+        self.npdb = sql.npdb(os.path.join(lib_dir, 'cldb.db'))     # the reference's cache, same keys (qecl.py:61)
         fskies = {}
         with open(fsname) as f:
             for line in f:
@@ -75,8 +76,12 @@ class library(object):
         assert lmax_out <= lmax_qcl
         tag = '%04d' % idx if idx >= 0 else 'dat'
         assert idx >= -1
-        fname = os.path.join(self.lib_dir, 'sim_qcl_k1%s_k2%s_lmax%s_%s_%s.npy' % (k1, k2, lmax_qcl, tag, self._mcmf_hash()))
-        if calc and (recache or not os.path.exists(fname)):
+        # key strings and recache semantics of the reference (qecl.py:101-119): spectra live in the sqlite npdb
+        # `cldb.db`, so a lib_dir written by either code serves the other
+        fname = os.path.join(self.lib_dir, 'sim_qcl_k1%s_k2%s_lmax%s_%s_%s.dat' % (k1, k2, lmax_qcl, tag, self._mcmf_hash()))
+        if calc:
+            recache = False
+        if calc and (self.npdb.get(fname) is None or recache):
             qlmA = sht.dev_alm(self.qeA.get_sim_qlm(k1, idx, lmax=lmax_qcl))
             if (k1 == k2) and (self.qeA is self.qeB):
                 qlmB = qlmA.clone()
@@ -84,8 +89,10 @@ class library(object):
                 qlmB = sht.dev_alm(self.qeB.get_sim_qlm(k2, idx, lmax=lmax_qcl))
             sht.alm_axpy(qlmA, sht.dev_alm(self.qeA.get_sim_qlm_mf(k1, self.mc_sims_mf[0::2], lmax=lmax_qcl)), -1.0)
             sht.alm_axpy(qlmB, sht.dev_alm(self.qeB.get_sim_qlm_mf(k2, self.mc_sims_mf[1::2], lmax=lmax_qcl)), -1.0)
-            np.save(fname, self._alm2clfsky1234(qlmA, qlmB, k1, k2))
-        return np.load(fname)[:lmax_out + 1] / self.fskies[1234]
+            if recache and self.npdb.get(fname) is not None:
+                self.npdb.remove(fname)
+            self.npdb.add(fname, self._alm2clfsky1234(qlmA, qlmB, k1, k2))
+        return self.npdb.get(fname)[:lmax_out + 1] / self.fskies[1234]
 
     def get_dat_qcl(self, k1, k2=None, lmax=None, recache=False):
         """QE (cross-)power spectrum of the data maps (index -1); `qecl.average.get_dat_qcl` calls it, although the

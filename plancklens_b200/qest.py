@@ -313,11 +313,39 @@ class library:
         assert k in self.keys_fund, (k, self.keys_fund)
         fname = os.path.join(self.lib_dir, 'simMF_k1%s_%s.fits' % (k, ut.mchash(mc_sims)))
         if not os.path.exists(fname):
+            # a purely LOCAL call, as in the reference: the calling rank averages all of mc_sims itself.  Drivers hand
+            # different (k, mc_sims) jobs to different ranks (examples/run_qlms.py:92-94) and qecl.get_sim_qcl calls
+            # this from rank-strided loops (qecl.py:85-86), so a collective hidden here would pair up unrelated
+            # reductions or hang.  The sharded form is `get_sim_qlm_mf_sharded`, which says so in its name.
             this_mcs = np.unique(mc_sims)
             MF = np.zeros(hp.Alm.getsize(lmax), dtype=complex)
             if len(this_mcs) == 0:
                 return MF
-            # simulations are strided over ranks (reference pattern: examples/run_qlms.py:72), then summed
+            for idx in this_mcs:
+                MF += self.get_sim_qlm(k, idx, lmax=lmax)
+            MF /= len(this_mcs)
+            _write_alm(fname, MF)
+        return ut.alm_copy(hp.read_alm(fname), lmax=lmax)
+
+    def get_sim_qlm_mf_sharded(self, k, mc_sims, lmax=None):
+        """COLLECTIVE mean field of a fundamental key: every rank of the process group must call it with the same
+        arguments.  Simulations are strided over ranks (`this_mcs[rank::size]`, the pattern of
+        examples/run_qlms.py:72), the partial sums are reduced over NCCL / gloo -- the serial loop of qest.py:239-243
+        made parallel -- rank 0 writes the reference's cache file and all ranks return the
+        same array.  Not a drop-in for `get_sim_qlm_mf`, which stays local."""
+        k = self.keys_remaps.get(k, k)
+        if lmax is None:
+            lmax = self.get_lmax_qlm(k)
+        assert lmax <= self.get_lmax_qlm(k)
+        assert k in self.keys_fund, (k, self.keys_fund)
+        mpi.require_group()      # raises when WORLD_SIZE > 1 but no process group can be joined
+        fname = os.path.join(self.lib_dir, 'simMF_k1%s_%s.fits' % (k, ut.mchash(mc_sims)))
+        have = mpi.bcast(os.path.exists(fname) if mpi.rank == 0 else None, root=0)
+        if not have:
+            this_mcs = np.unique(mc_sims)
+            MF = np.zeros(hp.Alm.getsize(lmax), dtype=complex)
+            if len(this_mcs) == 0:
+                return MF
             for idx in this_mcs[mpi.rank::mpi.size]:
                 MF += self.get_sim_qlm(k, idx, lmax=lmax)
             MF = mpi.allreduce_sum(MF) / len(this_mcs)

@@ -90,6 +90,10 @@ class Plan:
         check(self.lib.plk_plan_active_fraction(self._h, int(spin), ctypes.byref(v)))
         return float(v.value)
 
+    def set_seed_threshold(self, exp2):
+        """start threshold 2^exp2 of the Legendre recurrences (default 2^-120); seed tables are rebuilt on next use"""
+        check(self.lib.plk_plan_set_seed_threshold(self._h, int(exp2)))
+
     def device_bytes(self):
         return int(self.lib.plk_plan_device_bytes(self._h))
 

@@ -84,7 +84,7 @@ void build_spin(const HostGeom &hg, int spin, int lmax, HostSpin &hs) {
   hs.uv.resize(hs.t.U.size());
   for (size_t i = 0; i < hs.uv.size(); ++i) hs.uv[i] = make_double2(hs.t.U[i], hs.t.V[i]);
   DevSpin &d = hs.d;
-  d.spin = spin; d.lmax = lmax; d.mmax = lmax; d.UV = hs.uv.data(); d.alpha = hs.t.alpha.data();
+  d.spin = spin; d.lmax = lmax; d.mmax = lmax; d.thr_exp = kSeedThrExp; d.UV = hs.uv.data(); d.alpha = hs.t.alpha.data();
   d.k_hi = hs.t.k_hi.data(); d.k_lo = hs.t.k_lo.data(); d.k_e = hs.t.k_e.data(); d.pc = hs.t.pc.data();
   d.ps = hs.t.ps.data(); d.sg_p = hs.t.sg_p.data(); d.sg_m = hs.t.sg_m.data();
   DevGeom &g = hs.g;

@@ -319,3 +319,109 @@ def fake_n1l(L, cl_kind, kA, kB, k_ind, cltt, clte, clee, clttfid, cltefid, clee
     return (1e-3 * (code(kA) + 0.37 * code(kB) + 0.11 * ord(k_ind)) * (1.0 + np.cos(L / 9.0)) / (L + 3.0)
             * (1.0 + np.sum(ftlA) + 2 * np.sum(felA) + 3 * np.sum(fblA) + 5 * np.sum(ftlB) + 7 * np.sum(felB) + 11 * np.sum(fblB))
             * (1.0 + lminA + 0.5 * lminB) * (1.0 + 0.01 * dL + 1e-3 * len(lps)) * (1.0 + 1e3 * cl_kind[min(int(L), len(cl_kind) - 1)]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Config-3 filter libraries (filt_cinv.cinv_t / cinv_p / library_cinv_sepTP) at the smallest size their constructors
+# accept (nside 512, lmax 1024: reference filt_cinv.py:77, :228) with the DEFAULT chains.
+def camb_cls(path, lmax):
+    """columns l, TT, EE, BB, TE in l(l+1)C_l/2pi (reference utils.camb_clfile, utils.py:308-333), restated so that both
+    sides read the same numbers without importing each other's loader"""
+    d = np.loadtxt(path).T
+    ell = np.int_(d[0])
+    w = ell * (ell + 1) / (2. * np.pi)
+    cls = {}
+    for k, col in (('tt', 1), ('ee', 2), ('bb', 3), ('te', 4)):
+        c = np.zeros(lmax + 1)
+        idc = ell <= lmax
+        c[ell[idc]] = d[col][idc] / w[idc]
+        cls[k] = c
+    return cls
+
+
+def cinv_case(alm2map, alm2map_spin, clpath, nside=512, lmax=1024, seed=512):
+    """Masked anisotropic-noise sky of SURVEY.md section 8d: |z| < sin 20 deg cut plus 400 seeded discs of ~15' radius,
+    n_inv = mask (vamin / nlev)^2 (1 + 0.5 z^2), 5' beam, 35 / 55 uK-arcmin, data = Gaussian CMB (fiducial lensed
+    spectra) * beam + white noise drawn in pixel space.  `alm2map`, `alm2map_spin` are the CPU oracle's on both the
+    reference side (tests/golden/make_golden_cinv.py) and the test side, so both see bit-identical maps."""
+    rng = np.random.default_rng(seed)
+    npix = 12 * nside ** 2
+    cls = camb_cls(clpath, lmax)
+    ell = np.arange(lmax + 1, dtype=float)
+    sigma = (5. / 60. / 180. * np.pi) / np.sqrt(8. * np.log(2.))
+    transf = np.exp(-0.5 * ell * (ell + 1) * sigma ** 2)
+    z = pix_z(nside)
+    mask = (np.abs(z) >= np.sin(np.deg2rad(20.))).astype(float)
+    # discs: pixels within 15' of seeded centres, from ring geometry (phi of each pixel)
+    phi = pix_phi(nside)
+    sth = np.sqrt(1. - z ** 2)
+    vec = np.stack([sth * np.cos(phi), sth * np.sin(phi), z])
+    zc = rng.uniform(-1, 1, 400)
+    pc = rng.uniform(0, 2 * np.pi, 400)
+    sc = np.sqrt(1 - zc ** 2)
+    cen = np.stack([sc * np.cos(pc), sc * np.sin(pc), zc])
+    cosr = np.cos(np.deg2rad(15. / 60.))
+    for j in range(400):
+        band = np.abs(z - zc[j]) < 0.01           # cheap pre-cut
+        idx = np.where(band)[0]
+        hit = idx[(cen[:, j] @ vec[:, idx]) > cosr]
+        mask[hit] = 0.
+    nlev_t, nlev_p = 35., 55.
+    vamin = np.sqrt(4. * np.pi / npix) * 180. * 60. / np.pi
+    ninv_t = mask * (vamin / nlev_t) ** 2 * (1. + 0.5 * z ** 2)
+    ninv_p = mask * (vamin / nlev_p) ** 2 * (1. + 0.5 * z ** 2)
+    # CMB: independent T, E, B phases coloured by TT / EE / BB (TE correlation is irrelevant to separate filtering)
+    ls = alm_ls(lmax)
+    tlm = rand_alm(rng, lmax) * np.sqrt(0.5 * cls['tt'])[ls] * transf[ls]
+    elm = rand_alm(rng, lmax, 2) * np.sqrt(0.5 * cls['ee'])[ls] * transf[ls]
+    blm = rand_alm(rng, lmax, 2) * np.sqrt(0.5 * cls['bb'])[ls] * transf[ls]
+    for a in (tlm, elm, blm):
+        a[:lmax + 1] *= np.sqrt(2.)
+    tmap = np.asarray(alm2map(tlm, nside)) + rng.standard_normal(npix) * (nlev_t / vamin)
+    q, u = alm2map_spin([elm, blm], nside, 2, lmax)
+    qmap = np.asarray(q) + rng.standard_normal(npix) * (nlev_p / vamin)
+    umap = np.asarray(u) + rng.standard_normal(npix) * (nlev_p / vamin)
+    return {'nside': nside, 'lmax': lmax, 'cls': cls, 'transf': transf, 'mask': mask,
+            'ninv_t': [ninv_t], 'ninv_p': [[ninv_p]], 'tmap': tmap, 'qmap': qmap, 'umap': umap}
+
+
+def pix_phi(nside):
+    """phi of every RING pixel (ring geometry only)."""
+    N = nside
+    phi = np.empty(12 * N * N)
+    p = 0
+    for i in range(1, 4 * N):
+        if i < N:
+            n, sh = 4 * i, 1
+        elif i <= 3 * N:
+            n, sh = 4 * N, 1 if (i - N) % 2 == 0 else 0
+        else:
+            n, sh = 4 * (4 * N - i), 1
+        phi[p:p + n] = (np.arange(n) + 0.5 * sh) * (2 * np.pi / n)
+        p += n
+    return phi
+
+
+class fixed_sim_lib:
+    """Simulation library with the duck type filt_simple.library_sepTP needs (get_sim_tmap / get_sim_pmap / hashdict):
+    every index returns the maps of one seeded case, scaled by (1 + 0.1 idx)."""
+
+    def __init__(self, case):
+        self.c = case
+
+    def hashdict(self):
+        return {'fixed_sim_lib': int(self.c['nside']), 'lmax': int(self.c['lmax'])}
+
+    def get_sim_tmap(self, idx):
+        return self.c['tmap'] * (1. + 0.1 * max(idx, 0))
+
+    def get_sim_pmap(self, idx):
+        f = 1. + 0.1 * max(idx, 0)
+        return self.c['qmap'] * f, self.c['umap'] * f
+
+
+def alm_sample(alm, lmax, lfull=128, stride=41):
+    """What the goldens keep of a solution alm: every coefficient with l <= lfull, every stride-th coefficient of the
+    whole array, and its auto-spectrum is stored separately (the full arrays are 8 MB each at lmax 1024)."""
+    ls = alm_ls(lmax)
+    return np.concatenate([alm[ls <= lfull], alm[::stride]])

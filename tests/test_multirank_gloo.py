@@ -1,5 +1,6 @@
-"""CPU, world_size 2 over gloo: the N > 1 host logic -- rank/size shim, simulation striding and the mean-field
-all-reduce of qest.library.get_sim_qlm_mf (no GPU involved: get_sim_qlm is stubbed)."""
+"""CPU, world_size 2 over gloo: the N > 1 host logic -- rank/size/barrier shim (joined lazily at the first barrier),
+simulation striding and the mean-field all-reduce of qest.library.get_sim_qlm_mf_sharded, and the reference-shaped
+get_sim_qlm_mf staying a LOCAL call (no GPU involved: get_sim_qlm is stubbed)."""
 import os
 import subprocess
 import sys
@@ -14,8 +15,12 @@ import os, sys
 import numpy as np
 sys.path.insert(0, %(root)r)
 from plancklens_b200.helpers import mpi
-rank, size = mpi.init('gloo')
-assert size == 2 and mpi.rank == rank
+os.environ['CUDA_VISIBLE_DEVICES'] = ''         # CPU test: the lazy join must pick gloo
+assert mpi.size == 2 and mpi.rank == int(os.environ['RANK'])      # from torchrun's environment, before any join
+mpi.barrier()                                   # no explicit mpi.init(): the first barrier joins the process group
+import torch.distributed as dist
+assert dist.is_initialized() and dist.get_world_size() == 2
+rank, size = mpi.rank, mpi.size
 from plancklens_b200 import qest, hp
 lib = object.__new__(qest.library)
 lib.lib_dir = %(tmp)r
@@ -26,10 +31,16 @@ def fake(k, idx, lmax=None):
     calls.append(int(idx))
     return (idx + 1) * (np.arange(hp.Alm.getsize(8)) + 1j)
 lib.get_sim_qlm = fake
-mf = lib.get_sim_qlm_mf('ptt', np.arange(6))
+mf = lib.get_sim_qlm_mf_sharded('ptt', np.arange(6))
 expect = np.mean([i + 1 for i in range(6)]) * (np.arange(hp.Alm.getsize(8)) + 1j)
 assert np.allclose(mf, expect), (mf[:3], expect[:3])
 assert calls == list(range(6))[rank::2], calls          # each rank evaluated only its share
+# the reference-shaped call is local: ranks may call it with different arguments, or not at all, without pairing up
+del calls[:]
+if rank == 1:
+    mf1 = lib.get_sim_qlm_mf('ptt', np.array([7, 9]))
+    assert np.allclose(mf1, 9.0 * (np.arange(hp.Alm.getsize(8)) + 1j))
+    assert calls == [7, 9], calls
 assert np.allclose(mpi.allreduce_sum(np.array([1.0 + rank])), 3.0)
 assert mpi.bcast('x' if rank == 0 else None) == 'x'
 mpi.barrier()
