@@ -145,6 +145,19 @@ int plk_map_modes_dot_dev(plk_plan *plan, double *m, const double *w, double *su
 int plk_map_modes_sub_dev(plk_plan *plan, double *m, const double *w, const double *sums_dev,
                           const double *pinv_dev, void *stream);
 
+/* ---- counter-based Gaussian random numbers on the device (Philox4x32-10 + Box-Muller, FP64): the synthetic skies of
+ *      the throughput runs.  Replaces the host numpy draws of plancklens/sims/phas.py:137-195 (lib_phas.get_sim,
+ *      pix_lib_phas.get_sim); element i of stream `stream_id` depends on (seed, stream_id, i) only.
+ *   plk_randn_dev    : out[i] = (add ? add[i] : 0) + scale * z_i, i < n   (sims/maps.py:146-173: map + nlev/vamin * phase)
+ *   plk_randn_alm_dev: alm phases of a real field up to lmax: (z0 + i z1)/sqrt 2, real unit normal at m = 0
+ *                      (the recipe of sims/phas.py:162-168)
+ *   plk_philox_words_dev: the raw generator output, out[4 i + k], for bit-exact tests against the oracle */
+int plk_randn_dev(unsigned long long seed, unsigned long long stream_id, long long n, double scale, const double *add,
+                  double *out, void *stream);
+int plk_randn_alm_dev(unsigned long long seed, unsigned long long stream_id, int lmax, void *alm, void *stream);
+int plk_philox_words_dev(unsigned long long seed, unsigned long long stream_id, long long ncalls, unsigned int *out,
+                         void *stream);
+
 /* ---- m-partitioned ("distributed") transforms over the GPUs of one NVSwitch box: one process per GPU
  *      (BASELINE.json configs[4]: one nside-4096 transform split over 2/4/8 GPUs).
  *      The reference has no counterpart: a single healpy transform is one OpenMP process (shts.py:10).

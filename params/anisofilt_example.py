@@ -29,8 +29,9 @@ transf = hp.gauss_beam(5. / 60. / 180. * np.pi, lmax=lmax_ivf)
 cl_len = utils.camb_clfile(os.path.join(cls_path, 'FFP10_wdipole_lensedCls.dat'), lmax=max(lmax_ivf, lmax_qlm))
 cl_ivf = {k: cl_len[k][:lmax_ivf + 1] for k in ['tt', 'ee', 'bb', 'te']}
 
-pix_phas = phas.pix_lib_phas(os.path.join(TEMP, 'pix_phas_nside%s' % nside), 3, (hp.nside2npix(nside),))
-cmb_sims = cmbs.sims_cmb_unl(cl_ivf, phas.lib_phas(os.path.join(TEMP, 'cmb_phas'), 3, lmax_ivf))
+device_sims = bool(int(os.environ.get('PLK_DEVICE_SIMS', 0)))   # draw phases on the GPU (Philox kernels)
+pix_phas = phas.pix_lib_phas(os.path.join(TEMP, 'pix_phas_nside%s' % nside), 3, (hp.nside2npix(nside),), device=device_sims)
+cmb_sims = cmbs.sims_cmb_unl(cl_ivf, phas.lib_phas(os.path.join(TEMP, 'cmb_phas'), 3, lmax_ivf, device=device_sims))
 sims = maps_utils.sim_lib_shuffle(maps.cmb_maps_nlev(cmb_sims, transf, nlev_t, nlev_p, nside, pix_lib_phas=pix_phas),
                                   {idx: nsims if idx == -1 else idx for idx in range(-1, nsims)})
 

@@ -9,7 +9,8 @@ the 5' beam alone (`hp.pixwin` needs the HEALPix data files).  The spectra / res
 reference file (qecl, nhl, n1, qresp) are instantiated as there; `n1_dd` serves cached N1 curves only (the flat-sky
 integrator is the reference's Fortran extension, see plancklens_b200/n1/n1.py).
 
-Sizes can be scaled down for tests through the environment: PLK_NSIDE, PLK_LMAX_IVF, PLK_LMAX_QLM, PLK_NSIMS.
+Sizes can be scaled down for tests through the environment: PLK_NSIDE, PLK_LMAX_IVF, PLK_LMAX_QLM, PLK_NSIMS;
+PLK_DEVICE_SIMS=1 draws the simulations on the GPU.
 """
 import os
 
@@ -44,9 +45,10 @@ cl_weight = utils.camb_clfile(os.path.join(cls_path, 'FFP10_wdipole_lensedCls.da
 cl_weight['bb'] *= 0.
 #: CMB spectra entering the QE weights
 
-pix_phas = phas.pix_lib_phas(os.path.join(TEMP, 'pix_phas_nside%s' % nside), 3, (hp.nside2npix(nside),))
+device_sims = bool(int(os.environ.get('PLK_DEVICE_SIMS', 0)))   # draw phases on the GPU (Philox kernels)
+pix_phas = phas.pix_lib_phas(os.path.join(TEMP, 'pix_phas_nside%s' % nside), 3, (hp.nside2npix(nside),), device=device_sims)
 #: Noise simulation T, Q, U random phases instance.
-cmb_phas = phas.lib_phas(os.path.join(TEMP, 'cmb_phas'), 3, lmax_ivf)
+cmb_phas = phas.lib_phas(os.path.join(TEMP, 'cmb_phas'), 3, lmax_ivf, device=device_sims)
 cmb_sims = cmbs.sims_cmb_unl({k: cl_len[k][:lmax_ivf + 1] for k in ['tt', 'ee', 'bb', 'te']}, cmb_phas)
 #: Gaussian CMB skies with the lensed spectra (stand-in for planck2018_sims.cmb_len_ffp10()).
 

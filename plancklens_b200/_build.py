@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 SO = os.path.join(CSRC, 'libplk_b200.so')
 SOURCES = ['plk_api.cu']
-HEADERS = ['plk_common.h', 'plk_tables.h', 'plk_legendre.cuh', 'plk_fft.cuh', 'plk_blas.cuh', 'plk_wigner.cuh']
+HEADERS = ['plk_common.h', 'plk_tables.h', 'plk_legendre.cuh', 'plk_fft.cuh', 'plk_blas.cuh', 'plk_wigner.cuh', 'plk_rng.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -59,6 +59,9 @@ _SIGS = {
     'plk_profile_read': (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)]),
     'plk_plan_active_fraction': (c_int, [vp, c_int, ctypes.POINTER(c_dbl)]),
     'plk_fp64_peak': (c_int, [ctypes.POINTER(c_dbl), c_int]),
+    'plk_randn_dev': (c_int, [ctypes.c_ulonglong, ctypes.c_ulonglong, c_ll, c_dbl, vp, vp, vp]),
+    'plk_randn_alm_dev': (c_int, [ctypes.c_ulonglong, ctypes.c_ulonglong, c_int, vp, vp]),
+    'plk_philox_words_dev': (c_int, [ctypes.c_ulonglong, ctypes.c_ulonglong, c_ll, vp, vp]),
     'plk_map_mul_dev': (c_int, [c_ll, vp, vp, vp]),
     'plk_map_dot_dev': (c_int, [c_ll, vp, vp, vp, vp]),
     'plk_map_mul2_dev': (c_int, [c_ll, vp, vp, vp, vp]),

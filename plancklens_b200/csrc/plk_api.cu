@@ -14,6 +14,7 @@
 #include "plk_common.h"
 #include "plk_fft.cuh"
 #include "plk_legendre.cuh"
+#include "plk_rng.cuh"
 #include "plk_tables.h"
 #include "plk_wigner.cuh"
 
@@ -1045,6 +1046,32 @@ extern "C" int plk_rlm2alm_dev(int lmax, const double *rlm, void *alm, void *str
 extern "C" int plk_dense_matvec_dev(int n, const double *A, const double *x, double *y, void *stream) {
   if (!A || !x || !y || n < 1) return fail(PLK_EINVAL, "bad argument");
   matvec_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(n, A, x, y);
+  LAUNCHED();
+  return PLK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ device random numbers
+extern "C" int plk_randn_dev(unsigned long long seed, unsigned long long stream_id, long long n, double scale,
+                             const double *add, double *out, void *stream) {
+  if (!out || n < 0) return fail(PLK_EINVAL, "bad argument");
+  if (((uintptr_t)out & 15) || (add && ((uintptr_t)add & 15))) return fail(PLK_EINVAL, "buffers must be 16-byte aligned");
+  if (n == 0) return PLK_OK;
+  randn_kernel<<<flat_grid((n + 1) / 2), 256, 0, (cudaStream_t)stream>>>(seed, stream_id, n, scale, add, out);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_randn_alm_dev(unsigned long long seed, unsigned long long stream_id, int lmax, void *alm, void *stream) {
+  if (!alm || lmax < 0) return fail(PLK_EINVAL, "bad argument");
+  const long long nalm = alm_size(lmax, lmax);
+  randn_alm_kernel<<<flat_grid(nalm), 256, 0, (cudaStream_t)stream>>>(seed, stream_id, nalm, lmax, (cplx *)alm);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_philox_words_dev(unsigned long long seed, unsigned long long stream_id, long long ncalls,
+                                    unsigned int *out, void *stream) {
+  if (!out || ncalls < 0) return fail(PLK_EINVAL, "bad argument");
+  if (ncalls == 0) return PLK_OK;
+  philox_words_kernel<<<flat_grid(ncalls), 256, 0, (cudaStream_t)stream>>>(seed, stream_id, ncalls, out);
   LAUNCHED();
   return PLK_OK;
 }

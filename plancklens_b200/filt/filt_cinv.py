@@ -152,13 +152,20 @@ class cinv_t(cinv):
 
     def apply_ivf(self, tmap, soltn=None):
         """Inverse-variance filtered alm of a temperature map (numpy in, numpy out; the solve runs on the GPU)."""
+        return self.apply_ivf_dev(tmap, soltn=soltn).cpu().numpy()
+
+    def apply_ivf_dev(self, tmap, soltn=None):
+        """Same with the result left on the device (complex128 CUDA tensor); `tmap` and `soltn` may be numpy arrays or
+        CUDA tensors.  What `library_cinv_sepTP.get_sim_teblm_dev` hands to `qest` without a host round trip."""
+        from .. import sht
         if soltn is None:
             talm = util_alm.dalm.zeros(self.lmax)
         else:
-            talm = util_alm.dalm.from_numpy(soltn)
+            talm = util_alm.dalm(sht.dev_alm(soltn).clone())
         self.chain.solve(talm, tmap)
-        from .. import sht
-        return talm.almxfl(sht.dev_fl(self.rescal_cl, self.lmax), inplace=True).numpy()
+        if not hasattr(self, '_rescal_d'):
+            self._rescal_d = sht.dev_fl(self.rescal_cl, self.lmax)
+        return talm.almxfl(self._rescal_d, inplace=True).t
 
 
 class cinv_p(cinv):
@@ -216,15 +223,21 @@ class cinv_p(cinv):
 
     def apply_ivf(self, tmap, soltn=None):
         """Inverse-variance filtered (E, B) alms of a (Q, U) map pair."""
+        e, b = self.apply_ivf_dev(tmap, soltn=soltn)
+        return e.cpu().numpy(), b.cpu().numpy()
+
+    def apply_ivf_dev(self, tmap, soltn=None):
+        """Same with the (E, B) results left on the device; maps and `soltn` may be numpy arrays or CUDA tensors."""
+        from .. import sht
         if soltn is not None:
             assert len(soltn) == 2
-            assert hp.Alm.getlmax(soltn[0].size) == self.lmax and hp.Alm.getlmax(soltn[1].size) == self.lmax
-            talm = util_alm.eblm([util_alm.dalm.from_numpy(soltn[0]), util_alm.dalm.from_numpy(soltn[1])])
+            assert sht.alm_lmax(len(soltn[0])) == self.lmax and sht.alm_lmax(len(soltn[1])) == self.lmax
+            talm = util_alm.eblm([util_alm.dalm(sht.dev_alm(soltn[0]).clone()), util_alm.dalm(sht.dev_alm(soltn[1]).clone())])
         else:
             talm = util_alm.eblm([util_alm.dalm.zeros(self.lmax), util_alm.dalm.zeros(self.lmax)])
         assert len(tmap) == 2
         self.chain.solve(talm, [tmap[0], tmap[1]])
-        return talm.numpy()
+        return talm.elm.t, talm.blm.t
 
     def _calc_febl(self):
         assert 'eb' not in self.chain.s_cls.keys()
@@ -455,6 +468,12 @@ class library_cinv_sepTP(filt_simple.library_sepTP):
 
     def _apply_ivf_p(self, pmap, soltn=None):
         return self.cinv_p.apply_ivf(pmap, soltn=soltn)
+
+    def _apply_ivf_t_dev(self, tmap, soltn=None):
+        return self.cinv_t.apply_ivf_dev(tmap, soltn=soltn)
+
+    def _apply_ivf_p_dev(self, pmap, soltn=None):
+        return self.cinv_p.apply_ivf_dev(pmap, soltn=soltn)
 
     def get_tmliklm(self, idx):
         return hp.almxfl(self.get_sim_tlm(idx), self.cinv_t.cl['tt'])

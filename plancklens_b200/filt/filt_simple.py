@@ -113,6 +113,106 @@ class library_sepTP(object):
     def get_sim_bmliklm(self, idx):
         return hp.almxfl(self.get_sim_blm(idx), self.cl['bb'])
 
+    # -- the same products as CUDA tensors (no reference counterpart: there everything is a numpy array on the host).
+    #    `qest.library` asks for these when both of its filtering libraries provide them, which keeps a simulation on the
+    #    GPU from the simulated map to the quadratic estimate: maps from `sim_lib.get_sim_*map_dev`, the filter through
+    #    `_apply_ivf_*_dev`, and the last few filtered skies in a small device cache.  Disk caching (`self.cache`, same file
+    #    names as above) happens on a worker thread from pinned host copies, off the GPU's critical path.
+    _DEV_CACHE_SIMS = 4
+
+    def _dev_store(self):
+        if not hasattr(self, '_dev_alms'):
+            import collections
+            self._dev_alms = collections.OrderedDict()
+        return self._dev_alms
+
+    def _sim_map_dev(self, idx, which):
+        fun = getattr(self.sim_lib, 'get_sim_%smap_dev' % which, None)
+        if fun is not None:
+            return fun(idx)
+        return getattr(self.sim_lib, 'get_sim_%smap' % which)(idx)          # numpy (or tensors with device_maps)
+
+    def _write_async(self, fn, tensor):
+        """tensor -> pinned host copy (this stream) -> hp.write_alm on a worker thread, write-then-rename"""
+        import concurrent.futures as cf
+        import torch
+        if not hasattr(self, '_io_pool'):
+            self._io_pool = cf.ThreadPoolExecutor(max_workers=2)
+            self._io_pending = []
+        host = torch.empty(tensor.numel(), dtype=torch.complex128, pin_memory=True)
+        host.copy_(tensor, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+
+        def job():
+            ev.synchronize()
+            root, ext = os.path.splitext(fn)
+            tmp = '%s.tmp%d%s' % (root, os.getpid(), ext)        # keeps the extension hp.write_alm dispatches on
+            hp.write_alm(tmp, host.numpy(), overwrite=True)
+            os.replace(tmp, fn)
+        self._io_pending = [f for f in self._io_pending if not f.done()]
+        self._io_pending.append(self._io_pool.submit(job))
+
+    def flush(self):
+        """waits for the asynchronous cache writes of the device accessors"""
+        for f in getattr(self, '_io_pending', []):
+            f.result()
+        self._io_pending = []
+
+    def get_sim_teblm_dev(self, idx, fields='teb'):
+        """Inverse-variance filtered alms of simulation idx as complex128 CUDA tensors, in the order of `fields`."""
+        from .. import sht
+        store = self._dev_store()
+        ent = store.setdefault(idx, {})
+        store.move_to_end(idx)
+        if 't' in fields and 't' not in ent:
+            fn = self._fname(idx, 't')
+            if os.path.exists(fn):
+                ent['t'] = sht.dev_alm(hp.read_alm(fn))
+            else:
+                soltn = None if self.soltn_lib is None else self.soltn_lib.get_sim_tmliklm(idx)
+                if hasattr(self, '_apply_ivf_t_dev'):
+                    ent['t'] = self._apply_ivf_t_dev(self._sim_map_dev(idx, 't'), soltn=soltn)
+                else:
+                    ent['t'] = sht.dev_alm(self._apply_ivf_t(self.sim_lib.get_sim_tmap(idx), soltn=soltn))
+                if self.cache:
+                    self._write_async(fn, ent['t'])
+        if ('e' in fields or 'b' in fields) and 'e' not in ent:
+            fn_e, fn_b = self._fname(idx, 'e'), self._fname(idx, 'b')
+            if os.path.exists(fn_e) and os.path.exists(fn_b):
+                ent['e'], ent['b'] = sht.dev_alm(hp.read_alm(fn_e)), sht.dev_alm(hp.read_alm(fn_b))
+            else:
+                soltn = None
+                if self.soltn_lib is not None:
+                    soltn = np.array([self.soltn_lib.get_sim_emliklm(idx), self.soltn_lib.get_sim_bmliklm(idx)])
+                if hasattr(self, '_apply_ivf_p_dev'):
+                    ent['e'], ent['b'] = self._apply_ivf_p_dev(self._sim_map_dev(idx, 'p'), soltn=soltn)
+                else:
+                    e, b = self._apply_ivf_p(self.sim_lib.get_sim_pmap(idx), soltn=soltn)
+                    ent['e'], ent['b'] = sht.dev_alm(e), sht.dev_alm(b)
+                if self.cache:
+                    self._write_async(fn_e, ent['e'])
+                    self._write_async(fn_b, ent['b'])
+        while len(store) > self._DEV_CACHE_SIMS:
+            store.popitem(last=False)
+        return tuple(ent[f] for f in fields)
+
+    def _cl_dev(self, key, lmax):
+        from .. import sht
+        if not hasattr(self, '_cl_d'):
+            self._cl_d = {}
+        if (key, lmax) not in self._cl_d:
+            self._cl_d[(key, lmax)] = sht.dev_fl(self.cl[key], lmax)
+        return self._cl_d[(key, lmax)]
+
+    def get_sim_mliklm_dev(self, idx, fields='teb'):
+        """Wiener-filtered alms C_l^{aa} x (inverse-variance filtered a) on the device"""
+        from .. import sht
+        out = []
+        for f, a in zip(fields, self.get_sim_teblm_dev(idx, fields)):
+            out.append(sht.almxfl(a, self._cl_dev(f + f, sht.alm_lmax(a.numel()))))
+        return tuple(out)
+
 
 class library_jTP(object):
     """Inverse-variance and Wiener filtering of a simulation library, T and P filtered JOINTLY
@@ -251,6 +351,28 @@ class library_fullsky_sepTP(library_sepTP):
         elm = hp.almxfl(elm, self.get_fel() * utils.cli(self.transf['e'][:len(self.fel)]))
         blm = hp.almxfl(blm, self.get_fbl() * utils.cli(self.transf['b'][:len(self.fbl)]))
         return elm, blm
+
+
+    # device-resident forms: one analysis with the per-l filter fused (maps may be numpy arrays or CUDA tensors)
+    def _ivf_fl_dev(self, a):
+        from .. import sht
+        if not hasattr(self, '_fl_d'):
+            self._fl_d = {}
+        if a not in self._fl_d:
+            fl = {'t': self.get_ftl, 'e': self.get_fel, 'b': self.get_fbl}[a]()
+            self._fl_d[a] = sht.dev_fl(fl * utils.cli(self.transf[a][:len(fl)]), self.lmax_fl)
+        return self._fl_d[a]
+
+    def _apply_ivf_t_dev(self, tmap, soltn=None):
+        from .. import sht
+        assert len(tmap) == hp.nside2npix(self.nside), (len(tmap), self.nside)
+        return sht.get_plan(self.nside, self.lmax_fl).map2alm(sht.dev_map(tmap), fl=self._ivf_fl_dev('t'))
+
+    def _apply_ivf_p_dev(self, pmap, soltn=None):
+        from .. import sht
+        assert len(pmap[0]) == hp.nside2npix(self.nside) and len(pmap[0]) == len(pmap[1])
+        return sht.get_plan(self.nside, self.lmax_fl).map2alm_spin(sht.dev_map(pmap[0]), sht.dev_map(pmap[1]), 2,
+                                                                   flg=self._ivf_fl_dev('e'), flc=self._ivf_fl_dev('b'))
 
 
 class library_fullsky_alms_sepTP(library_fullsky_sepTP):

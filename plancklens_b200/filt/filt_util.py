@@ -47,6 +47,25 @@ class library_ftl:
                 out[o:o + lmax_in + 1 - m] = alm[i:i + lmax_in + 1 - m]
         return hp.almxfl(out, fl)
 
+    # device-resident accessors, present when the wrapped library has them (filt_simple.library_sepTP)
+    def _cut_dev(self, alm, a):
+        from .. import sht
+        if not hasattr(self, '_lf_d'):
+            self._lf_d = {}
+        if a not in self._lf_d:
+            self._lf_d[a] = sht.dev_fl({'t': self.lfilt_t, 'e': self.lfilt_e, 'b': self.lfilt_b}[a], self.lmax)
+        if sht.alm_lmax(alm.numel()) != self.lmax:
+            alm = sht.alm_copy(alm, self.lmax)          # truncates or zero-pads
+        return sht.almxfl(alm, self._lf_d[a])
+
+    def __getattr__(self, name):
+        if name in ('get_sim_teblm_dev', 'get_sim_mliklm_dev') and hasattr(self.ivfs, name):
+            inner = getattr(self.ivfs, name)
+            return lambda idx, fields='teb': tuple(self._cut_dev(x, f) for f, x in zip(fields, inner(idx, fields)))
+        if name == 'flush' and hasattr(self.ivfs, 'flush'):
+            return self.ivfs.flush
+        raise AttributeError(name)
+
     def get_sim_tlm(self, idx):
         return self._cut(self.ivfs.get_sim_tlm(idx), self.lfilt_t)
 
@@ -173,6 +192,14 @@ class library_shuffle:
 
     def get_fbl(self):
         return self.ivfs.get_fbl()
+
+    def __getattr__(self, name):
+        if name in ('get_sim_teblm_dev', 'get_sim_mliklm_dev') and hasattr(self.ivfs, name):
+            inner = getattr(self.ivfs, name)
+            return lambda idx, fields='teb': inner(self.idxs[idx], fields)
+        if name == 'flush' and hasattr(self.ivfs, 'flush'):
+            return self.ivfs.flush
+        raise AttributeError(name)
 
     def get_sim_tlm(self, idx):
         return self.ivfs.get_sim_tlm(self.idxs[idx])

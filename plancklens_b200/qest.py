@@ -447,8 +447,47 @@ class library:
         f2 = self.f2map1 if swapped else self.f2map2
         return f1, f2
 
+    # ---- device-resident evaluation: used whenever both filtering libraries hand out CUDA tensors
+    #      (`get_sim_teblm_dev` / `get_sim_mliklm_dev`, filt_simple.library_sepTP and its wrappers): nothing of a
+    #      simulation visits the host between the simulated map and the estimate
+    def _dev_ok(self):
+        return all(hasattr(f.ivfs, 'get_sim_teblm_dev') and hasattr(f.ivfs, 'get_sim_mliklm_dev')
+                   for f in (self.f2map1, self.f2map2)) and os.environ.get('PLK_QE_DEVICE', '1') != '0'
+
+    def _dev_gclm(self, idx, k, swapped=False):
+        """(G, C) CUDA tensors of a fundamental lensing key; same legs and per-l weights as the host-fed paths below"""
+        f1, f2 = self._legs(idx, k, swapped)
+        fields = {'ptt': 't', 'p_p': 'eb', 'p': 'teb'}[k]
+        bars = dict(zip(fields, f1.ivfs.get_sim_teblm_dev(idx, fields)))
+        wfs = dict(zip(fields, f2.ivfs.get_sim_mliklm_dev(idx, fields)))
+        lmax = sht.alm_lmax(next(iter(bars.values())).numel())
+        qe = self._engine(lmax)
+        if k == 'p':            # C^TE cross terms of the Wiener legs (qest.py:582-588, :613-618)
+            b2 = bars if f2.ivfs is f1.ivfs else dict(zip('te', f2.ivfs.get_sim_teblm_dev(idx, 'te')))
+            one, clte = f2._one_dev(lmax), f2._clte_dev(lmax)
+            twf = sht.alm_combine([(wfs['t'], one), (b2['e'], clte)])
+            ewf = sht.alm_combine([(wfs['e'], one), (b2['t'], clte)])
+            return qe.p(bars['t'], bars['e'], bars['b'], twf, ewf, wfs['b'], merge_analysis=self.merge_analysis)
+        if k == 'ptt':
+            return qe.ptt(bars['t'], wfs['t'])
+        return qe.p_p(bars['e'], bars['b'], wfs['e'], wfs['b'])
+
+    def get_sim_qlm_dev(self, k, idx):
+        """Gradient and curl estimates of 'ptt', 'p_p' or 'p' as CUDA tensors, symmetrised like `get_sim_qlm` when the
+        two legs differ; not cached (mean-field and spectra accumulations that stay on the GPU)."""
+        assert k in ['ptt', 'p_p', 'p'], k
+        assert self._dev_ok(), "both filtering libraries must provide device-resident alms"
+        G, C = self._dev_gclm(idx, k)
+        if not self.f2map1.ivfs == self.f2map2.ivfs:
+            G2, C2 = self._dev_gclm(idx, k, swapped=True)
+            G, C = (G + G2) * 0.5, (C + C2) * 0.5
+        return G, C
+
     def _get_sim_Tgclm(self, idx, k, swapped=False):
         """T-only estimator, gradient and curl (reference: qest.py:248-263)."""
+        if self._dev_ok():
+            G, C = self._dev_gclm(idx, k, swapped)
+            return self._engine(self._qe.lmax_ivf).to_host(G, C)
         f1, f2 = self._legs(idx, k, swapped)
         tbar = f1.ivfs.get_sim_tlm(idx)
         twf = f2.wf_tlm(idx, k)
@@ -458,6 +497,9 @@ class library:
 
     def _get_sim_Pgclm(self, idx, k, swapped=False):
         """P-only estimator (reference: qest.py:265-285)."""
+        if self._dev_ok():
+            G, C = self._dev_gclm(idx, k, swapped)
+            return self._engine(self._qe.lmax_ivf).to_host(G, C)
         f1, f2 = self._legs(idx, k, swapped)
         ebar, bbar = f1.ivfs.get_sim_elm(idx), f1.ivfs.get_sim_blm(idx)
         ewf, bwf = f2.wf_eblm(idx, k)
@@ -468,6 +510,9 @@ class library:
     def _get_sim_MVgclm(self, idx, k, swapped=False):
         """MV estimator = P + T pieces with the C^TE cross terms in the Wiener legs (reference: qest.py:318-322)."""
         assert k == 'p'
+        if self._dev_ok():
+            G, C = self._dev_gclm(idx, k, swapped)
+            return self._engine(self._qe.lmax_ivf).to_host(G, C)
         f1, f2 = self._legs(idx, k, swapped)
         tbar, ebar, bbar = f1.ivfs.get_sim_tlm(idx), f1.ivfs.get_sim_elm(idx), f1.ivfs.get_sim_blm(idx)
         qe = self._engine(hp.Alm.getlmax(tbar.size))
@@ -747,6 +792,20 @@ class lib_filt2map_sepTP(lib_filt2map):
         if k == 'p':
             elm = elm + hp.almxfl(self.ivfs.get_sim_tlm(idx), self.clte)      # qest.py:613-618
         return elm, blm
+
+    def _clte_dev(self, lmax):
+        if not hasattr(self, '_clte_d'):
+            self._clte_d = {}
+        if lmax not in self._clte_d:
+            self._clte_d[lmax] = sht.dev_fl(self.clte, lmax)
+        return self._clte_d[lmax]
+
+    def _one_dev(self, lmax):
+        if not hasattr(self, '_one_d'):
+            self._one_d = {}
+        if lmax not in self._one_d:
+            self._one_d[lmax] = torch.ones(lmax + 1, dtype=torch.float64, device='cuda')
+        return self._one_d[lmax]
 
     def _cl_dev(self):
         """filtering weights C_l^{TT, EE, BB} of the ivfs and C_l^{TE}, on the device"""

@@ -252,6 +252,18 @@ def alm_dotn(avec, bvec, lmin=0, out=None):
     return out
 
 
+def alm_combine(terms, out=None):
+    """sum_j fl_j[l] a_j[l, m] on the device for up to four (alm tensor, device fl tensor) pairs (plk_alm_combine_dev)"""
+    n = len(terms)
+    lmax = alm_lmax(terms[0][0].numel())
+    out = torch.empty_like(terms[0][0]) if out is None else out
+    ins = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in terms])
+    fls = (ctypes.c_void_p * n)(*[t[1].data_ptr() for t in terms])
+    nfl = (ctypes.c_int * n)(*[int(t[1].numel()) for t in terms])
+    check(_lib.load().plk_alm_combine_dev(lmax, n, ins, fls, nfl, _ptr(out), _stream()))
+    return out
+
+
 def alm2cl(a, b=None):
     """hp.alm2cl on device alms -> device float64[lmax + 1]"""
     b = a if b is None else b
@@ -344,3 +356,25 @@ def map_ninv3(q, u, nqq, nqu, nuu):
 def map_cmul_acc(ar, ai, br, bi, dr, di):
     """(dr + i di) += (ar + i ai)(br + i bi); ai / bi may be None"""
     check(_lib.load().plk_map_cmul_acc_dev(ar.numel(), _ptr(ar), _ptr(ai), _ptr(br), _ptr(bi), _ptr(dr), _ptr(di), _stream()))
+
+
+# ---- counter-based Gaussian random numbers on the device (Philox4x32-10, plk_rng.cuh)
+def randn(seed, stream_id, n, scale=1.0, add=None, out=None):
+    """out[i] = (add[i] if add is given else 0) + scale * z_i with unit normals z_i that depend on (seed, stream_id, i)"""
+    out = torch.empty(int(n), dtype=torch.float64, device='cuda') if out is None else out
+    check(_lib.load().plk_randn_dev(int(seed), int(stream_id), int(n), float(scale), _ptr(add), _ptr(out), _stream()))
+    return out
+
+
+def randn_alm(seed, stream_id, lmax):
+    """unit-variance alm phases of a real field (reference recipe sims/phas.py:162-168) as a complex128 CUDA tensor"""
+    out = torch.empty(alm_size(lmax), dtype=torch.complex128, device='cuda')
+    check(_lib.load().plk_randn_alm_dev(int(seed), int(stream_id), int(lmax), _ptr(out), _stream()))
+    return out
+
+
+def philox_words(seed, stream_id, ncalls):
+    """raw generator output [ncalls, 4] (int32 carrier of the uint32 words); tests only"""
+    out = torch.empty((int(ncalls), 4), dtype=torch.int32, device='cuda')
+    check(_lib.load().plk_philox_words_dev(int(seed), int(stream_id), int(ncalls), _ptr(out), _stream()))
+    return out

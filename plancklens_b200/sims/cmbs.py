@@ -61,6 +61,33 @@ class sims_cmb_unl:
         assert field in self.fields, self.fields
         return self._get_sim_alm(idx, self.fields.index(field))
 
+    # ---- the same on the device (phase library built with device=True): phases drawn by the Philox kernel, coloured by
+    #      one alm_combine launch per field; nothing touches the host
+    def _phases_dev(self, idx):
+        if getattr(self, '_dpha_idx', None) != idx:
+            self._dpha = [self.lib_pha.get_sim_dev(idx, i) for i in range(len(self.fields))]
+            self._dpha_idx = idx
+        return self._dpha
+
+    def get_sim_alm_dev(self, idx, field):
+        """complex128 CUDA tensor of field `field` of simulation idx"""
+        from .. import sht
+        assert field in self.fields, self.fields
+        idf = self.fields.index(field)
+        if not hasattr(self, '_rmat_d'):
+            self._rmat_d = {}
+        terms = []
+        for i, ph in enumerate(self._phases_dev(idx)):
+            if np.any(self.rmat[:, idf, i]):
+                if (idf, i) not in self._rmat_d:
+                    self._rmat_d[(idf, i)] = sht.dev_fl(self.rmat[:, idf, i], self.lmax)
+                terms.append((ph, self._rmat_d[(idf, i)]))
+        assert 1 <= len(terms) <= 4, len(terms)
+        return sht.alm_combine(terms)
+
+    def has_device_sims(self):
+        return bool(getattr(self.lib_pha, 'device', False))
+
     def get_sim_tlm(self, idx):
         return self.get_sim_alm(idx, 't')
 

@@ -25,22 +25,50 @@ class cmb_maps(object):
         return ret
 
     def get_sim_tmap(self, idx):
-        tlm = hp.almxfl(self.sims_cmb_len.get_sim_tlm(idx), self.cl_transf_T)
         if self.device_maps:
-            from .. import sht
-            t = sht.get_plan(self.nside, hp.Alm.getlmax(tlm.size)).alm2map(sht.dev_alm(tlm))
-            return self._add_noise_dev(t, idx, 't')
+            return self.get_sim_tmap_dev(idx)
+        tlm = hp.almxfl(self.sims_cmb_len.get_sim_tlm(idx), self.cl_transf_T)
         return hp.alm2map(tlm, self.nside) + self.get_sim_tnoise(idx)
 
     def get_sim_pmap(self, idx):
+        if self.device_maps:
+            return self.get_sim_pmap_dev(idx)
         elm = hp.almxfl(self.sims_cmb_len.get_sim_elm(idx), self.cl_transf_P)
         blm = hp.almxfl(self.sims_cmb_len.get_sim_blm(idx), self.cl_transf_P)
-        if self.device_maps:
-            from .. import sht
-            Q, U = sht.get_plan(self.nside, hp.Alm.getlmax(elm.size)).alm2map_spin(sht.dev_alm(elm), sht.dev_alm(blm), 2)
-            return self._add_noise_dev(Q, idx, 'q'), self._add_noise_dev(U, idx, 'u')
         Q, U = hp.alm2map_spin([elm, blm], self.nside, 2, hp.Alm.getlmax(elm.size))
         return Q + self.get_sim_qnoise(idx), U + self.get_sim_unoise(idx)
+
+    # ---- device-resident simulated maps (float64 CUDA tensors): CMB alms from the device when the CMB library draws
+    #      there, transfer function fused into the synthesis, noise added by the generator kernel itself
+    def _cmb_alm_dev(self, idx, field):
+        from .. import sht
+        lib = self.sims_cmb_len
+        if hasattr(lib, 'get_sim_alm_dev') and lib.has_device_sims():
+            return lib.get_sim_alm_dev(idx, field)
+        return sht.dev_alm(getattr(lib, 'get_sim_%slm' % field)(idx))
+
+    def _transf_dev(self, which, lmax):
+        from .. import sht
+        if not hasattr(self, '_tf_d'):
+            self._tf_d = {}
+        if (which, lmax) not in self._tf_d:
+            self._tf_d[(which, lmax)] = sht.dev_fl(self.cl_transf_T if which == 't' else self.cl_transf_P, lmax)
+        return self._tf_d[(which, lmax)]
+
+    def get_sim_tmap_dev(self, idx):
+        from .. import sht
+        tlm = self._cmb_alm_dev(idx, 't')
+        lmax = sht.alm_lmax(tlm.numel())
+        t = sht.get_plan(self.nside, lmax).alm2map(tlm, fl=self._transf_dev('t', lmax))
+        return self._add_noise_dev(t, idx, 't')
+
+    def get_sim_pmap_dev(self, idx):
+        from .. import sht
+        elm, blm = self._cmb_alm_dev(idx, 'e'), self._cmb_alm_dev(idx, 'b')
+        lmax = sht.alm_lmax(elm.numel())
+        fl = self._transf_dev('p', lmax)
+        Q, U = sht.get_plan(self.nside, lmax).alm2map_spin(elm, blm, 2, flg=fl, flc=fl)
+        return self._add_noise_dev(Q, idx, 'q'), self._add_noise_dev(U, idx, 'u')
 
     def _add_noise_dev(self, m, idx, field):
         """m += noise map of `field` in ('t', 'q', 'u') on the device"""
@@ -88,9 +116,12 @@ class cmb_maps_nlev(cmb_maps):
         return np.sqrt(hp.nside2pixarea(self.nside, degrees=True)) * 60
 
     def _add_noise_dev(self, m, idx, field):
-        # unit-variance phases go to the device as drawn; the nlev / vamin scaling is the axpy coefficient
         from .. import sht
         idf, nlev = {'t': (0, self.nlev_t), 'q': (1, self.nlev_p), 'u': (2, self.nlev_p)}[field]
+        if getattr(self.pix_lib_phas, 'device', False):
+            # drawn on the device: map + nlev / vamin * phase in the generator kernel's own pass over the pixels
+            return self.pix_lib_phas.get_sim_dev(idx, idf, scale=nlev / self._vamin(), add=m).reshape(-1)
+        # host phases go to the device as drawn; the nlev / vamin scaling is the axpy coefficient
         return sht.map_axpy(m, sht.dev_map(self.pix_lib_phas.get_sim(idx, idf=idf)), nlev / self._vamin())
 
     def get_sim_tnoise(self, idx):

@@ -15,6 +15,13 @@ class sim_lib_shuffle:
     def get_sim_pmap(self, idx):
         return self.sim_lib.get_sim_pmap(int(self._shuffle[idx]))
 
+    def __getattr__(self, name):
+        # device-resident accessors exist when the wrapped library has them (maps.cmb_maps.get_sim_*map_dev)
+        if name in ('get_sim_tmap_dev', 'get_sim_pmap_dev') and hasattr(self.sim_lib, name):
+            fun = getattr(self.sim_lib, name)
+            return lambda idx: fun(int(self._shuffle[idx]))
+        raise AttributeError(name)
+
     def hashdict(self):
         return {'sim_lib': self.sim_lib.hashdict(), 'shuffle': self._shuffle}
 

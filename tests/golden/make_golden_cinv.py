@@ -6,10 +6,15 @@ oracle/healpy_shim standing in for healpy (healpy is not installable here, SURVE
 
 Pinned: top-level iteration counts, eps traces, the inverse-variance filtered alms out of `library_cinv_sepTP`
 (i.e. `apply_ivf` after `rescal_cl`), the Wiener-filtered alms, the isotropic approximations (ftl / fel / fbl / tal) and
-the mask the libraries derive.  Takes ~1 h on 8 cores (the dense coarse preconditioners are 4225 + 2178 operator
+the mask the libraries derive.  Takes ~10 min on 8 cores (the dense coarse preconditioners are 4225 + 2178 operator
 applications on the CPU oracle).
 
-Run from the repo root:  python tests/golden/make_golden_cinv.py
+Run from the repo root:
+  python tests/golden/make_golden_cinv.py            35 / 55 uK-arcmin  -> reference_golden_cinv.npz (T 12, P 3 iterations)
+  python tests/golden/make_golden_cinv.py deep       3 / 4 uK-arcmin    -> reference_golden_cinv_deep.npz (T 8, P 22)
+  python tests/golden/make_golden_cinv.py refresh    deep polarization filter pushed to eps_min = 1e-7 (the default chain
+                                                     rows otherwise), past the `roundoff = 25` residual refresh of
+                                                     cd_solve.py:79-81 -> reference_golden_cinv_refresh.npz
 """
 import os
 import sys
@@ -30,7 +35,9 @@ from plancklens.filt import filt_cinv  # noqa: E402  (reference)
 import golden_inputs as gi  # noqa: E402
 
 CLPATH = '/root/reference/plancklens/data/cls/FFP10_wdipole_lensedCls.dat'
-c = gi.cinv_case(hp.alm2map, hp.alm2map_spin, CLPATH)
+MODE = sys.argv[1] if len(sys.argv) > 1 else ''
+DEEP = MODE in ('deep', 'refresh')
+c = gi.cinv_case(hp.alm2map, hp.alm2map_spin, CLPATH, **({'nlev_t': 3., 'nlev_p': 4.} if DEEP else {}))
 lmax, nside = c['lmax'], c['nside']
 out = {'mask_sum': np.array([c['mask'].sum()]), 'tmap_sum': np.array([c['tmap'].sum(), np.abs(c['tmap']).sum()]),
        'qmap_sum': np.array([c['qmap'].sum(), np.abs(c['qmap']).sum()])}
@@ -44,6 +51,25 @@ def traced(chain, store):
         return orig(stage, it, eps, **kw)
     chain.log = log
 
+
+if MODE == 'refresh':
+    from plancklens.qcinv import cd_solve
+    with tempfile.TemporaryDirectory() as tmp:
+        descr = [[2, ["split(dense(), 32, diag_cl)"], 512, 256, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [1, ["split(stage(2),  512, diag_cl)"], 1024, 512, 3, 0.0, cd_solve.tr_cg, cd_solve.cache_mem()],
+                 [0, ["split(stage(1), 1024, diag_cl)"], lmax, nside, np.inf, 1.0e-7, cd_solve.tr_cg, cd_solve.cache_mem()]]
+        cinv_p = filt_cinv.cinv_p(os.path.join(tmp, 'cinv_p'), lmax, nside, c['cls'], c['transf'], c['ninv_p'], chain_descr=descr)
+        tr_p = []
+        traced(cinv_p.chain, tr_p)
+        elm, blm = cinv_p.apply_ivf([c['qmap'], c['umap']])
+        out['p_trace'] = np.array([t for t in tr_p if t[0] == 0])
+        print('P iterations to 1e-7:', int(out['p_trace'][-1][1]))
+        for name, alm in (('elm', elm), ('blm', blm)):
+            out[name + '_sample'] = gi.alm_sample(alm, lmax)
+    fn = os.path.join(ROOT, 'tests', 'golden', 'reference_golden_cinv_refresh.npz')
+    np.savez_compressed(fn, **out)
+    print('wrote', fn)
+    sys.exit(0)
 
 with tempfile.TemporaryDirectory() as tmp:
     t0 = time.time()
@@ -91,6 +117,6 @@ with tempfile.TemporaryDirectory() as tmp:
     out['tlm2_cl'] = hp.alm2cl(tlm2)
     print('T warm-start iterations:', int(out['t2_trace'][-1][1]))
 
-fn = os.path.join(ROOT, 'tests', 'golden', 'reference_golden_cinv.npz')
+fn = os.path.join(ROOT, 'tests', 'golden', 'reference_golden_cinv%s.npz' % ('_deep' if DEEP else ''))
 np.savez_compressed(fn, **out)
 print('wrote', fn, {k: np.shape(v) for k, v in out.items()})

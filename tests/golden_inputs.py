@@ -339,11 +339,13 @@ def camb_cls(path, lmax):
     return cls
 
 
-def cinv_case(alm2map, alm2map_spin, clpath, nside=512, lmax=1024, seed=512):
+def cinv_case(alm2map, alm2map_spin, clpath, nside=512, lmax=1024, seed=512, nlev_t=35., nlev_p=55.):
     """Masked anisotropic-noise sky of SURVEY.md section 8d: |z| < sin 20 deg cut plus 400 seeded discs of ~15' radius,
     n_inv = mask (vamin / nlev)^2 (1 + 0.5 z^2), 5' beam, 35 / 55 uK-arcmin, data = Gaussian CMB (fiducial lensed
     spectra) * beam + white noise drawn in pixel space.  `alm2map`, `alm2map_spin` are the CPU oracle's on both the
-    reference side (tests/golden/make_golden_cinv.py) and the test side, so both see bit-identical maps."""
+    reference side (tests/golden/make_golden_cinv.py) and the test side, so both see bit-identical maps.
+    The "deep" variant (nlev_t 3, nlev_p 4 uK-arcmin) is signal dominated to l ~ lmax: several tens of top-level
+    iterations, past the `roundoff = 25` residual refresh of cd_solve.py:79-81."""
     rng = np.random.default_rng(seed)
     npix = 12 * nside ** 2
     cls = camb_cls(clpath, lmax)
@@ -366,7 +368,6 @@ def cinv_case(alm2map, alm2map_spin, clpath, nside=512, lmax=1024, seed=512):
         idx = np.where(band)[0]
         hit = idx[(cen[:, j] @ vec[:, idx]) > cosr]
         mask[hit] = 0.
-    nlev_t, nlev_p = 35., 55.
     vamin = np.sqrt(4. * np.pi / npix) * 180. * 60. / np.pi
     ninv_t = mask * (vamin / nlev_t) ** 2 * (1. + 0.5 * z ** 2)
     ninv_p = mask * (vamin / nlev_p) ** 2 * (1. + 0.5 * z ** 2)
