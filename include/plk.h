@@ -137,6 +137,9 @@ int plk_map_cmul_acc_dev(long long n, const double *ar, const double *ai, const 
 /* opfilt_pp.py:292-301: (q,u) <- [[nqq, nqu],[nqu, nuu]] (q,u) */
 int plk_map_ninv3_dev(long long n, double *q, double *u, const double *nqq, const double *nqu, const double *nuu,
                       void *stream);
+/* hp.ud_grade(map, nside_out, power=-2) on RING maps: out_p = sum of the (nside_in / nside_out)^2 children of p
+ * (opfilt_tt.py:172-181, opfilt_pp.py:244-251: the inverse-noise maps of the coarse multigrid levels) */
+int plk_udgrade_sum_dev(int nside_in, const double *in, int nside_out, double *out, void *stream);
 /* template_removal.py dot()/accum() for monopole + dipole on a RING map of the plan's nside
  * (opfilt_tt.py:193-205):
  *   if w != NULL: m_p <- m_p w_p first (in place);  sums_dev[0..3] = sum_p m_p * {1, x_p, y_p, z_p} */

@@ -10,6 +10,7 @@ import os
 import subprocess
 
 import numpy as np
+import scipy.fft as sfft
 
 from . import ref_geom as rg
 
@@ -150,21 +151,24 @@ def legendre_anal_mlist(nside, spin, lmax, X1, X2, mlist):
     return G, C
 
 
-def phase2map(nside, X):
+def phase2map(nside, X, workers=None):
     """Ring FFT stage of synthesis: X[ring, m] -> RING-ordered real map.
-    map_j = X_0 + 2 Re sum_{m>0} X_m e^{i m (phi0 + 2 pi j / nphi)}; m >= nphi/2 aliases onto the ring's band."""
+    map_j = X_0 + 2 Re sum_{m>0} X_m e^{i m (phi0 + 2 pi j / nphi)}; m >= nphi/2 aliases onto the ring's band.
+    `workers`: threads of the batched pocketfft calls (scipy.fft; -1 = all cores), used by the CPU baseline."""
     g = _Geom.get(nside)
     mmax = X.shape[1] - 1
     out = np.empty(12 * nside * nside)
     m = np.arange(mmax + 1)
-    for n in np.unique(g.nphi):
+
+    def one(n):
         rows = np.where(g.nphi == n)[0]
         Xs = X[rows] * np.exp(1j * m[None, :] * g.phi0[rows][:, None])
+        big = rows.size > 64                                      # the equatorial class: thread inside the batched FFT
         if 2 * mmax < n:
             # no aliasing: Hermitian half spectrum straight into a complex-to-real FFT
             h = np.zeros((rows.size, n // 2 + 1), dtype=complex)
             h[:, :mmax + 1] = Xs
-            x = np.fft.irfft(h, n=n, axis=1) * n
+            x = sfft.irfft(h, n=n, axis=1, workers=workers if big else None) * n
         else:
             full = np.zeros((rows.size, n), dtype=complex)       # spectrum of the m >= 0 part, wrapped mod n
             for j0 in range(0, mmax + 1, n):
@@ -173,27 +177,43 @@ def phase2map(nside, X):
             d = full.copy()                                        # add the conjugate (m < 0) images
             d[:, 0] += np.conj(full[:, 0]) - np.conj(Xs[:, 0])    # m = 0 itself has no mirror term
             d[:, 1:] += np.conj(full[:, :0:-1])
-            x = (np.fft.ifft(d, axis=1) * n).real
+            x = (sfft.ifft(d, axis=1, workers=workers if big else None) * n).real
         for a, r in enumerate(rows):
             out[g.start[r]:g.start[r] + n] = x[a]
+    _for_each_ring_length(one, np.unique(g.nphi)[::-1], workers)
     return out
 
 
-def map2phase(nside, mp, mmax):
+def _for_each_ring_length(fun, lengths, workers):
+    """the ~nside distinct cap-ring lengths are independent: spread them over threads when the caller asks for any"""
+    if workers in (None, 0, 1):
+        for n in lengths:
+            fun(n)
+        return
+    import concurrent.futures as cf
+    import os
+    nthr = os.cpu_count() if workers < 0 else workers
+    with cf.ThreadPoolExecutor(max_workers=nthr) as pool:
+        list(pool.map(fun, lengths))
+
+
+def map2phase(nside, mp, mmax, workers=None):
     """Adjoint ring FFT: X[ring, m] = sum_j map_j e^{-i m phi_j} (no weights)."""
     g = _Geom.get(nside)
     X = np.empty((g.nring, mmax + 1), dtype=complex)
     m = np.arange(mmax + 1)
-    for n in np.unique(g.nphi):
+
+    def one(n):
         rows = np.where(g.nphi == n)[0]
         x = np.stack([mp[g.start[r]:g.start[r] + n] for r in rows])
-        h = np.fft.rfft(x, axis=1)
+        h = sfft.rfft(x, axis=1, workers=workers if rows.size > 64 else None)
         if mmax <= n // 2:
             d = h[:, :mmax + 1]
         else:
             k = m % n
             d = np.where((k <= n // 2)[None, :], h[:, np.minimum(k, n // 2)], np.conj(h[:, np.minimum(n - k, n // 2)]))
         X[rows] = d * np.exp(-1j * m[None, :] * g.phi0[rows][:, None])
+    _for_each_ring_length(one, np.unique(g.nphi)[::-1], workers)
     return X
 
 

@@ -68,6 +68,7 @@ _SIGS = {
     'plk_map_qe_pp_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'plk_map_cmul_acc_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp, vp]),
     'plk_map_ninv3_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp]),
+    'plk_udgrade_sum_dev': (c_int, [c_int, vp, c_int, vp, vp]),
     'plk_map_modes_dot_dev': (c_int, [vp, vp, vp, vp, vp]),
     'plk_map_modes_sub_dev': (c_int, [vp, vp, vp, vp, vp, vp]),
 }

@@ -988,6 +988,15 @@ extern "C" int plk_map_ninv3_dev(long long n, double *q, double *u, const double
   LAUNCHED();
   return PLK_OK;
 }
+extern "C" int plk_udgrade_sum_dev(int nside_in, const double *in, int nside_out, double *out, void *stream) {
+  if (!in || !out) return fail(PLK_EINVAL, "NULL buffer");
+  if (nside_in < 1 || nside_out < 1 || (nside_in & (nside_in - 1)) || (nside_out & (nside_out - 1)) || nside_out > nside_in ||
+      nside_in > 8192)
+    return fail(PLK_EINVAL, "nside_in (%d) and nside_out (%d) must be powers of two, nside_out <= nside_in <= 8192", nside_in, nside_out);
+  udgrade_sum_kernel<<<flat_grid(12LL * nside_out * nside_out), 256, 0, (cudaStream_t)stream>>>(nside_in, in, nside_out, out);
+  LAUNCHED();
+  return PLK_OK;
+}
 extern "C" int plk_map_modes_dot_dev(plk_plan *p, double *m, const double *w, double *sums_dev, void *stream) {
   CHECK_PLAN(p);
   if (!m || !sums_dev) return fail(PLK_EINVAL, "NULL buffer");

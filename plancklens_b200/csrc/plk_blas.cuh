@@ -322,6 +322,80 @@ __global__ void phase_transpose_kernel(const cplx *__restrict__ T, int tpitch, c
   }
 }
 
+// ------------------------------------------------------------------ HEALPix degrade (sum of children), RING in / RING out
+// hp.ud_grade(n_inv, nside_out, power=-2) of opfilt_tt.py:172-181 / opfilt_pp.py:244-251 without the RING <-> NEST
+// permutations of the full-resolution map: one thread per OUTPUT pixel finds its (face, x, y) from the ring geometry,
+// walks its (nside_in / nside_out)^2 children in a fixed order and looks each one up at its RING position.
+// Index arithmetic: the published HEALPix pixelisation (Gorski et al. 2005), faces 0-3 north, 4-7 equatorial, 8-11 south.
+struct HpxFace { int jrll[12], jpll[12]; };
+PLK_HD HpxFace hpx_faces() {
+  HpxFace f = {{2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4}, {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7}};
+  return f;
+}
+PLK_HD long long hpx_isqrt(long long v) {
+  long long r = (long long)sqrt((double)v + 0.5);
+  while (r * r > v) --r;
+  while ((r + 1) * (r + 1) <= v) ++r;
+  return r;
+}
+PLK_HD void hpx_ring2xyf(long long nside, long long pix, int &ix, int &iy, int &face) {
+  const HpxFace F = hpx_faces();
+  const long long ncap = 2 * nside * (nside - 1), npix = 12 * nside * nside, nl2 = 2 * nside, nl4 = 4 * nside;
+  long long iring, iphi, kshift, nr;
+  if (pix < ncap) {
+    iring = (1 + hpx_isqrt(1 + 2 * pix)) >> 1;
+    iphi = pix + 1 - 2 * iring * (iring - 1);
+    kshift = 0; nr = iring;
+    face = (int)((iphi - 1) / nr);
+  } else if (pix < npix - ncap) {
+    const long long ip = pix - ncap, tmp = ip / nl4;
+    iring = tmp + nside;
+    iphi = ip - tmp * nl4 + 1;
+    kshift = (iring + nside) & 1;
+    nr = nside;
+    const long long ire = tmp + 1, irm = nl2 + 1 - tmp;
+    const long long ifm = (iphi - ire / 2 + nside - 1) / nside, ifp = (iphi - irm / 2 + nside - 1) / nside;
+    face = (int)((ifp == ifm) ? (ifp | 4) : ((ifp < ifm) ? ifp : (ifm + 8)));
+  } else {
+    const long long ip = npix - pix;
+    iring = (1 + hpx_isqrt(2 * ip - 1)) >> 1;
+    iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1));
+    kshift = 0; nr = iring;
+    iring = 2 * nl2 - iring;
+    face = 8 + (int)((iphi - 1) / nr);
+  }
+  const long long irt = iring - (long long)F.jrll[face] * nside + 1;
+  long long ipt = 2 * iphi - (long long)F.jpll[face] * nr - kshift - 1;
+  if (ipt >= nl2) ipt -= 8 * nside;
+  ix = (int)((ipt - irt) >> 1);
+  iy = (int)((-ipt - irt) >> 1);
+}
+PLK_HD long long hpx_xyf2ring(long long nside, int ix, int iy, int face) {
+  const HpxFace F = hpx_faces();
+  const long long nl4 = 4 * nside, ncap = 2 * nside * (nside - 1), npix = 12 * nside * nside;
+  const long long jr = (long long)F.jrll[face] * nside - ix - iy - 1;
+  long long nr, n_before, kshift;
+  if (jr < nside) { nr = jr; n_before = 2 * nr * (nr - 1); kshift = 0; }
+  else if (jr > 3 * nside) { nr = nl4 - jr; n_before = npix - 2 * (nr + 1) * nr; kshift = 0; }
+  else { nr = nside; n_before = ncap + (jr - nside) * nl4; kshift = (jr - nside) & 1; }
+  long long jp = ((long long)F.jpll[face] * nr + ix - iy + 1 + kshift) / 2;
+  if (jp > nl4) jp -= nl4;
+  else if (jp < 1) jp += nl4;
+  return n_before + jp - 1;
+}
+__global__ void udgrade_sum_kernel(int nside_in, const double *__restrict__ in, int nside_out, double *__restrict__ out) {
+  const long long npo = 12LL * nside_out * nside_out;
+  const int f = nside_in / nside_out;
+  for (long long po = (long long)blockIdx.x * blockDim.x + threadIdx.x; po < npo; po += (long long)gridDim.x * blockDim.x) {
+    int ix, iy, face;
+    hpx_ring2xyf(nside_out, po, ix, iy, face);
+    double acc = 0.0;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) acc += in[hpx_xyf2ring(nside_in, ix * f + dx, iy * f + dy, face)];
+    out[po] = acc;
+  }
+}
+
 // real-harmonic packing used by the dense preconditioner (reference: qcinv/dense.py:16-53)
 __global__ void alm2rlm_kernel(int lmax, const cplx *__restrict__ alm, double *__restrict__ rlm) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;

@@ -253,7 +253,7 @@ class alm_filter_ninv(object):
         self._load_ninv()
         if nside == self.nside:
             return self
-        return alm_filter_ninv([hp.ud_grade(n, nside, power=-2) for n in self.n_inv], self.b_transf_e,
+        return alm_filter_ninv([sht.ud_grade_sum(sht.dev_map(n), nside).cpu().numpy() for n in self.n_inv], self.b_transf_e,
                                b_transf_b=self.b_transf_b)
 
     def _fl(self, which, lmax):

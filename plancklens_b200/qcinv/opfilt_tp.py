@@ -220,7 +220,7 @@ class alm_filter_ninv(object):
         if nside == self.nside:
             return self
         print("DEGRADING WITH NO MARGE MAPS")
-        return alm_filter_ninv([hp.ud_grade(n, nside, power=-2) for n in self.n_inv], self.b_transf_t,
+        return alm_filter_ninv([sht.ud_grade_sum(sht.dev_map(n), nside).cpu().numpy() for n in self.n_inv], self.b_transf_t,
                                b_transf_e=self.b_transf_e, b_transf_b=self.b_transf_b,
                                marge_monopole=self.marge_monopole, marge_dipole=self.marge_dipole)
 

@@ -242,7 +242,7 @@ class alm_filter_ninv(object):
         if nside == self.nside:
             return self
         print("DEGRADING WITH NO MARGE MAPS")
-        return alm_filter_ninv(hp.ud_grade(self.n_inv, nside, power=-2), self.b_transf,
+        return alm_filter_ninv(sht.ud_grade_sum(self._ninv_d, nside).cpu().numpy(), self.b_transf,
                                marge_monopole=self.marge_monopole, marge_dipole=self.marge_dipole,
                                marge_uptolmin=self.marge_uptolmin, marge_maps=[])
 

@@ -321,6 +321,15 @@ def fp64_peak_tflops(reps=3):
     return float(v.value)
 
 
+def ud_grade_sum(m, nside_out):
+    """hp.ud_grade(m, nside_out, power=-2) of a RING map on the device: every coarse pixel = sum of its children"""
+    nside_in = int(round((m.numel() // 12) ** 0.5))
+    assert 12 * nside_in ** 2 == m.numel(), m.numel()
+    out = torch.empty(12 * int(nside_out) ** 2, dtype=torch.float64, device='cuda')
+    check(_lib.load().plk_udgrade_sum_dev(nside_in, _ptr(m), int(nside_out), _ptr(out), _stream()))
+    return out
+
+
 def map_mul(y, a):
     check(_lib.load().plk_map_mul_dev(y.numel(), _ptr(y), _ptr(a), _stream()))
     return y

@@ -217,3 +217,39 @@ extern "C" int emul_legendre_anal(int nside, int lmax, int spin, int pitch, cons
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- HEALPix degrade, Philox
+#include "../../plancklens_b200/csrc/plk_blas.cuh"
+#include "../../plancklens_b200/csrc/plk_rng.cuh"
+
+// the index arithmetic of udgrade_sum_kernel, one output pixel after the other
+extern "C" int emul_udgrade_sum(int nside_in, const double *in, int nside_out, double *out) {
+  const long long npo = 12LL * nside_out * nside_out;
+  const int f = nside_in / nside_out;
+  for (long long po = 0; po < npo; ++po) {
+    int ix, iy, face;
+    hpx_ring2xyf(nside_out, po, ix, iy, face);
+    double acc = 0.0;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) acc += in[hpx_xyf2ring(nside_in, ix * f + dx, iy * f + dy, face)];
+    out[po] = acc;
+  }
+  return 0;
+}
+// ring -> (face, x, y) -> ring must be the identity
+extern "C" long long emul_hpx_roundtrip_errors(int nside) {
+  long long bad = 0;
+  for (long long p = 0; p < 12LL * nside * nside; ++p) {
+    int ix, iy, face;
+    hpx_ring2xyf(nside, p, ix, iy, face);
+    if (ix < 0 || iy < 0 || ix >= nside || iy >= nside || face < 0 || face > 11 || hpx_xyf2ring(nside, ix, iy, face) != p) ++bad;
+  }
+  return bad;
+}
+extern "C" int emul_philox_words(unsigned long long seed, unsigned long long stream, long long ncalls, unsigned int *out) {
+  for (long long i = 0; i < ncalls; ++i) {
+    const Philox4 p = philox4x32_10((uint64_t)i, stream, seed);
+    for (int k = 0; k < 4; ++k) out[4 * i + k] = p.v[k];
+  }
+  return 0;
+}
