@@ -75,6 +75,14 @@ int plk_alm2map_dev(plk_plan *plan, int spin, const void *alm1, const void *alm2
 int plk_map2alm_dev(plk_plan *plan, int spin, const double *map1, const double *map2, const double *fl1,
                     const double *fl2, void *alm1, void *alm2, void *stream);
 
+/* Analysis with an additive per-l term folded into the output pass (no separate combine kernel):
+ *   alm_c = fl_c[l] * analysis_c + afl_c[l] * add_c[l, m]      (afl_c: lmax + 1 doubles; add_c must not alias alm_c)
+ * -- the forward operator of the CG filters, A x = S^-1 x + B^t N^-1 B x (qcinv/opfilt_tt.py:67-73, opfilt_pp.py:51-55
+ * with a diagonal S^-1): add = x, afl = 1 / C_l.  add2 / afl2 are ignored for spin 0. */
+int plk_map2alm_add_dev(plk_plan *plan, int spin, const double *map1, const double *map2, const double *fl1,
+                        const double *fl2, const void *add1, const double *afl1, const void *add2, const double *afl2,
+                        void *alm1, void *alm2, void *stream);
+
 /* ---- transforms, host pointers (numpy arrays on the Python side) */
 int plk_alm2map_host(plk_plan *plan, int spin, const void *alm1, const void *alm2, double *map1, double *map2);
 int plk_map2alm_host(plk_plan *plan, int spin, const double *map1, const double *map2, void *alm1, void *alm2);
@@ -100,6 +108,18 @@ int plk_alm_dot2_dev(int lmax, int lmin, const void *a1, const void *b1, const v
 /* n <= 4 components (opfilt_tp.py:46-58: T, E and B summed, all from lmin), host arrays of device pointers */
 int plk_alm_dotn_dev(int lmax, int lmin, int n, const void *const *a, const void *const *b, double *result_dev,
                      void *stream);
+/* One-kernel form of the dot products above (n <= 4 components) with the CG step-length arithmetic of
+ * cd_solve.py:69-71, :95-99 folded into the final sum (the block that finishes last adds the per-m partials in a fixed
+ * order, so results are reproducible):
+ *   out3[0] = s = sum_j dot(a_j, b_j)
+ *   num != NULL: out3[1] = scale * num[0] / s, out3[2] = -out3[1]     (alpha = (d.r)/(d.Ad) and -alpha)
+ *   den != NULL: out3[1] = scale * s / den[0], out3[2] = -out3[1]     (beta = -(d'.Ad)/(d.Ad) with scale = -1)
+ * num, den, out3 are device pointers; a zero divisor gives 0.  At most one of num / den. */
+int plk_alm_dot_fused_dev(int lmax, int lmin, int n, const void *const *a, const void *const *b, const double *num,
+                          const double *den, double scale, double *out3, void *stream);
+/* y1 += a x1 ; y2 -= a x2 with a read from device memory: solution and residual update of one CG iteration
+ * (cd_solve.py:75, :82-84) in one pass */
+int plk_alm_axpy2_dev(long long n, const double *a_dev, const void *x1, void *y1, const void *x2, void *y2, void *stream);
 /* cl[l] = 1/(2l+1) sum_m a_lm conj(b_lm) over m = -l..l for real fields (hp.alm2cl; qecl.py:148, nhl.py:175-189) */
 int plk_alm2cl_dev(int lmax, const void *a, const void *b, double *cl, void *stream);
 /* out_dev[0] = scale * num_dev[0] / den_dev[0]: CG step lengths (cd_solve.py:69-71, :95-99) kept on the device so that

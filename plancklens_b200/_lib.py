@@ -31,6 +31,9 @@ _SIGS = {
     'plk_alm_dot_dev': (c_int, [c_int, c_int, vp, vp, vp, vp]),
     'plk_alm_dot2_dev': (c_int, [c_int, c_int, vp, vp, vp, vp, vp, vp]),
     'plk_alm_dotn_dev': (c_int, [c_int, c_int, c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]),
+    'plk_alm_dot_fused_dev': (c_int, [c_int, c_int, c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, c_dbl, vp, vp]),
+    'plk_alm_axpy2_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp]),
+    'plk_map2alm_add_dev': (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'plk_alm2cl_dev': (c_int, [c_int, vp, vp, vp, vp]),
     'plk_scalar_ratio_dev': (c_int, [vp, vp, c_dbl, vp, vp]),
     'plk_alm_copy_dev': (c_int, [c_int, vp, c_int, vp, vp]),

@@ -472,8 +472,9 @@ static int legendre_synth(plk_plan *p, int spin, const void *alm1, const void *a
   return 0;
 }
 
+struct AlmAdd { const cplx *a1 = nullptr, *a2 = nullptr; const double *f1 = nullptr, *f2 = nullptr; };
 static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, const double *fl1, const double *fl2,
-                         void *alm1, void *alm2, cudaStream_t st, const plk_dist *dd = nullptr) {
+                         void *alm1, void *alm2, cudaStream_t st, const plk_dist *dd = nullptr, AlmAdd add = AlmAdd()) {
   int rc = ensure_spin(p, spin);
   if (rc) return rc;
   const DevSpin &d = p->spins[spin].d;
@@ -504,8 +505,8 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   prof_end(st);
   LAUNCHED();
   dim3 pg((p->lmax + 256) / 256, nm);
-  if (spin == 0) finish_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, nullptr, (cplx *)alm1, nullptr, morder);
-  else finish_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, fl2, (cplx *)alm1, (cplx *)alm2, morder);
+  if (spin == 0) finish_alm_kernel<false><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, nullptr, (cplx *)alm1, nullptr, morder, add.a1, add.f1, nullptr, nullptr);
+  else finish_alm_kernel<true><<<pg, 256, 0, st>>>(d, (const double *)p->part.p, stride, ntile, fl1, fl2, (cplx *)alm1, (cplx *)alm2, morder, add.a1, add.f1, add.a2, add.f2);
   LAUNCHED();
   return 0;
 }
@@ -584,8 +585,8 @@ extern "C" int plk_alm2map_dev(plk_plan *p, int spin, const void *alm1, const vo
   return PLK_OK;
 }
 
-extern "C" int plk_map2alm_dev(plk_plan *p, int spin, const double *map1, const double *map2, const double *fl1,
-                               const double *fl2, void *alm1, void *alm2, void *stream) {
+static int map2alm_impl(plk_plan *p, int spin, const double *map1, const double *map2, const double *fl1,
+                        const double *fl2, void *alm1, void *alm2, void *stream, AlmAdd add) {
   CHECK_PLAN(p);
   if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
   if (!alm1 || !map1 || (spin > 0 && (!map2 || !alm2))) return fail(PLK_EINVAL, "NULL buffer");
@@ -596,7 +597,22 @@ extern "C" int plk_map2alm_dev(plk_plan *p, int spin, const double *map1, const 
   const int *mtop = p->spins[spin].d.mtop;
   if ((rc = ring_anal(p, map1, (cplx *)p->X1.p, st, mtop))) return rc;
   if (spin > 0 && (rc = ring_anal(p, map2, (cplx *)p->X2.p, st, mtop))) return rc;
-  return legendre_anal(p, spin, (const cplx *)p->X1.p, (const cplx *)p->X2.p, fl1, fl2, alm1, alm2, st);
+  return legendre_anal(p, spin, (const cplx *)p->X1.p, (const cplx *)p->X2.p, fl1, fl2, alm1, alm2, st, nullptr, add);
+}
+extern "C" int plk_map2alm_dev(plk_plan *p, int spin, const double *map1, const double *map2, const double *fl1,
+                               const double *fl2, void *alm1, void *alm2, void *stream) {
+  return map2alm_impl(p, spin, map1, map2, fl1, fl2, alm1, alm2, stream, AlmAdd());
+}
+// analysis with an additive per-l term folded into the output pass: alm_c = fl_c * analysis_c + afl_c[l] * add_c
+// (afl_c: lmax + 1 doubles; add_c must not alias alm_c)
+extern "C" int plk_map2alm_add_dev(plk_plan *p, int spin, const double *map1, const double *map2, const double *fl1,
+                                   const double *fl2, const void *add1, const double *afl1, const void *add2,
+                                   const double *afl2, void *alm1, void *alm2, void *stream) {
+  if (!add1 || !afl1 || (spin > 0 && (!add2 || !afl2))) return fail(PLK_EINVAL, "NULL additive term");
+  if (add1 == alm1 || (spin > 0 && add2 == alm2)) return fail(PLK_EINVAL, "additive term aliases the output");
+  AlmAdd add;
+  add.a1 = (const cplx *)add1; add.f1 = afl1; add.a2 = (const cplx *)add2; add.f2 = afl2;
+  return map2alm_impl(p, spin, map1, map2, fl1, fl2, alm1, alm2, stream, add);
 }
 
 // ------------------------------------------------------------------------------------------ m-partitioned transforms
@@ -853,11 +869,16 @@ extern "C" int plk_map2alm_host(plk_plan *p, int spin, const double *map1, const
 
 // ------------------------------------------------------------------------------------------ BLAS-1 / pixel passes
 static double *g_scratch = nullptr;   // per-process reduction scratch (current device at first use)
+static unsigned int *g_ticket = nullptr;   // ticket counters of the last-block reductions (zero between launches)
 static const size_t kScratchDoubles = 1 << 17;
 static int scratch() {
   if (g_scratch) return 0;
   cudaError_t e = cudaMalloc((void **)&g_scratch, kScratchDoubles * sizeof(double));
   if (e != cudaSuccess) return fail(PLK_ENOMEM, "cudaMalloc(scratch) failed: %s", cudaGetErrorString(e));
+  e = cudaMalloc((void **)&g_ticket, 64 * sizeof(unsigned int));
+  if (e != cudaSuccess) return fail(PLK_ENOMEM, "cudaMalloc(ticket) failed: %s", cudaGetErrorString(e));
+  e = cudaMemset(g_ticket, 0, 64 * sizeof(unsigned int));
+  if (e != cudaSuccess) return fail(PLK_ECUDA, "cudaMemset(ticket) failed: %s", cudaGetErrorString(e));
   return 0;
 }
 static int flat_grid(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
@@ -913,6 +934,33 @@ extern "C" int plk_alm_dotn_dev(int lmax, int lmin, int n, const void *const *a,
     LAUNCHED();
   }
   final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, n * (lmax + 1), 1, result_dev);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_dot_fused_dev(int lmax, int lmin, int n, const void *const *a, const void *const *b, const double *num,
+                                     const double *den, double scale, double *out3, void *stream) {
+  if (!a || !b || !out3 || lmax < 0 || n < 1 || n > 4) return fail(PLK_EINVAL, "bad argument");
+  if (num && den) return fail(PLK_EINVAL, "give num or den, not both");
+  int rc = scratch();
+  if (rc) return rc;
+  if ((size_t)n * ((size_t)lmax + 1) > kScratchDoubles / 2) return fail(PLK_EINVAL, "lmax too large");
+  DotArgs q;
+  q.n = n;
+  for (int j = 0; j < 4; ++j) { q.a[j] = nullptr; q.b[j] = nullptr; }
+  for (int j = 0; j < n; ++j) {
+    if (!a[j] || !b[j]) return fail(PLK_EINVAL, "NULL component");
+    q.a[j] = (const cplx *)a[j]; q.b[j] = (const cplx *)b[j];
+  }
+  // second half of the scratch: the first half belongs to the two-kernel dots, which may be in flight on the stream
+  dot_fused_kernel<<<n * (lmax + 1), 256, 0, (cudaStream_t)stream>>>(q, lmax, lmin, g_scratch + kScratchDoubles / 2, g_ticket,
+                                                                      num, den, scale, out3);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_axpy2_dev(long long n, const double *a_dev, const void *x1, void *y1, const void *x2, void *y2, void *stream) {
+  if (!a_dev || !x1 || !y1 || !x2 || !y2 || n < 0) return fail(PLK_EINVAL, "bad argument");
+  axpy2_kernel<<<flat_grid(2 * n), 256, 0, (cudaStream_t)stream>>>(2 * n, a_dev, (const double *)x1, (double *)y1,
+                                                                    (const double *)x2, (double *)y2);
   LAUNCHED();
   return PLK_OK;
 }
@@ -1002,9 +1050,8 @@ extern "C" int plk_map_modes_dot_dev(plk_plan *p, double *m, const double *w, do
   if (!m || !sums_dev) return fail(PLK_EINVAL, "NULL buffer");
   int rc = ensure(p->partial, (size_t)4 * p->nring * sizeof(double));
   if (rc) return rc;
-  modes_dot_kernel<<<p->nring, 256, 0, (cudaStream_t)stream>>>(p->rings, m, w, (double *)p->partial.p);
-  LAUNCHED();
-  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const double *)p->partial.p, p->nring, 4, sums_dev);
+  if ((rc = scratch())) return rc;
+  modes_dot_kernel<<<p->nring, 256, 0, (cudaStream_t)stream>>>(p->rings, m, w, (double *)p->partial.p, g_ticket + 1, sums_dev);
   LAUNCHED();
   return PLK_OK;
 }

@@ -39,16 +39,23 @@ __global__ void prep_alm_kernel(DevSpin t, const cplx *__restrict__ a1, const cp
 template <bool SPIN>
 __global__ void finish_alm_kernel(DevSpin t, const double *__restrict__ part, long long part_stride, int ntile,
                                   const double *__restrict__ fl1, const double *__restrict__ fl2,
-                                  cplx *__restrict__ a1, cplx *__restrict__ a2, const int *__restrict__ morder) {
+                                  cplx *__restrict__ a1, cplx *__restrict__ a2, const int *__restrict__ morder,
+                                  const cplx *__restrict__ add1 = nullptr, const double *__restrict__ afl1 = nullptr,
+                                  const cplx *__restrict__ add2 = nullptr, const double *__restrict__ afl2 = nullptr) {
+  // add1 / add2 (optional): out_c += afl_c[l] * add_c[l, m] -- the S^-1 x term of the CG forward operators
+  // (opfilt_tt.py:67-73, opfilt_pp.py:51-55 with a diagonal S^-1) folded into the analysis output pass
   constexpr int NV = SPIN ? 4 : 2;
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = morder[blockIdx.y];
   if (l > t.lmax || l < m) return;
   const int64_t i = alm_idx(t.lmax, l, m);
   const int l0 = m > t.spin ? m : t.spin;
+  cplx e1 = mk(0.0, 0.0), e2 = mk(0.0, 0.0);
+  if (add1) { const cplx x = add1[i]; const double f = afl1[l]; e1 = mk(f * x.x, f * x.y); }
+  if (SPIN && add2) { const cplx x = add2[i]; const double f = afl2[l]; e2 = mk(f * x.x, f * x.y); }
   if (l < l0) {
-    a1[i] = mk(0.0, 0.0);
-    if (SPIN) a2[i] = mk(0.0, 0.0);
+    a1[i] = e1;
+    if (SPIN) a2[i] = e2;
     return;
   }
   double v[NV];
@@ -67,14 +74,14 @@ __global__ void finish_alm_kernel(DevSpin t, const double *__restrict__ part, lo
   const double al = t.alpha[i];
   const double s1 = al * (fl1 ? fl1[l] : 1.0);
   if (!SPIN) {
-    a1[i] = mk(s1 * v[0], s1 * v[1]);
+    a1[i] = mk(fma(s1, v[0], e1.x), fma(s1, v[1], e1.y));
   } else {
     const double s2 = al * (fl2 ? fl2[l] : 1.0);
     const double sg = (t.spin & 1) ? -1.0 : 1.0;
     // +a = S+, -a' = (-1)^s S-;  G = -1/2 (+a + -a') ; C = i/2 (+a - -a')
     const double pr = v[0], pi = v[1], mr = sg * v[2], mi = sg * v[3];
-    a1[i] = mk(-0.5 * s1 * (pr + mr), -0.5 * s1 * (pi + mi));
-    a2[i] = mk(-0.5 * s2 * (pi - mi), 0.5 * s2 * (pr - mr));
+    a1[i] = mk(fma(-0.5 * s1, pr + mr, e1.x), fma(-0.5 * s1, pi + mi, e1.y));
+    a2[i] = mk(fma(-0.5 * s2, pi - mi, e2.x), fma(0.5 * s2, pr - mr, e2.y));
   }
 }
 
@@ -139,6 +146,63 @@ __global__ void final_sum_kernel(const double *__restrict__ partial, int n, int 
   }
 }
 
+// Last-block pattern: every block publishes its partial, takes a ticket; the block that draws the last ticket sums all
+// partials in a FIXED order (thread-strided, then the block tree) -- the result does not depend on which block that is.
+PLK_D bool last_block_ticket(unsigned int *counter, bool *s_last) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    *s_last = (t == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (*s_last) __threadfence();
+  return *s_last;
+}
+// One-kernel weighted dot product of up to four alm pairs (opfilt_tt.py:43-51, opfilt_pp.py:27-34, opfilt_tp.py:46-58)
+// with the CG step-length arithmetic of cd_solve.py:69-71, :95-99 folded into the final sum:
+//   out[0] = s = sum_j sum_{l >= lmin} w_m Re(a_j conj b_j)
+//   num != null:  out[1] = scale * num[0] / s,  out[2] = -out[1]       (alpha = (d.r) / (d.Ad) and -alpha)
+//   den != null:  out[1] = scale * s / den[0],  out[2] = -out[1]       (beta = -(d'.Ad) / (d.Ad))
+// A zero divisor gives 0 (the reference's monitor stops a stage whose residual is exactly zero before dividing).
+struct DotArgs { const cplx *a[4], *b[4]; int n; };
+__global__ void dot_fused_kernel(DotArgs q, int lmax, int lmin, double *__restrict__ partial, unsigned int *counter,
+                                 const double *__restrict__ num, const double *__restrict__ den, double scale,
+                                 double *__restrict__ out) {
+  __shared__ double sh[32];
+  __shared__ bool s_last;
+  const int j = blockIdx.x / (lmax + 1), m = blockIdx.x - j * (lmax + 1);
+  const cplx *a = q.a[j], *b = q.b[j];
+  double acc = 0.0;
+  const int lo = m > lmin ? m : lmin;
+  const int64_t base = alm_idx(lmax, 0, m);
+  for (int l = lo + threadIdx.x; l <= lmax; l += blockDim.x) {
+    const cplx x = a[base + l], y = b[base + l];
+    acc = fma(x.x, y.x, fma(x.y, y.y, acc));
+  }
+  const double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = (m == 0 ? 1.0 : 2.0) * r;
+  if (!last_block_ticket(counter, &s_last)) return;
+  double tot = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += __ldcg(partial + i);
+  const double s = block_sum(tot, sh);
+  if (threadIdx.x == 0) {
+    out[0] = s;
+    if (num) { const double v = s != 0.0 ? scale * (num[0] / s) : 0.0; out[1] = v; out[2] = -v; }
+    else if (den) { const double d = den[0]; const double v = d != 0.0 ? scale * (s / d) : 0.0; out[1] = v; out[2] = -v; }
+    *counter = 0u;
+  }
+}
+// y1 += a x1 ; y2 -= a x2 (a from device memory): the solution and residual updates of one CG iteration
+// (cd_solve.py:75, :82-84) in one pass
+__global__ void axpy2_kernel(long long n2, const double *__restrict__ a_dev, const double *__restrict__ x1,
+                             double *__restrict__ y1, const double *__restrict__ x2, double *__restrict__ y2) {
+  const double aa = *a_dev;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    y1[i] = fma(aa, x1[i], y1[i]);
+    y2[i] = fma(-aa, x2[i], y2[i]);
+  }
+}
+
 // cl[l] = 1/(2l+1) sum_m w_m Re(a_lm conj b_lm), w_0 = 1, w_{m>0} = 2 (hp.alm2cl); one thread per l, coalesced over l
 __global__ void alm2cl_kernel(int lmax, const cplx *__restrict__ a, const cplx *__restrict__ b, double *__restrict__ cl) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,7 +220,8 @@ __global__ void alm2cl_kernel(int lmax, const cplx *__restrict__ a, const cplx *
 // out[0] = scale * num[0] / den[0]: the CG step lengths (cd_solve.py:69-71, :95-99) without a host round trip
 __global__ void scalar_ratio_kernel(const double *__restrict__ num, const double *__restrict__ den, double scale,
                                     double *__restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = scale * (num[0] / den[0]);
+  // a zero denominator gives 0: an exactly-zero residual (all-zero or fully masked input) must not poison the solve
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = den[0] != 0.0 ? scale * (num[0] / den[0]) : 0.0;
 }
 
 __global__ void alm_copy_kernel(int lmax_in, const cplx *__restrict__ in, int lmax_out, cplx *__restrict__ out) {
@@ -237,8 +302,9 @@ struct DevRings {
   const double *z, *sth;    // [nring]
 };
 __global__ void modes_dot_kernel(DevRings r, double *__restrict__ m, const double *__restrict__ w,
-                                 double *__restrict__ partial) {
+                                 double *__restrict__ partial, unsigned int *counter, double *__restrict__ sums) {
   __shared__ double sh[32];
+  __shared__ bool s_last;
   const int ir = blockIdx.x;
   const int n = r.nphi[ir];
   const long long st = r.start[ir];
@@ -255,6 +321,15 @@ __global__ void modes_dot_kernel(DevRings r, double *__restrict__ m, const doubl
     partial[0 * r.nring + ir] = r0; partial[1 * r.nring + ir] = r1;
     partial[2 * r.nring + ir] = r2; partial[3 * r.nring + ir] = r3;
   }
+  // the block with the last ticket sums the ring partials in ring order (fixed, deterministic)
+  if (!last_block_ticket(counter, &s_last)) return;
+  for (int j = 0; j < 4; ++j) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < r.nring; i += blockDim.x) acc += __ldcg(partial + (size_t)j * r.nring + i);
+    const double t = block_sum(acc, sh);
+    if (threadIdx.x == 0) sums[j] = t;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
 }
 // m_p -= w_p * sum_a mode_a(p) coef_a,  coef = pinv(4x4, row-major) @ sums
 __global__ void modes_sub_kernel(DevRings r, double *__restrict__ m, const double *__restrict__ w,
@@ -383,16 +458,63 @@ PLK_HD long long hpx_xyf2ring(long long nside, int ix, int iy, int face) {
   else if (jp < 1) jp += nl4;
   return n_before + jp - 1;
 }
+// Sum of the f^2 children of output pixel (face, ix, iy) in the ORDER numpy uses for
+// `nest_map.reshape(npix_out, f * f).sum(axis=1)` -- what healpy.ud_grade and the oracle do: children in NEST order
+// (x in the even bits of the child index, y in the odd ones), fewer than 8 terms added one after the other, otherwise
+// numpy's pairwise summation (eight interleaved partial sums per block of <= 128 terms, combined as a balanced tree;
+// longer rows are halved recursively).  Matching the order keeps the degraded inverse-noise maps bit-identical to the
+// reference's, which matters more than it should: the dense coarse preconditioner inverts "all but the ntmpl lowest
+// eigenmodes" (dense.py:94-105), and when eigenvalues around that cut are nearly degenerate a last-bit change of the
+// matrix swaps the modes and moves the whole CG trajectory by ~eps_min.
+PLK_HD int hpx_compress_even_bits(unsigned int v) {
+  v &= 0x55555555u;
+  v = (v | (v >> 1)) & 0x33333333u;
+  v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+  v = (v | (v >> 4)) & 0x00FF00FFu;
+  v = (v | (v >> 8)) & 0x0000FFFFu;
+  return (int)v;
+}
+PLK_HD double hpx_child(const double *in, int nside_in, int f, int ix, int iy, int face, int k) {
+  const int dx = hpx_compress_even_bits((unsigned int)k), dy = hpx_compress_even_bits((unsigned int)k >> 1);
+  return in[hpx_xyf2ring(nside_in, ix * f + dx, iy * f + dy, face)];
+}
+PLK_HD double hpx_block_sum(const double *in, int nside_in, int f, int ix, int iy, int face, int k0, int n) {   // 8 <= n <= 128
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = hpx_child(in, nside_in, f, ix, iy, face, k0 + j);
+  for (int i = 8; i < n; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] += hpx_child(in, nside_in, f, ix, iy, face, k0 + i + j);
+  }
+  return ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+}
+PLK_HD double hpx_children_sum(const double *in, int nside_in, int nside_out, int ix, int iy, int face) {
+  const int f = nside_in / nside_out, fac = f * f;
+  if (fac < 8) {
+    double res = 0.0;
+    for (int k = 0; k < fac; ++k) res += hpx_child(in, nside_in, f, ix, iy, face, k);
+    return res;
+  }
+  if (fac <= 128) return hpx_block_sum(in, nside_in, f, ix, iy, face, 0, fac);
+  // fac = 4^j > 128: numpy halves the row until the pieces hold 128 terms; the halves are added as a balanced tree
+  double blk[128];
+  int nb = fac / 128;
+  if (nb > 128) nb = 128;                      // f <= 128 (nside ratio); larger ratios fall back to longer leaves below
+  const int leaf = fac / nb;
+  for (int b = 0; b < nb; ++b) {
+    if (leaf <= 128) blk[b] = hpx_block_sum(in, nside_in, f, ix, iy, face, b * leaf, leaf);
+    else { double t = 0.0; for (int k = 0; k < leaf; ++k) t += hpx_child(in, nside_in, f, ix, iy, face, b * leaf + k); blk[b] = t; }
+  }
+  for (int n = nb; n > 1; n >>= 1)
+    for (int b = 0; b < n / 2; ++b) blk[b] = blk[2 * b] + blk[2 * b + 1];
+  return blk[0];
+}
 __global__ void udgrade_sum_kernel(int nside_in, const double *__restrict__ in, int nside_out, double *__restrict__ out) {
   const long long npo = 12LL * nside_out * nside_out;
-  const int f = nside_in / nside_out;
   for (long long po = (long long)blockIdx.x * blockDim.x + threadIdx.x; po < npo; po += (long long)gridDim.x * blockDim.x) {
     int ix, iy, face;
     hpx_ring2xyf(nside_out, po, ix, iy, face);
-    double acc = 0.0;
-    for (int dy = 0; dy < f; ++dy)
-      for (int dx = 0; dx < f; ++dx) acc += in[hpx_xyf2ring(nside_in, ix * f + dx, iy * f + dy, face)];
-    out[po] = acc;
+    out[po] = hpx_children_sum(in, nside_in, nside_out, ix, iy, face);
   }
 }
 

@@ -71,8 +71,12 @@ class multigrid_chain:
         monitor = cd_monitors.monitor_basic(dot_op, logger=logger, iter_max=self.bstage.iter_max,
                                             eps_min=self.bstage.eps_min, d0=dot_op(tpn_alm, tpn_alm))
         fwd_op = self.opfilt.fwd_op(self.s_cls, self.n_inv_filt)
-        self.niter = cd_solve.cd_solve(dsol, tpn_alm, fwd_op, self.bstage.pre_ops, dot_op, monitor,
-                                       tr=self.bstage.tr, cache=self.bstage.cache)
+        if cd_solve.can_solve_dev(self.bstage.pre_ops, dot_op, self.bstage.tr) and os.environ.get('PLK_CG_DEVTOP', '1') != '0':
+            # step lengths stay on the device: one host synchronisation per iteration (the monitor's) instead of four
+            self.niter = cd_solve.cd_solve_dev(dsol, tpn_alm, fwd_op, self.bstage.pre_ops, dot_op, monitor)
+        else:
+            self.niter = cd_solve.cd_solve(dsol, tpn_alm, fwd_op, self.bstage.pre_ops, dot_op, monitor,
+                                           tr=self.bstage.tr, cache=self.bstage.cache)
         finifunc(dsol, self.s_cls, self.n_inv_filt)
         self.last_monitor = monitor
         if writeback is not None:

@@ -58,6 +58,11 @@ class dot_op:
         assert alm1.lmax == alm2.lmax
         return sht.alm_dot2(alm1.elm.t, alm2.elm.t, alm1.blm.t, alm2.blm.t, lmin=2)
 
+    def fused(self, alm1, alm2, num=None, den=None, scale=1.0):
+        """[s, r, -r] on the device in one kernel (see opfilt_tt.dot_op.fused)"""
+        assert alm1.lmax == alm2.lmax
+        return sht.alm_dot_fused([alm1.elm.t, alm1.blm.t], [alm2.elm.t, alm2.blm.t], lmin=2, num=num, den=den, scale=scale)
+
 
 class _lmat2:
     """Per-l symmetric 2x2 matrix applied to an (E, B) pair: one four-term combine per component."""
@@ -109,6 +114,7 @@ class fwd_op:
         lmax = len(n_inv_filt.b_transf) - 1
         self.s_inv_filt = alm_filter_sinv(s_cls, lmax)
         self.n_inv_filt = n_inv_filt
+        self._sl_d = {}
 
     def hashdict(self):
         return {'s_inv_filt': self.s_inv_filt.hashdict(), 'n_inv_filt': self.n_inv_filt.hashdict()}
@@ -121,6 +127,21 @@ class fwd_op:
             # A 0 = 0 exactly (every stage is linear): skip the two spin-2 transforms on the zero start vector of the
             # solver.  The reference has this shortcut in opfilt_tt (opfilt_tt.py:68) only; the result is identical.
             return alm * 1.0
+        sl = self.s_inv_filt.slinv
+        if isinstance(alm.elm, dalm) and not np.any(sl[:, 0, 1]):
+            # diagonal S^-1 (no EB spectrum, the usual case): apply_alm (opfilt_pp.py:253-270) with the S^-1 x term
+            # folded into the output pass of the spin-2 analysis -- two transforms and the N^-1 kernel, nothing else
+            nf = self.n_inv_filt
+            nf._load_ninv()
+            lmax = alm.lmax
+            plan = sht.get_plan(nf.nside, lmax)
+            qmap, umap = plan.alm2map_spin(alm.elm.t, alm.blm.t, 2, flg=nf._fl('ein', lmax), flc=nf._fl('bin', lmax))
+            nf.apply_map([qmap, umap])
+            if lmax not in self._sl_d:
+                self._sl_d[lmax] = (sht.dev_fl(sl[:, 0, 0], lmax), sht.dev_fl(sl[:, 1, 1], lmax))
+            se, sb = self._sl_d[lmax]
+            e, b = plan.map2alm_spin_add(qmap, umap, 2, nf._fl('eout', lmax), nf._fl('bout', lmax), alm.elm.t, se, alm.blm.t, sb)
+            return eblm([dalm(e, lmax), dalm(b, lmax)])
         nlm = alm * 1.0
         self.n_inv_filt.apply_alm(nlm)
         slm = self.s_inv_filt.calc(alm)

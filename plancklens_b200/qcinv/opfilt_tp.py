@@ -54,6 +54,12 @@ class dot_op:
         assert alm1.lmaxt == alm1.lmaxe == alm1.lmaxb
         return sht.alm_dotn([alm1.tlm.t, alm1.elm.t, alm1.blm.t], [alm2.tlm.t, alm2.elm.t, alm2.blm.t], lmin=0)
 
+    def fused(self, alm1, alm2, num=None, den=None, scale=1.0):
+        """[s, r, -r] on the device in one kernel (see opfilt_tt.dot_op.fused)"""
+        assert alm1.lmaxt == alm1.lmaxe == alm1.lmaxb == alm2.lmaxt == alm2.lmaxe == alm2.lmaxb
+        return sht.alm_dot_fused([alm1.tlm.t, alm1.elm.t, alm1.blm.t], [alm2.tlm.t, alm2.elm.t, alm2.blm.t], lmin=0,
+                                 num=num, den=den, scale=scale)
+
     def __call__(self, alm1, alm2):
         return float(self.dev(alm1, alm2).item())
 

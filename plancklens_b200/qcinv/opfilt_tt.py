@@ -68,6 +68,12 @@ class dot_op:
         assert alm1.lmax == alm2.lmax
         return sht.alm_dot(alm1.t, alm2.t, lmin=0)
 
+    def fused(self, alm1, alm2, num=None, den=None, scale=1.0):
+        """[s, r, -r] on the device in ONE kernel: s the dot product, r = scale * num / s or scale * s / den
+        (the step lengths of cd_solve.py:69-71, :95-99)"""
+        assert alm1.lmax == alm2.lmax
+        return sht.alm_dot_fused([alm1.t], [alm2.t], lmin=0, num=num, den=den, scale=scale)
+
 
 class fwd_op:
     """A x = C_l^{-1} x + B^t N^{-1} B x  (reference: opfilt_tt.py:54-73)."""
@@ -76,7 +82,7 @@ class fwd_op:
         self.cltt_inv = _cli(s_cls['tt'])
         self.n_inv_filt = n_inv_filt
         self._cltt_inv_d = _dev(self.cltt_inv)
-        self._ones_d = None
+        self._cli_d = {}
 
     def hashdict(self):
         return {'cltt_inv': clhash(self.cltt_inv), 'n_inv_filt': self.n_inv_filt.hashdict()}
@@ -87,10 +93,15 @@ class fwd_op:
     def calc(self, talm):
         if talm.is_zero():   # do nothing if zero (reference: opfilt_tt.py:68)
             return talm
-        alm = talm.copy()
-        self.n_inv_filt.apply_alm(alm)
-        alm.t = _combine2(alm.t, None, talm.t, self._cltt_inv_d)
-        return alm
+        # apply_alm (opfilt_tt.py:183-190) with the C_l^-1 x term folded into the output pass of the analysis
+        nf = self.n_inv_filt
+        lmax = talm.lmax
+        plan = sht.get_plan(nf.nside, lmax)
+        tmap = plan.alm2map(talm.t, fl=nf.fl_in(lmax))
+        nf.apply_map(tmap)
+        if lmax not in self._cli_d:
+            self._cli_d[lmax] = sht.dev_fl(self.cltt_inv, lmax)
+        return dalm(plan.map2alm_add(tmap, nf.fl_out(lmax), talm.t, self._cli_d[lmax]), lmax)
 
 
 def _combine2(a, fla, b, flb):

@@ -120,6 +120,25 @@ class Plan:
         check(self.lib.plk_map2alm_dev(self._h, 0, _ptr(m), None, _ptr(fl), None, _ptr(out), None, _stream()))
         return out
 
+    def map2alm_add(self, m, fl, add, afl, out=None):
+        """fl * map2alm(m) + afl[l] * add in one output pass (CG forward operators); add must not alias out"""
+        assert m.numel() == self.npix and add.numel() == self.nalm and afl.numel() == self.lmax + 1
+        out = torch.empty(self.nalm, dtype=torch.complex128, device='cuda') if out is None else out
+        check(self.lib.plk_map2alm_add_dev(self._h, 0, _ptr(m), None, _ptr(fl), None, _ptr(add), _ptr(afl), None, None,
+                                           _ptr(out), None, _stream()))
+        return out
+
+    def map2alm_spin_add(self, m1, m2, spin, flg, flc, addg, aflg, addc, aflc, out=None):
+        assert spin in (1, 2, 3), spin
+        assert addg.numel() == self.nalm and addc.numel() == self.nalm
+        assert aflg.numel() == self.lmax + 1 and aflc.numel() == self.lmax + 1
+        if out is None:
+            out = (torch.empty(self.nalm, dtype=torch.complex128, device='cuda'),
+                   torch.empty(self.nalm, dtype=torch.complex128, device='cuda'))
+        check(self.lib.plk_map2alm_add_dev(self._h, spin, _ptr(m1), _ptr(m2), _ptr(flg), _ptr(flc), _ptr(addg), _ptr(aflg),
+                                           _ptr(addc), _ptr(aflc), _ptr(out[0]), _ptr(out[1]), _stream()))
+        return out
+
     def map2alm_spin(self, m1, m2, spin, flg=None, flc=None, out=None):
         assert spin in (1, 2, 3), spin
         assert m1.numel() == self.npix and m2.numel() == self.npix
@@ -250,6 +269,23 @@ def alm_dotn(avec, bvec, lmin=0, out=None):
     pb = (ctypes.c_void_p * n)(*[t.data_ptr() for t in bvec])
     check(lib.plk_alm_dotn_dev(lmax, lmin, n, pa, pb, _ptr(out), _stream()))
     return out
+
+
+def alm_dot_fused(avec, bvec, lmin=0, num=None, den=None, scale=1.0, out=None):
+    """One-kernel dot product of up to four alm pairs -> 3-element device tensor [s, r, -r] with r = scale * num / s
+    (num given), scale * s / den (den given); num / den are 1-element device tensors (plk_alm_dot_fused_dev)"""
+    n = len(avec)
+    lmax = alm_lmax(avec[0].numel())
+    out = torch.empty(3, dtype=torch.float64, device='cuda') if out is None else out
+    pa = (ctypes.c_void_p * n)(*[t.data_ptr() for t in avec])
+    pb = (ctypes.c_void_p * n)(*[t.data_ptr() for t in bvec])
+    check(_lib.load().plk_alm_dot_fused_dev(lmax, int(lmin), n, pa, pb, _ptr(num), _ptr(den), float(scale), _ptr(out), _stream()))
+    return out
+
+
+def alm_axpy2(y1, x1, y2, x2, a_dev):
+    """y1 += a x1 ; y2 -= a x2, a a 1-element device tensor"""
+    check(_lib.load().plk_alm_axpy2_dev(y1.numel(), _ptr(a_dev), _ptr(x1), _ptr(y1), _ptr(x2), _ptr(y2), _stream()))
 
 
 def alm_combine(terms, out=None):

@@ -229,11 +229,9 @@ extern "C" int emul_udgrade_sum(int nside_in, const double *in, int nside_out, d
   for (long long po = 0; po < npo; ++po) {
     int ix, iy, face;
     hpx_ring2xyf(nside_out, po, ix, iy, face);
-    double acc = 0.0;
-    for (int dy = 0; dy < f; ++dy)
-      for (int dx = 0; dx < f; ++dx) acc += in[hpx_xyf2ring(nside_in, ix * f + dx, iy * f + dy, face)];
-    out[po] = acc;
+    out[po] = hpx_children_sum(in, nside_in, nside_out, ix, iy, face);
   }
+  (void)f;
   return 0;
 }
 // ring -> (face, x, y) -> ring must be the identity

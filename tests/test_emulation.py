@@ -97,7 +97,7 @@ def test_seeds_with_scaled_rampup(emul, oracle_sht):
     assert rel_l2(X1[:, :lmax + 1], R1) < 1e-12 and rel_l2(X2[:, :lmax + 1], R2) < 1e-12
 
 
-@pytest.mark.parametrize("nside_in,nside_out", [(1, 1), (2, 1), (8, 2), (16, 16), (32, 4), (64, 8), (128, 64)])
+@pytest.mark.parametrize("nside_in,nside_out", [(1, 1), (2, 1), (8, 2), (16, 16), (32, 4), (64, 8), (128, 64), (64, 4), (128, 4), (256, 4)])
 def test_udgrade_index_arithmetic(emul, nside_in, nside_out):
     """HEALPix ring <-> (face, x, y) arithmetic of the device degrade kernel against the oracle's NEST-based
     ud_grade (sum of children) -- same host-device code, driven from a host loop"""
@@ -109,7 +109,8 @@ def test_udgrade_index_arithmetic(emul, nside_in, nside_out):
     out = np.zeros(12 * nside_out ** 2)
     emul.emul_udgrade_sum(nside_in, vp(m.ctypes.data), nside_out, vp(out.ctypes.data))
     ref = rg.ud_grade_sum(m, nside_out)
-    assert np.max(np.abs(out - ref)) < 1e-13 * np.max(np.abs(ref))
+    # bit-identical: the kernel adds the children in numpy's own order (NEST order, pairwise summation)
+    assert np.array_equal(out, ref)
     # which children belong to which parent is exact: an indicator map comes back as exact counts
     ones, unit = np.zeros(12 * nside_out ** 2), np.ones(12 * nside_in ** 2)
     emul.emul_udgrade_sum(nside_in, vp(unit.ctypes.data), nside_out, vp(ones.ctypes.data))

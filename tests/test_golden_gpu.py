@@ -160,6 +160,7 @@ def test_cg_graph_and_device_scalar_stages_equal_host_loop(gold, mods, pol, monk
     res = []
     for fixed, graph in (('0', '0'), ('1', '0'), ('1', '1')):
         monkeypatch.setenv('PLK_CG_FIXED', fixed)
+        monkeypatch.setenv('PLK_CG_DEVTOP', fixed)       # '0': the reference's host loop at the top level as well
         monkeypatch.setenv('PLK_CG_GRAPH', graph)
         if pol:
             nf = mods['opfilt_pp'].alm_filter_ninv(c['ninv_p1'], c['transf'])
