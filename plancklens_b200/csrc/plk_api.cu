@@ -416,7 +416,7 @@ static int ensure_work(plk_plan *p) {
   if ((rc = ensure(p->rec, nalm * 32 + 64))) return rc;
   size_t pb = 0;
   for (int sp = 0; sp < 2; ++sp) {
-    const int nr = pick_nr(p, sp ? env_int("PLK_NR_ANAS", 2) : env_int("PLK_NR_ANA0", 4));
+    const int nr = pick_nr(p, sp ? env_int("PLK_NR_ANAS", 4) : env_int("PLK_NR_ANA0", 4));
     const size_t ntile = (p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr);
     pb = std::max(pb, ntile * nalm * (sp ? 4 : 2) * sizeof(double));
   }
@@ -480,7 +480,7 @@ static int legendre_anal(plk_plan *p, int spin, const cplx *X1, const cplx *X2, 
   const DevSpin &d = p->spins[spin].d;
   const size_t nalm = (size_t)alm_size(p->lmax, p->mmax);
   const int nv = spin ? 4 : 2;
-  const int nr = pick_nr(p, spin ? env_int("PLK_NR_ANAS", 2) : env_int("PLK_NR_ANA0", 4));
+  const int nr = pick_nr(p, spin ? env_int("PLK_NR_ANAS", 4) : env_int("PLK_NR_ANA0", 4));
   const int ntile = (p->npair + kNCW * 32 * nr - 1) / (kNCW * 32 * nr);
   const long long stride = (long long)nalm * nv;
   if ((rc = ensure_work(p))) return rc;

@@ -529,7 +529,9 @@ PLK_D void butterfly16(double (&v)[16], int lane) {
 }
 
 template <bool SPIN, int NR>
-__global__ void __launch_bounds__(kLegThreads, (SPIN && NR == 2) ? PLK_ANA_MINB_S2 : PLK_ANA_MINB)
+// NR = 4: two resident blocks (255 registers, no spills) beat three with NR = 2 -- half the butterfly shuffles per FMA:
+// spin s 8.21 -> 7.67 ms, spin 0 2.86 -> 2.82 ms at nside = lmax = 2048 (variants a / NR 4, round 2)
+__global__ void __launch_bounds__(kLegThreads, NR == 4 ? 2 : ((SPIN && NR == 2) ? PLK_ANA_MINB_S2 : PLK_ANA_MINB))
 legendre_anal_kernel(DevGeom g, DevSpin t, const cplx *__restrict__ X1, const cplx *__restrict__ X2, int pitch,
                      double *__restrict__ part, long long part_stride /* doubles per tile */,
                      const int *__restrict__ morder, int dbg) {
