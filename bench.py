@@ -498,7 +498,10 @@ def run_dist(rank, world, dist, steps=3, warmup=2):
     out = {"nside": nside, "lmax_ivf": lmax, "lmax_qlm": lmax_qlm, "n_gpus": world, "ms_per_estimate": ms, "steps": steps}
     sync()
     if rank == 0:
-        # the single-GPU plan on the same inputs (other ranks idle): reference point and bit-identity check
+        # the single-GPU plan on the same inputs (other ranks idle): reference point and bit-identity check.  Same
+        # kernels on both sides: the m-partitioned ring stage multiplies the legs in separate kernels, so the single-GPU
+        # estimate is evaluated that way too (its default folds the products into the analysis ring kernel)
+        os.environ['PLK_QE_FUSED'] = '0'
         ref = qest.qe_device(nside, lmax, lmax_qlm)
         for _ in range(2):
             Gr, Cr = ref.p(tbar, ebar, bbar, twf, ewf, bwf)
@@ -508,6 +511,7 @@ def run_dist(rank, world, dist, steps=3, warmup=2):
         e1.record()
         torch.cuda.synchronize()
         ms1 = e0.elapsed_time(e1)
+        os.environ.pop('PLK_QE_FUSED', None)
         flop = F0(lmax, nside) + 4 * Fs(lmax, nside) + Fs(lmax_qlm, nside)
         out.update({"ms_single_gpu": ms1, "speedup": ms1 / ms, "efficiency": ms1 / ms / world,
                     "bit_identical_to_single_gpu": bool(torch.equal(G, Gr) and torch.equal(C, Cr)),

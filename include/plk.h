@@ -83,6 +83,22 @@ int plk_map2alm_add_dev(plk_plan *plan, int spin, const double *map1, const doub
                         const double *fl2, const void *add1, const double *afl1, const void *add2, const double *afl2,
                         void *alm1, void *alm2, void *stream);
 
+/* Analysis of maps that are never written to memory: pixel p of input component c is evaluated inside the ring kernel as
+ *   sum_{k < nterm} scale[k] * a[k][p] * (b[k] ? b[k][p] : 1)          (device pointers, 32-byte aligned, npix doubles)
+ * -- the per-pixel leg products of the quadratic estimators (qest.py:256-257: G t, C t; qest.py:276-278:
+ * (Q - iU)(G3 + iC3) - (Q + iU)(G1 - iC1)) and the N^-1 multiply of the one-map polarization filter
+ * (opfilt_pp.py:272-303) fused into the transform that consumes them.  add1 == NULL: no additive term. */
+#define PLK_MAX_PIX_TERMS 6
+typedef struct plk_pixprog {
+  int nterm;
+  const double *a[PLK_MAX_PIX_TERMS];
+  const double *b[PLK_MAX_PIX_TERMS];
+  double scale[PLK_MAX_PIX_TERMS];
+} plk_pixprog;
+int plk_map2alm_pix_dev(plk_plan *plan, int spin, const plk_pixprog *pix1, const plk_pixprog *pix2, const double *fl1,
+                        const double *fl2, const void *add1, const double *afl1, const void *add2, const double *afl2,
+                        void *alm1, void *alm2, void *stream);
+
 /* ---- transforms, host pointers (numpy arrays on the Python side) */
 int plk_alm2map_host(plk_plan *plan, int spin, const void *alm1, const void *alm2, double *map1, double *map2);
 int plk_map2alm_host(plk_plan *plan, int spin, const double *map1, const double *map2, void *alm1, void *alm2);

@@ -8,6 +8,14 @@ _LIB = None
 
 c_int, c_ll, c_dbl, vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_void_p
 
+PLK_MAX_PIX_TERMS = 6
+
+
+class PixProg(ctypes.Structure):
+    """plk_pixprog of include/plk.h"""
+    _fields_ = [('nterm', c_int), ('a', vp * PLK_MAX_PIX_TERMS), ('b', vp * PLK_MAX_PIX_TERMS), ('scale', c_dbl * PLK_MAX_PIX_TERMS)]
+
+
 _SIGS = {
     'plk_last_error': (ctypes.c_char_p, []),
     'plk_version': (c_int, []),
@@ -34,6 +42,7 @@ _SIGS = {
     'plk_alm_dot_fused_dev': (c_int, [c_int, c_int, c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, c_dbl, vp, vp]),
     'plk_alm_axpy2_dev': (c_int, [c_ll, vp, vp, vp, vp, vp, vp]),
     'plk_map2alm_add_dev': (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'plk_map2alm_pix_dev': (c_int, [vp, c_int, ctypes.POINTER(PixProg), ctypes.POINTER(PixProg), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'plk_alm2cl_dev': (c_int, [c_int, vp, vp, vp, vp]),
     'plk_scalar_ratio_dev': (c_int, [vp, vp, c_dbl, vp, vp]),
     'plk_alm_copy_dev': (c_int, [c_int, vp, c_int, vp, vp]),

@@ -280,6 +280,7 @@ extern "C" int plk_plan_create(plk_plan **out, int nside, int lmax, int mmax) {
   }
   f.mtop = nullptr;
   f.dist_n = 0; f.dist_mblk = 1;
+  f.pix.n = 0;
 
   // per-ring table for the template (monopole / dipole) kernels
   {
@@ -526,10 +527,11 @@ static int ring_synth(plk_plan *p, const cplx *X, double *map, cudaStream_t st, 
   return 0;
 }
 static int ring_anal(plk_plan *p, const double *map, cplx *X, cudaStream_t st, const int *mtop = nullptr,
-                     const plk_dist *dd = nullptr, int which = 0) {
+                     const plk_dist *dd = nullptr, int which = 0, const PixProg *pix = nullptr) {
   const double w = 4.0 * M_PI / (double)p->npix;
   DevFFT f = p->f;
   f.mtop = mtop;
+  if (pix) f.pix = *pix;
   if (dd) {
     f.dist_n = dd->nranks; f.dist_mblk = dd->mblk;
     for (int q = 0; q < dd->nranks; ++q) f.dist_x[q] = which ? dd->px2[q] : dd->px1[q];
@@ -585,19 +587,50 @@ extern "C" int plk_alm2map_dev(plk_plan *p, int spin, const void *alm1, const vo
   return PLK_OK;
 }
 
+static int to_pixprog(const plk_pixprog *in, long long npix, PixProg *out) {
+  if (in->nterm < 1 || in->nterm > kMaxPixTerms) return fail(PLK_EINVAL, "pixel program needs 1..%d terms, got %d", kMaxPixTerms, in->nterm);
+  out->n = in->nterm;
+  for (int k = 0; k < kMaxPixTerms; ++k) { out->a[k] = nullptr; out->b[k] = nullptr; out->s[k] = 0.0; }
+  for (int k = 0; k < in->nterm; ++k) {
+    if (!in->a[k]) return fail(PLK_EINVAL, "pixel program term %d has no map", k);
+    if (((uintptr_t)in->a[k] & 31) || ((uintptr_t)in->b[k] & 31)) return fail(PLK_EINVAL, "pixel program maps must be 32-byte aligned");
+    out->a[k] = in->a[k]; out->b[k] = in->b[k]; out->s[k] = in->scale[k];
+  }
+  (void)npix;
+  return 0;
+}
 static int map2alm_impl(plk_plan *p, int spin, const double *map1, const double *map2, const double *fl1,
-                        const double *fl2, void *alm1, void *alm2, void *stream, AlmAdd add) {
+                        const double *fl2, void *alm1, void *alm2, void *stream, AlmAdd add,
+                        const plk_pixprog *pix1 = nullptr, const plk_pixprog *pix2 = nullptr) {
   CHECK_PLAN(p);
   if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
-  if (!alm1 || !map1 || (spin > 0 && (!map2 || !alm2))) return fail(PLK_EINVAL, "NULL buffer");
+  if (!alm1 || (!map1 && !pix1) || (spin > 0 && ((!map2 && !pix2) || !alm2))) return fail(PLK_EINVAL, "NULL buffer");
+  PixProg q1, q2;
+  q1.n = q2.n = 0;
+  if (pix1) { int rc0 = to_pixprog(pix1, p->npix, &q1); if (rc0) return rc0; }
+  if (spin > 0 && pix2) { int rc0 = to_pixprog(pix2, p->npix, &q2); if (rc0) return rc0; }
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ensure_phase(p, spin ? 2 : 1);
   if (rc) return rc;
   if ((rc = ensure_spin(p, spin))) return rc;
   const int *mtop = p->spins[spin].d.mtop;
-  if ((rc = ring_anal(p, map1, (cplx *)p->X1.p, st, mtop))) return rc;
-  if (spin > 0 && (rc = ring_anal(p, map2, (cplx *)p->X2.p, st, mtop))) return rc;
+  if ((rc = ring_anal(p, map1, (cplx *)p->X1.p, st, mtop, nullptr, 0, pix1 ? &q1 : nullptr))) return rc;
+  if (spin > 0 && (rc = ring_anal(p, map2, (cplx *)p->X2.p, st, mtop, nullptr, 0, pix2 ? &q2 : nullptr))) return rc;
   return legendre_anal(p, spin, (const cplx *)p->X1.p, (const cplx *)p->X2.p, fl1, fl2, alm1, alm2, st, nullptr, add);
+}
+// Analysis of maps that are never materialised: component c of the input is the pixel program pix_c (see plk_pixprog);
+// optional additive term as in plk_map2alm_add_dev (add1 == NULL: none).
+extern "C" int plk_map2alm_pix_dev(plk_plan *p, int spin, const plk_pixprog *pix1, const plk_pixprog *pix2, const double *fl1,
+                                   const double *fl2, const void *add1, const double *afl1, const void *add2,
+                                   const double *afl2, void *alm1, void *alm2, void *stream) {
+  if (!pix1 || (spin > 0 && !pix2)) return fail(PLK_EINVAL, "NULL pixel program");
+  AlmAdd add;
+  if (add1) {
+    if (!afl1 || (spin > 0 && (!add2 || !afl2))) return fail(PLK_EINVAL, "NULL additive term");
+    if (add1 == alm1 || (spin > 0 && add2 == alm2)) return fail(PLK_EINVAL, "additive term aliases the output");
+    add.a1 = (const cplx *)add1; add.f1 = afl1; add.a2 = (const cplx *)add2; add.f2 = afl2;
+  }
+  return map2alm_impl(p, spin, nullptr, nullptr, fl1, fl2, alm1, alm2, stream, add, pix1, pix2);
 }
 extern "C" int plk_map2alm_dev(plk_plan *p, int spin, const double *map1, const double *map2, const double *fl1,
                                const double *fl2, void *alm1, void *alm2, void *stream) {

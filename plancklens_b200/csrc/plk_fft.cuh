@@ -26,6 +26,42 @@ namespace plk {
 constexpr int kTinyQ = 8;
 constexpr int kFftThreads = 256;
 
+// "Pixel program" of the analysis ring kernel: instead of reading one map, pixel p is evaluated on the fly as
+//   sum_{k < n} s_k a_k[p] (b_k ? b_k[p] : 1)
+// -- the per-pixel products of the quadratic estimators (qest.py:256-257, :276-278) and the N^-1 multiply of the CG
+// operators (opfilt_pp.py:272-303, one-map form) fused into the kernel that consumes them.  n == 0: plain map read.
+constexpr int kMaxPixTerms = 6;
+struct PixProg {
+  int n;
+  const double *a[kMaxPixTerms], *b[kMaxPixTerms];
+  double s[kMaxPixTerms];
+};
+PLK_HD double pix_eval(const PixProg &q, const double *map, long long p) {
+  if (q.n == 0) return map[p];
+  double v = 0.0;
+  for (int k = 0; k < q.n; ++k) {
+    v = fma(q.s[k] * q.a[k][p], q.b[k] ? q.b[k][p] : 1.0, v);
+  }
+  return v;
+}
+// four consecutive pixels starting at p (a multiple of 4: every ring starts on a 32-byte boundary)
+PLK_HD void pix_eval4(const PixProg &q, long long p, double (&v)[4]) {
+  v[0] = v[1] = v[2] = v[3] = 0.0;
+  for (int k = 0; k < q.n; ++k) {
+    double a[4], b[4] = {1.0, 1.0, 1.0, 1.0};
+#if defined(__CUDA_ARCH__)
+    const double4 av = *reinterpret_cast<const double4 *>(q.a[k] + p);
+    a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+    if (q.b[k]) { const double4 bv = *reinterpret_cast<const double4 *>(q.b[k] + p); b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w; }
+#else
+    for (int j = 0; j < 4; ++j) { a[j] = q.a[k][p + j]; if (q.b[k]) b[j] = q.b[k][p + j]; }
+#endif
+    const double sk = q.s[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fma(sk * a[j], b[j], v[j]);
+  }
+}
+
 struct DevFFT {
   int nside, npair, nring;
   int Wn;                   // twiddle table size (power of two >= every M)
@@ -42,6 +78,7 @@ struct DevFFT {
   int dist_n, dist_mblk;    // dist_n <= 1: single GPU
   cplx *dist_x[kMaxRanks];
   int nb4_maxm, nb1_minm;   // DFTs batched per pass: 4 (M <= nb4_maxm), 1 (M >= nb1_minm), else 2
+  PixProg pix;              // analysis only: how a pixel value is obtained (pix.n == 0: read from the map argument)
 };
 PLK_HD int auto_nbatch(const DevFFT &f, int M) { return M == 0 ? 0 : (M >= f.nb1_minm ? 1 : (M <= f.nb4_maxm ? 4 : 2)); }
 PLK_HD cplx *phase_out(const DevFFT &f, cplx *X, int m) {
@@ -405,9 +442,9 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
   if (M == 0) {
     for (int w = ctx.tid(); w < nhalf * (mmax + 1); w += ctx.nthr()) {
       const int half = w / (mmax + 1), m = w - half * (mmax + 1);
-      const double *in = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]);
+      const long long p0 = half == 0 ? f.start_n[ip] : f.start_s[ip];
       cplx acc = mk(0.0, 0.0);
-      for (int j = 0; j < n; ++j) acc = acc + in[j] * expipi32(-m * (shifted + 2 * j), n);
+      for (int j = 0; j < n; ++j) acc = acc + pix_eval(f.pix, map, p0 + j) * expipi32(-m * (shifted + 2 * j), n);
       phase_out(f, X, m)[(size_t)(half == 0 ? ip : f.nring - 1 - ip) * pitch + m] = wgt * acc;
     }
     return;
@@ -421,11 +458,11 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
     // the same thread owns the same X element in both passes
     for (int pass = 0; pass < 2 * nhalf; ++pass) {
       const int half = pass >> 1, a = pass & 1;
-      const double *in0 = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]) + 2 * a;
+      const long long p0 = (half == 0 ? f.start_n[ip] : f.start_s[ip]) + 2 * a;
       for (int i = ctx.tid(); i < M; i += ctx.nthr()) {
         cplx v = mk(0.0, 0.0);
         if (i < q) {
-          v = mk(in0[4 * i], -in0[4 * i + 1]);
+          v = mk(pix_eval(f.pix, map, p0 + 4 * i), -pix_eval(f.pix, map, p0 + 4 * i + 1));
           if (M != q) v = v * chirp(i, q);
         }
         buf[SW(i)] = v;
@@ -459,9 +496,17 @@ PLK_HD void ring_anal_body(Ctx ctx, const DevFFT &f, int ip, const double *map, 
       const int hh = w >> bits, i = w & (M - 1), half = h0 + hh;
       cplx v0 = mk(0.0, 0.0), v1 = mk(0.0, 0.0);
       if (i < q) {
-        const double *in = map + (half == 0 ? f.start_n[ip] : f.start_s[ip]) + 4 * i;
-        v0 = mk(in[0], -in[1]);      // conj(y^{(0)}_t), y^{(a)}_t = x_{4t+2a} + i x_{4t+2a+1}
-        v1 = mk(in[2], -in[3]);
+        const long long p0 = (half == 0 ? f.start_n[ip] : f.start_s[ip]) + 4 * i;
+        if (f.pix.n == 0) {
+          const double *in = map + p0;
+          v0 = mk(in[0], -in[1]);      // conj(y^{(0)}_t), y^{(a)}_t = x_{4t+2a} + i x_{4t+2a+1}
+          v1 = mk(in[2], -in[3]);
+        } else {
+          double pv[4];
+          pix_eval4(f.pix, p0, pv);
+          v0 = mk(pv[0], -pv[1]);
+          v1 = mk(pv[2], -pv[3]);
+        }
         if (M != q) { const cplx c = chirp(i, q); v0 = v0 * c; v1 = v1 * c; }
       }
       buf[((size_t)(2 * hh) << bits) + SW(i)] = v0;

@@ -133,23 +133,35 @@ class library_sepTP(object):
         return getattr(self.sim_lib, 'get_sim_%smap' % which)(idx)          # numpy (or tensors with device_maps)
 
     def _write_async(self, fn, tensor):
-        """tensor -> pinned host copy (this stream) -> hp.write_alm on a worker thread, write-then-rename"""
+        """tensor -> pinned host copy on a side stream -> hp.write_alm on a worker thread (write-then-rename).
+        Pinned buffers are pooled (cudaHostAlloc of tens of MB costs milliseconds) and the copy waits on an event of the
+        compute stream, so neither the allocation nor the D2H transfer sits on the GPU's critical path."""
         import concurrent.futures as cf
         import torch
         if not hasattr(self, '_io_pool'):
             self._io_pool = cf.ThreadPoolExecutor(max_workers=2)
             self._io_pending = []
-        host = torch.empty(tensor.numel(), dtype=torch.complex128, pin_memory=True)
-        host.copy_(tensor, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+            self._io_stream = torch.cuda.Stream()
+            self._io_free = {}
+        n = tensor.numel()
+        free = self._io_free.setdefault(n, [])
+        host = free.pop() if free else torch.empty(n, dtype=torch.complex128, pin_memory=True)
+        ready = torch.cuda.Event()
+        ready.record()                                        # the tensor is complete on the compute stream
+        with torch.cuda.stream(self._io_stream):
+            self._io_stream.wait_event(ready)
+            host.copy_(tensor, non_blocking=True)
+            tensor.record_stream(self._io_stream)             # keep the device memory alive until the copy has run
+            done = torch.cuda.Event()
+            done.record()
 
         def job():
-            ev.synchronize()
+            done.synchronize()
             root, ext = os.path.splitext(fn)
             tmp = '%s.tmp%d%s' % (root, os.getpid(), ext)        # keeps the extension hp.write_alm dispatches on
             hp.write_alm(tmp, host.numpy(), overwrite=True)
             os.replace(tmp, fn)
+            free.append(host)
         self._io_pending = [f for f in self._io_pending if not f.done()]
         self._io_pending.append(self._io_pool.submit(job))
 

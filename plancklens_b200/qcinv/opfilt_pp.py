@@ -9,6 +9,7 @@ One `fwd_op`: spin-2 synthesis with the E/B transfer functions fused, the N^{-1}
 combination kernel per component for S^{-1} x + N x.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -136,11 +137,17 @@ class fwd_op:
             lmax = alm.lmax
             plan = sht.get_plan(nf.nside, lmax)
             qmap, umap = plan.alm2map_spin(alm.elm.t, alm.blm.t, 2, flg=nf._fl('ein', lmax), flc=nf._fl('bin', lmax))
-            nf.apply_map([qmap, umap])
             if lmax not in self._sl_d:
                 self._sl_d[lmax] = (sht.dev_fl(sl[:, 0, 0], lmax), sht.dev_fl(sl[:, 1, 1], lmax))
             se, sb = self._sl_d[lmax]
-            e, b = plan.map2alm_spin_add(qmap, umap, 2, nf._fl('eout', lmax), nf._fl('bout', lmax), alm.elm.t, se, alm.blm.t, sb)
+            if len(nf.n_inv) == 1 and not nf.wmarg and os.environ.get('PLK_CG_PIXFUSED', '1') != '0':
+                # one N^-1 map, no templates (opfilt_pp.py:292): the multiply happens inside the analysis ring kernel
+                ninv = nf._ninv_d[0]
+                e, b = plan.map2alm_spin_pix([(1.0, qmap, ninv)], [(1.0, umap, ninv)], 2, flg=nf._fl('eout', lmax),
+                                             flc=nf._fl('bout', lmax), addg=alm.elm.t, aflg=se, addc=alm.blm.t, aflc=sb)
+            else:
+                nf.apply_map([qmap, umap])
+                e, b = plan.map2alm_spin_add(qmap, umap, 2, nf._fl('eout', lmax), nf._fl('bout', lmax), alm.elm.t, se, alm.blm.t, sb)
             return eblm([dalm(e, lmax), dalm(b, lmax)])
         nlm = alm * 1.0
         self.n_inv_filt.apply_alm(nlm)

@@ -143,13 +143,46 @@ class qe_device:
         torch.cuda.current_stream().synchronize()
         return self._pin[0].numpy().copy(), self._pin[1].numpy().copy()
 
+    # ---- leg products evaluated INSIDE the analysis ring kernel (plk_map2alm_pix_dev): the product maps of
+    #      qest.py:256-257 and :276-278 are never written; single-GPU plans only (the m-partitioned ring stage keeps the
+    #      separate product kernels)
+    def _fused(self):
+        return hasattr(self.plan_qlm, 'map2alm_spin_pix') and os.environ.get('PLK_QE_FUSED', '1') != '0'
+
+    def _t_legs(self, tbar, twf):
+        b = self._buf
+        t = self.plan_ivf.alm2map(tbar, out=b[0])
+        G, C = self.plan_ivf.alm2map_spin(twf, None, 1, flg=self.fl_t1, out=(b[1], b[2]))
+        return [(1.0, G, t)], [(1.0, C, t)]
+
+    def _p_legs(self, ebar, bbar, ewf, bwf):
+        b = self._buf
+        Q, U = self.plan_ivf.alm2map_spin(ebar, bbar, 2, flg=self.fl_half, flc=self.fl_half, out=(b[3], b[8]))
+        G3, C3 = self.plan_ivf.alm2map_spin(ewf, bwf, 3, flg=self.fl_p3, flc=self.fl_p3, out=(b[4], b[5]))
+        G1, C1 = self.plan_ivf.alm2map_spin(ewf, bwf, 1, flg=self.fl_p1, flc=self.fl_p1, out=(b[6], b[7]))
+        # (Q - iU)(G3 + iC3) - (Q + iU)(G1 - iC1)
+        re = [(1.0, Q, G3), (1.0, U, C3), (-1.0, Q, G1), (-1.0, U, C1)]
+        im = [(1.0, Q, C3), (-1.0, U, G3), (-1.0, U, G1), (1.0, Q, C1)]
+        return re, im
+
+    def _analyse_fused(self, re, im):
+        return self.plan_qlm.map2alm_spin_pix(re, im, 1, flg=self.fl_out, flc=self.fl_out)
+
     def ptt(self, tbar, twf):
+        if self._fused():
+            return self._analyse_fused(*self._t_legs(tbar, twf))
         return self.analyse(*self.t_products(tbar, twf))
 
     def p_p(self, ebar, bbar, ewf, bwf):
+        if self._fused():
+            return self._analyse_fused(*self._p_legs(ebar, bbar, ewf, bwf))
         return self.analyse(*self.p_products(ebar, bbar, ewf, bwf))
 
     def p(self, tbar, ebar, bbar, twf, ewf, bwf, merge_analysis=True):
+        if merge_analysis and self._fused():
+            rp, ip = self._p_legs(ebar, bbar, ewf, bwf)
+            rt, it = self._t_legs(tbar, twf)
+            return self._analyse_fused(rp + rt, ip + it)        # 5 product terms per component, one spin-1 analysis
         b = self._buf
         re, im = self.p_products(ebar, bbar, ewf, bwf)             # in b[8], b[9]
         if merge_analysis:

@@ -139,6 +139,37 @@ class Plan:
                                            _ptr(addc), _ptr(aflc), _ptr(out[0]), _ptr(out[1]), _stream()))
         return out
 
+    @staticmethod
+    def _pixprog(terms):
+        """[(scale, a, b or None), ...] -> plk_pixprog: pixel value = sum scale * a[p] * b[p]"""
+        assert 1 <= len(terms) <= _lib.PLK_MAX_PIX_TERMS, len(terms)
+        q = _lib.PixProg()
+        q.nterm = len(terms)
+        for k, (s, a, b) in enumerate(terms):
+            q.a[k] = a.data_ptr()
+            q.b[k] = b.data_ptr() if b is not None else None
+            q.scale[k] = float(s)
+        return q
+
+    def map2alm_pix(self, terms, fl=None, add=None, afl=None, out=None):
+        """spin-0 analysis of the map sum_k scale_k a_k b_k, evaluated inside the ring kernel (never materialised)"""
+        out = torch.empty(self.nalm, dtype=torch.complex128, device='cuda') if out is None else out
+        q = self._pixprog(terms)
+        check(self.lib.plk_map2alm_pix_dev(self._h, 0, ctypes.byref(q), None, _ptr(fl), None, _ptr(add), _ptr(afl), None, None,
+                                           _ptr(out), None, _stream()))
+        return out
+
+    def map2alm_spin_pix(self, terms1, terms2, spin, flg=None, flc=None, addg=None, aflg=None, addc=None, aflc=None, out=None):
+        """spin-s analysis of two maps given as pixel programs (QE leg products, N^-1 multiplies), optional additive term"""
+        assert spin in (1, 2, 3), spin
+        if out is None:
+            out = (torch.empty(self.nalm, dtype=torch.complex128, device='cuda'),
+                   torch.empty(self.nalm, dtype=torch.complex128, device='cuda'))
+        q1, q2 = self._pixprog(terms1), self._pixprog(terms2)
+        check(self.lib.plk_map2alm_pix_dev(self._h, spin, ctypes.byref(q1), ctypes.byref(q2), _ptr(flg), _ptr(flc), _ptr(addg),
+                                           _ptr(aflg), _ptr(addc), _ptr(aflc), _ptr(out[0]), _ptr(out[1]), _stream()))
+        return out
+
     def map2alm_spin(self, m1, m2, spin, flg=None, flc=None, out=None):
         assert spin in (1, 2, 3), spin
         assert m1.numel() == self.npix and m2.numel() == self.npix

@@ -49,7 +49,7 @@ void build_fft(const HostGeom &hg, HostFFT &h) {
   DevFFT &f = h.f;
   f.nside = hg.nside; f.npair = np; f.nring = hg.nring; f.Wn = Mmax; f.W = h.W.data(); f.V = h.V.data();
   f.voff = h.voff.data(); f.M = h.M.data(); f.nphi = h.nphi.data(); f.shifted = h.shifted.data();
-  f.start_n = h.sn.data(); f.start_s = h.ss.data(); f.order = h.order.data(); f.mtop = nullptr; f.dist_n = 0; f.nb4_maxm = 1024; f.nb1_minm = 8192;
+  f.start_n = h.sn.data(); f.start_s = h.ss.data(); f.order = h.order.data(); f.mtop = nullptr; f.dist_n = 0; f.nb4_maxm = 1024; f.nb1_minm = 8192; f.pix.n = 0;
   std::vector<cplx> buf(Mmax + Mmax / 4);
   for (int ip = 0; ip < np; ++ip) bluestein_setup_body(BlockCtx(), f, ip, h.V.data(), buf.data());
 }

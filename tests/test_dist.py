@@ -66,8 +66,10 @@ def test_simulated_ranks_equal_single_gpu(nside, lmax, nranks):
 
 
 @pytest.mark.gpu
-def test_simulated_ranks_qe_p():
-    """The 'p' estimator through qe_device with every transform m-split over 4 simulated ranks."""
+def test_simulated_ranks_qe_p(monkeypatch):
+    """The 'p' estimator through qe_device with every transform m-split over 4 simulated ranks: bit-identical to the
+    single-GPU estimate evaluated with the same kernels (separate leg-product kernels, PLK_QE_FUSED=0), and equal to
+    round-off to the single-GPU default, which evaluates the leg products inside the analysis ring kernel."""
     import torch
     import golden_inputs as gi
     from plancklens_b200 import dist_sht, hp, qest, sht
@@ -78,11 +80,15 @@ def test_simulated_ranks_qe_p():
     ewf = hp.almxfl(q['elm1'], cls['ee']) + hp.almxfl(q['tlm1'], cls['te'])
     bwf = hp.almxfl(q['blm1'], cls['bb'])
     args = [d(x) for x in (q['tlm1'], q['elm1'], q['blm1'], twf, ewf, bwf)]
+    fused = qest.qe_device(q['nside'], q['lmax'], q['lmax_qlm']).p(*args)
+    monkeypatch.setenv('PLK_QE_FUSED', '0')
     ref = qest.qe_device(q['nside'], q['lmax'], q['lmax_qlm']).p(*args)
     got = qest.qe_device(q['nside'], q['lmax'], q['lmax_qlm'],
                          plan_ivf=dist_sht.SimGroup(q['nside'], q['lmax'], 4),
                          plan_qlm=dist_sht.SimGroup(q['nside'], q['lmax_qlm'], 4)).p(*args)
     assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    for a, b in zip(fused, ref):
+        assert float(torch.linalg.norm(a - b) / torch.linalg.norm(b)) < 1e-13
 
 
 @pytest.mark.gpu

@@ -90,3 +90,50 @@ def test_modes_dot_one_kernel(nside):
     for _ in range(3):     # repeated launches: ticket counter reset
         got = plan.modes_dot(dm.clone(), w=sht.dev_map(w)).cpu().numpy()
         assert np.max(np.abs(got - modes @ (m * w))) < 1e-12 * npix ** 0.5
+
+
+@pytest.mark.parametrize("nside,lmax", [(8, 16), (64, 100), (256, 300)])
+def test_analysis_of_pixel_programs(nside, lmax):
+    """plk_map2alm_pix_dev: the ring kernel evaluates sum_k s_k a_k b_k per pixel instead of reading a product map
+    (QE leg products, N^-1 multiply) -- same alm as analysing the materialised product"""
+    import torch
+    from plancklens_b200 import sht
+    rng = np.random.default_rng(nside)
+    plan = sht.get_plan(nside, lmax)
+    npix = 12 * nside ** 2
+    m = [sht.dev_map(rng.standard_normal(npix)) for _ in range(9)]
+    fl = sht.dev_fl(rng.uniform(0.5, 1.5, lmax + 1), lmax)
+    re = [(1.0, m[0], m[1]), (1.0, m[2], m[3]), (-1.0, m[0], m[4]), (-1.0, m[2], m[5]), (1.0, m[6], m[7])]
+    im = [(1.0, m[0], m[3]), (-1.0, m[2], m[1]), (-1.0, m[2], m[4]), (1.0, m[0], m[5]), (0.5, m[6], None)]
+    mre = m[0] * m[1] + m[2] * m[3] - m[0] * m[4] - m[2] * m[5] + m[6] * m[7]
+    mim = m[0] * m[3] - m[2] * m[1] - m[2] * m[4] + m[0] * m[5] + 0.5 * m[6]
+    for spin in (1, 2):
+        g, c = plan.map2alm_spin_pix(re, im, spin, flg=fl, flc=fl)
+        wg, wc = plan.map2alm_spin(mre, mim, spin, flg=fl, flc=fl)
+        assert rel_l2(g.cpu().numpy(), wg.cpu().numpy()) < 1e-13 and rel_l2(c.cpu().numpy(), wc.cpu().numpy()) < 1e-13
+    a = plan.map2alm_pix(re, fl=fl)
+    assert rel_l2(a.cpu().numpy(), plan.map2alm(mre, fl=fl).cpu().numpy()) < 1e-13
+    x1, x2 = sht.dev_alm(rand_alm(rng, lmax)), sht.dev_alm(rand_alm(rng, lmax))
+    g, c = plan.map2alm_spin_pix(re[:1], im[:1], 2, flg=fl, flc=fl, addg=x1, aflg=fl, addc=x2, aflc=fl)
+    wg, wc = plan.map2alm_spin_add(m[0] * m[1], m[0] * m[3], 2, fl, fl, x1, fl, x2, fl)
+    assert rel_l2(g.cpu().numpy(), wg.cpu().numpy()) < 1e-13 and rel_l2(c.cpu().numpy(), wc.cpu().numpy()) < 1e-13
+
+
+def test_qe_fused_products_equal_separate_kernels(monkeypatch):
+    import golden_inputs as gi
+    from plancklens_b200 import hp, qest, sht
+    q = gi.qe_case()
+    d = sht.dev_alm
+    cls = q['cls']
+    twf = hp.almxfl(q['tlm1'], cls['tt']) + hp.almxfl(q['elm1'], cls['te'])
+    ewf = hp.almxfl(q['elm1'], cls['ee']) + hp.almxfl(q['tlm1'], cls['te'])
+    bwf = hp.almxfl(q['blm1'], cls['bb'])
+    args = [d(x) for x in (q['tlm1'], q['elm1'], q['blm1'], twf, ewf, bwf)]
+    out = {}
+    for fused in ('1', '0'):
+        monkeypatch.setenv('PLK_QE_FUSED', fused)
+        qe = qest.qe_device(q['nside'], q['lmax'], q['lmax_qlm'])
+        out[fused] = [qe.p(*args), qe.ptt(args[0], args[3]), qe.p_p(args[1], args[2], args[4], args[5])]
+    for a, b in zip(out['1'], out['0']):
+        for x, y in zip(a, b):
+            assert rel_l2(x.cpu().numpy(), y.cpu().numpy()) < 1e-13
