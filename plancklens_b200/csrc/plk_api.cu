@@ -656,17 +656,21 @@ extern "C" int plk_dist_partition(int nside, int mmax, int nranks, int mblk, int
     return fail(PLK_EINVAL, "bad argument (nside %d, nranks %d, mblk %d)", nside, nranks, mblk);
   const int npair = 2 * nside;
   if (pair_lo) {
-    // cost of ring pair ip in the ring-FFT / pixel stage: pixels (both rings except the equator, the last pair)
-    // times the measured relative cost per pixel of its FFT path (B200, nside 4096: power-of-two rings 1, Bluestein
-    // 2.6, single-buffer Bluestein with M = 8192 4.2)
+    // Cost of ring pair ip in the ring-FFT / pixel stage, in microseconds of one SM-parallel component pass, fitted to
+    // the per-rank stage times of the nside-4096 / lmax-4000 'p' estimate on 8 B200 (profiles/r02_dist.md):
+    //   power-of-two rings (q = 2^j, incl. the whole equatorial belt): 0.42 us at q = 4096, scaled with q log2 q
+    //   Bluestein rings: 5.2e-6 * 2 M log2 M + 1.9e-5 q with M = nextpow2(2 q - 1) -- two M-point FFTs whatever q is,
+    //   so the cost per PIXEL falls with q inside a size class (the round-1 model, pixels x a per-class factor, gave the
+    //   polar ranks 7.1 ms of ring synthesis against 4.3 ms for the ranks holding the long Bluestein rings)
     std::vector<double> cum(npair + 1, 0.0);
-    const int nb1 = env_int("PLK_FFT_NB1_MINM", 8192);
     for (int ip = 0; ip < npair; ++ip) {
       const int q = ip < nside ? ip + 1 : nside;
-      const double n = 4.0 * q * (ip == npair - 1 ? 1 : 2);
-      double w = 1.0;
-      if (q > kTinyQ && (q & (q - 1)) != 0) w = nextpow2(2 * q - 1) >= nb1 ? 4.2 : 2.6;
-      cum[ip + 1] = cum[ip] + n * w;
+      double c;
+      if (q <= kTinyQ) c = 0.02 + 1.0e-5 * (mmax + 1);                       // direct sums over all m
+      else if ((q & (q - 1)) == 0) c = 0.42 * (double)q * ilog2(q) / (4096.0 * 12.0);
+      else { const int M = nextpow2(2 * q - 1); c = 5.2e-6 * 2.0 * M * ilog2(M) + 1.9e-5 * q; }
+      if (ip == npair - 1) c *= 0.5;                                          // the equator has no southern twin
+      cum[ip + 1] = cum[ip] + c;
     }
     pair_lo[0] = 0;
     for (int q = 1; q < nranks; ++q) {
