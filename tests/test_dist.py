@@ -18,17 +18,23 @@ def test_partition_is_a_balanced_cover(nside, mmax, nranks):
     pair_lo, owner = dist_sht.partition(nside, mmax, nranks)
     assert pair_lo[0] == 0 and pair_lo[-1] == 2 * nside and np.all(np.diff(pair_lo) >= 0)
     assert owner.min() >= 0 and owner.max() < nranks and owner.size == mmax + 1
-    # ring pairs are dealt by ring-FFT cost (pixels x relative cost of the FFT path: Bluestein cap rings are 2.6 - 4.2 x
-    # dearer per pixel than the power-of-two equatorial rings), so ranks holding the caps get fewer pixels
+    # ring pairs are dealt by ring-FFT cost -- the fitted per-ring model of plk_dist_partition: power-of-two rings
+    # ~ q log2 q, Bluestein cap rings two M-point FFTs whatever their length -- so every rank gets the same modelled time
     npix_pair = np.array([(8 if ip < 2 * nside - 1 else 4) * (ip + 1 if ip < nside else nside) for ip in range(2 * nside)])
     assert npix_pair.sum() == 12 * nside ** 2
     q = np.array([ip + 1 if ip < nside else nside for ip in range(2 * nside)])
     pow2 = (q & (q - 1)) == 0
     M = 2 ** np.ceil(np.log2(np.maximum(2 * q - 1, 1)))
-    w = np.where(pow2 | (q <= 8), 1.0, np.where(M >= 8192, 4.2, 2.6))
-    cost = np.array([(npix_pair * w)[pair_lo[r]:pair_lo[r + 1]].sum() for r in range(nranks)])
+    lg = lambda v: np.ceil(np.log2(np.maximum(v, 1)))
+    c = np.where(q <= 8, 0.02 + 1e-5 * (mmax + 1),
+                 np.where(pow2, 0.37 * q * lg(q) / (4096. * 12.), 5.2e-6 * 2. * M * lg(M) + 1.9e-5 * q))
+    c[-1] *= 0.5
+    cost = np.array([c[pair_lo[r]:pair_lo[r + 1]].sum() for r in range(nranks)])
     if nside >= 2048:
         assert np.max(np.abs(cost / cost.mean() - 1)) < 0.02
+        # ranks holding the polar caps get fewer pixels than the ranks of the equatorial belt
+        pix = np.array([npix_pair[pair_lo[r]:pair_lo[r + 1]].sum() for r in range(nranks)])
+        assert pix[0] < pix[-1]
     # Legendre work per rank ~ sum over owned m of (mmax - m + 1): within 5 % at production sizes
     work = np.array([np.sum(mmax - np.where(owner == q)[0] + 1) for q in range(nranks)], dtype=float)
     if mmax >= 2048:
