@@ -229,6 +229,11 @@ int plk_dist_ring_synth(plk_dist *dist, int spin, double *map1, double *map2, vo
 int plk_dist_ring_anal(plk_dist *dist, int spin, const double *map1, const double *map2, void *stream);
 int plk_dist_legendre_anal(plk_dist *dist, int spin, const double *fl1, const double *fl2, void *alm1, void *alm2,
                            void *stream);
+/* with the additive term of plk_map2alm_add_dev on this rank's m rows (m-distributed CG forward operator: SURVEY.md
+ * section 8e.2 "CG dots become a scalar all-reduce; alm stay m-distributed between calls") */
+int plk_dist_legendre_anal_add(plk_dist *dist, int spin, const double *fl1, const double *fl2, const void *add1,
+                               const double *afl1, const void *add2, const double *afl2, void *alm1, void *alm2,
+                               void *stream);
 
 /* ---- Wigner small-d transforms on a set of nodes x_i = cos(theta_i): what
  *      plancklens/wigners/wigners.f90:566-684 provides to utils_spin.wignerc (utils_spin.py:52-93), and through it to

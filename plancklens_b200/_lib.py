@@ -65,6 +65,7 @@ _SIGS = {
     'plk_dist_ring_synth': (c_int, [vp, c_int, vp, vp, vp]),
     'plk_dist_ring_anal': (c_int, [vp, c_int, vp, vp, vp]),
     'plk_dist_legendre_anal': (c_int, [vp, c_int, vp, vp, vp, vp, vp]),
+    'plk_dist_legendre_anal_add': (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'plk_wignerpos_dev': (c_int, [vp, c_int, vp, c_int, c_int, c_int, vp, vp]),
     'plk_wignercoeff_dev': (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp]),
     'plk_profile_enable': (c_int, [c_int]),

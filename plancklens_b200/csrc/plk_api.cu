@@ -859,6 +859,22 @@ extern "C" int plk_dist_legendre_anal(plk_dist *d, int spin, const double *fl1, 
   return legendre_anal(d->plan, spin, d->X1, d->X2, fl1, fl2, alm1, alm2, (cudaStream_t)stream, d);
 }
 
+// Same with the additive per-l term of plk_map2alm_add_dev applied to this rank's m rows only: the S^-1 x term of an
+// m-distributed CG forward operator (rows of other ranks stay zero)
+extern "C" int plk_dist_legendre_anal_add(plk_dist *d, int spin, const double *fl1, const double *fl2, const void *add1,
+                                          const double *afl1, const void *add2, const double *afl2, void *alm1, void *alm2,
+                                          void *stream) {
+  int rc = dist_ready(d);
+  if (rc) return rc;
+  if (spin < 0 || spin > 3) return fail(PLK_EINVAL, "spin must be 0..3, got %d", spin);
+  if (!alm1 || (spin > 0 && !alm2)) return fail(PLK_EINVAL, "NULL buffer");
+  if (!add1 || !afl1 || (spin > 0 && (!add2 || !afl2))) return fail(PLK_EINVAL, "NULL additive term");
+  if (add1 == alm1 || (spin > 0 && add2 == alm2)) return fail(PLK_EINVAL, "additive term aliases the output");
+  AlmAdd add;
+  add.a1 = (const cplx *)add1; add.f1 = afl1; add.a2 = (const cplx *)add2; add.f2 = afl2;
+  return legendre_anal(d->plan, spin, d->X1, d->X2, fl1, fl2, alm1, alm2, (cudaStream_t)stream, d, add);
+}
+
 // ------------------------------------------------------------------------------------------ host-pointer variants
 extern "C" int plk_alm2map_host(plk_plan *p, int spin, const void *alm1, const void *alm2, double *map1, double *map2) {
   CHECK_PLAN(p);

@@ -87,8 +87,15 @@ class _DistHandle:
     def ring_anal(self, spin, m1, m2):
         check(self.lib.plk_dist_ring_anal(self._h, spin, _ptr(m1), _ptr(m2), _stream()))
 
-    def legendre_anal(self, spin, fl1, fl2, a1, a2):
-        check(self.lib.plk_dist_legendre_anal(self._h, spin, _ptr(fl1), _ptr(fl2), _ptr(a1), _ptr(a2), _stream()))
+    def legendre_anal(self, spin, fl1, fl2, a1, a2, add=None):
+        """add = (x1, afl1[, x2, afl2]): out rows of this rank += afl[l] * x (m-distributed CG forward operator)"""
+        if add is None:
+            check(self.lib.plk_dist_legendre_anal(self._h, spin, _ptr(fl1), _ptr(fl2), _ptr(a1), _ptr(a2), _stream()))
+        else:
+            x1, f1 = add[0], add[1]
+            x2, f2 = (add[2], add[3]) if spin else (None, None)
+            check(self.lib.plk_dist_legendre_anal_add(self._h, spin, _ptr(fl1), _ptr(fl2), _ptr(x1), _ptr(f1), _ptr(x2), _ptr(f2),
+                                                      _ptr(a1), _ptr(a2), _stream()))
 
 
 class DistPlan:
@@ -173,7 +180,7 @@ class DistPlan:
         for a in alms:
             self.dist.all_reduce(torch.view_as_real(a), group=self.group)
 
-    def map2alm(self, m, fl=None, out=None, reduce=True):
+    def map2alm(self, m, fl=None, out=None, reduce=True, add=None):
         out = torch.empty(self.nalm, dtype=torch.complex128, device='cuda') if out is None else out
         self._mark('start')
         self.barrier()
@@ -182,14 +189,14 @@ class DistPlan:
         self._mark('ring_anal')
         self.barrier()
         self._mark('barrier1')
-        self.h.legendre_anal(0, fl, None, out, None)
+        self.h.legendre_anal(0, fl, None, out, None, add=add)
         self._mark('legendre_anal')
         if reduce:
             self._reduce(out)
             self._mark('allreduce_alm')
         return out
 
-    def map2alm_spin(self, m1, m2, spin, flg=None, flc=None, out=None, reduce=True):
+    def map2alm_spin(self, m1, m2, spin, flg=None, flc=None, out=None, reduce=True, add=None):
         if out is None:
             out = (torch.empty(self.nalm, dtype=torch.complex128, device='cuda'),
                    torch.empty(self.nalm, dtype=torch.complex128, device='cuda'))
@@ -200,7 +207,7 @@ class DistPlan:
         self._mark('ring_anal')
         self.barrier()
         self._mark('barrier1')
-        self.h.legendre_anal(spin, flg, flc, out[0], out[1])
+        self.h.legendre_anal(spin, flg, flc, out[0], out[1], add=add)
         self._mark('legendre_anal')
         if reduce:
             self._reduce(out[0], out[1])
