@@ -20,7 +20,9 @@ starting from its cached inverse-variance filtered alms (what `run_qlms.py -k p 
              lmax 2048 and lmax 3000, simulations drawn, filtered and estimated on the GPU, sharded idx % N over ranks:
              simulations/s, CG iterations and iterations/s, per-stage ms, algorithmic TFLOP/s and roofline fraction
   extra.dist   : (N > 1) BASELINE.json configs[4]: ONE 'p' estimate at nside 4096 / lmax_ivf 4000 / lmax_qlm 5000 with every
-             transform m-partitioned over the N GPUs, checked bit-for-bit against the single-GPU plan on rank 0
+             transform m-partitioned over the N GPUs, checked bit-for-bit against the single-GPU plan on rank 0;
+             extra.target.lmax2048.dist_cg: the masked T and P filters of one simulation with the forward operator
+             m-partitioned (dots as scalar all-reduces), against the single-GPU solve of the same maps
   cpu_baseline : the CPU oracle port of the headline step on a bounded sample, host cores stated
 `--impl reference` runs the CPU port alone: the FULL step (every m), for as many of the requested steps as fit a time
 budget, and prints the ms_per_step it measured (the reference itself needs healpy, which is absent here).
@@ -373,7 +375,47 @@ def cg_flops(lmax, it_t, it_p, algorithmic=True):
     return ft, fp
 
 
-def run_target(lmax, nsims, tmp, mask, z, rank, world, dist, peak_nominal):
+def run_dist_cg(lib, lmax, rank, world, dist):
+    """The masked-sky T and P filters of one simulation with the forward operator m-partitioned over the ranks
+    (qcinv/dist_cg.py), next to the single-GPU solve of the same maps: iterations, ms, speed-up."""
+    import torch
+    from plancklens_b200.qcinv import dist_cg, util_alm
+    idx = 7777                                   # the same simulation on every rank (counter-based draws)
+    tmap = lib['sims'].get_sim_tmap_dev(idx)
+    qmap, umap = lib['sims'].get_sim_pmap_dev(idx)
+    out = {}
+    for name, cinv, maps, zero in (
+            ('T', lib['cinv_t'], tmap, lambda: util_alm.dalm.zeros(lmax)),
+            ('P', lib['cinv_p'], [qmap, umap], lambda: util_alm.eblm([util_alm.dalm.zeros(lmax), util_alm.dalm.zeros(lmax)]))):
+        chain = cinv.chain
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ref = zero()
+        torch.cuda.synchronize()
+        e[0].record()
+        chain.solve(ref, maps)
+        e[1].record()
+        n1 = chain.niter
+        dc = dist_cg.dist_chain(chain)
+        dc.solve(zero(), maps)                   # warm-up of the m-partitioned plan
+        dist.barrier()
+        got = zero()
+        e[2].record()
+        n = dc.solve(got, maps)
+        e[3].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        err = max(float(torch.linalg.norm(a.t - b.t) / torch.linalg.norm(b.t)) for a, b in zip(dist_cg._comps(got), dist_cg._comps(ref)))
+        out[name] = {"iterations_single_gpu": int(n1), "iterations_m_partitioned": int(n), "ms_single_gpu": float(t[0].item()),
+                     "ms_m_partitioned": float(t[1].item()), "speedup": float(t[0].item() / t[1].item()),
+                     "iter_per_s_m_partitioned": n / (float(t[1].item()) * 1e-3), "rel_l2_vs_single_gpu": err}
+        del dc
+    out["note"] = "forward operator split by m over the ranks, dots as scalar all-reduces, multigrid preconditioner replicated " \
+                  "on every rank (Amdahl: only the two full-resolution transforms of an iteration are split)"
+    return out
+
+
+def run_target(lmax, nsims, tmp, mask, z, rank, world, dist, peak_nominal, with_dist_cg=False):
     import torch
     from plancklens_b200 import sht
     t0 = time.perf_counter()
@@ -469,6 +511,13 @@ def run_target(lmax, nsims, tmp, mask, z, rank, world, dist, peak_nominal):
                        "(reference default chains) -> library_cinv_sepTP -> library_ftl (lmin %d) -> qest.library_sepTP 'p'; "
                        "filtered alms cached to disk asynchronously (PLK_CACHE_FORMAT=%s); mean-field sum reduced over "
                        "ranks inside the timed region" % (LMIN_IVF, os.environ.get('PLK_CACHE_FORMAT', 'fits'))}
+    if with_dist_cg and world > 1:
+        try:
+            res["dist_cg"] = run_dist_cg(lib, lmax, rank, world, dist)
+        except Exception as ex:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            res["dist_cg"] = {"failed": repr(ex)}
     del lib
     return res
 
@@ -710,7 +759,8 @@ def main():
                 mask, z = synthetic_sky_model(NSIDE)
                 extra['target'] = {'fsky': float(mask.mean())}
                 for lm in TARGET_LMAX:
-                    extra['target']['lmax%d' % lm] = run_target(lm, args.target_sims, tmp, mask, z, rank, world, dist, peak_nominal)
+                    extra['target']['lmax%d' % lm] = run_target(lm, args.target_sims, tmp, mask, z, rank, world, dist, peak_nominal,
+                                                                 with_dist_cg=(lm == TARGET_LMAX[0] and not args.no_dist))
                     sht.clear_plans()
                     import gc
                     gc.collect()
