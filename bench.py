@@ -519,6 +519,11 @@ def run_target(lmax, nsims, tmp, mask, z, rank, world, dist, peak_nominal, with_
             traceback.print_exc(file=sys.stderr)
             res["dist_cg"] = {"failed": repr(ex)}
     del lib
+    # the alm caches of this lmax (3 x 34-72 MB per simulation and rank) are not needed any more
+    barrier()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(os.path.join(tmp, 'lmax%d' % lmax), ignore_errors=True)
     return res
 
 
