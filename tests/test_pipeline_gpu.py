@@ -182,3 +182,27 @@ def test_cinv_tp_joint_filter_pipeline(tmp_path):
     qlms = qest.library_jtTP(str(tmp_path / 'qlms'), ivfs, ivfs, nside, lmax_qlm=lmax)
     G = qlms.get_sim_qlm('p', 0)
     assert np.all(np.isfinite(G)) and np.any(G != 0)
+
+
+@pytest.mark.parametrize("key", ['ptt', 'p_p', 'p'])
+def test_qe_power_equals_semi_analytic_n0(key):
+    """Known answer 8 of SURVEY.md section 8c (the idea of the reference's own test, tests/test_w.py:58-62, taken to the
+    map level): for a Gaussian, unlensed sky the raw spectrum of the unnormalised estimator is its Gaussian noise bias,
+    C_L^{qq} = N0_L, with N0 computed semi-analytically from the spectra of the same filtered maps by one-dimensional
+    Wigner-d integrals (nhl.get_nhl).  The two sides share no code below the filtered alms -- five syntheses, pixel
+    products and a spin-1 analysis on one, Gauss-Legendre quadrature of small-d matrices on the other -- so a wrong
+    factor, sign or spin convention anywhere in the QE path shows up as a ratio far from one.  nside 512, lmax 1024:
+    ~5e4 modes per band, realisation-dependent N0, so the ratio holds to a few per cent."""
+    from plancklens_b200 import hp
+    with tempfile.TemporaryDirectory() as tmp:
+        par = _load_params('idealized_example', {'PLENS': tmp, 'PLK_NSIDE': '512', 'PLK_LMAX_IVF': '1024', 'PLK_LMAX_QLM': '1200',
+                                                 'PLK_NSIMS': '2', 'PLK_DEVICE_SIMS': '1'})
+        for k in (key, 'x' + key[1:]):              # gradient and curl estimators
+            q = par.qlms_dd.get_sim_qlm(k, 0)
+            cl = hp.alm2cl(q) / par.qlms_dd.fsky12
+            n0 = par.nhl_dd.get_sim_nhl(0, k, k)
+            assert n0.shape == cl.shape
+            for lo, hi in ((10, 100), (100, 300), (300, 600), (600, 900)):
+                w = 2 * np.arange(lo, hi) + 1.
+                r = np.sum(w * cl[lo:hi]) / np.sum(w * n0[lo:hi])
+                assert abs(r - 1.) < 0.05, (k, lo, hi, r)
