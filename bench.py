@@ -606,7 +606,7 @@ def main():
     ap.add_argument('--ref-budget-s', type=float, default=150.0, help="wall-clock budget of the --impl reference arm")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-target', action='store_true', help="skip the masked-sky CG-filtered pipeline (extra.target)")
-    ap.add_argument('--target-sims', type=int, default=4, help="timed simulations per rank and lmax of extra.target")
+    ap.add_argument('--target-sims', type=int, default=6, help="timed simulations per rank and lmax of extra.target")
     ap.add_argument('--no-dist', action='store_true', help="skip the m-partitioned nside-4096 estimate (extra.dist, N > 1)")
     args = ap.parse_args()
     if args.impl == 'reference':
