@@ -658,7 +658,7 @@ extern "C" int plk_dist_partition(int nside, int mmax, int nranks, int mblk, int
   if (pair_lo) {
     // Cost of ring pair ip in the ring-FFT / pixel stage, in microseconds of one SM-parallel component pass, fitted to
     // the per-rank stage times of the nside-4096 / lmax-4000 'p' estimate on 8 B200 (profiles/r02_dist.md):
-    //   power-of-two rings (q = 2^j, incl. the whole equatorial belt): 0.37 us at q = 4096, scaled with q log2 q
+    //   power-of-two rings (q = 2^j, incl. the whole equatorial belt): 0.40 us at q = 4096, scaled with q log2 q
     //   Bluestein rings: 5.2e-6 * 2 M log2 M + 1.9e-5 q with M = nextpow2(2 q - 1) -- two M-point FFTs whatever q is,
     //   so the cost per PIXEL falls with q inside a size class (the round-1 model, pixels x a per-class factor, gave the
     //   polar ranks 7.1 ms of ring synthesis against 4.3 ms for the ranks holding the long Bluestein rings)
@@ -667,7 +667,7 @@ extern "C" int plk_dist_partition(int nside, int mmax, int nranks, int mblk, int
       const int q = ip < nside ? ip + 1 : nside;
       double c;
       if (q <= kTinyQ) c = 0.02 + 1.0e-5 * (mmax + 1);                       // direct sums over all m
-      else if ((q & (q - 1)) == 0) c = 0.37 * (double)q * ilog2(q) / (4096.0 * 12.0);
+      else if ((q & (q - 1)) == 0) c = 0.40 * (double)q * ilog2(q) / (4096.0 * 12.0);
       else { const int M = nextpow2(2 * q - 1); c = 5.2e-6 * 2.0 * M * ilog2(M) + 1.9e-5 * q; }
       if (ip == npair - 1) c *= 0.5;                                          // the equator has no southern twin
       cum[ip + 1] = cum[ip] + c;

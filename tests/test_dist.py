@@ -27,7 +27,7 @@ def test_partition_is_a_balanced_cover(nside, mmax, nranks):
     M = 2 ** np.ceil(np.log2(np.maximum(2 * q - 1, 1)))
     lg = lambda v: np.ceil(np.log2(np.maximum(v, 1)))
     c = np.where(q <= 8, 0.02 + 1e-5 * (mmax + 1),
-                 np.where(pow2, 0.37 * q * lg(q) / (4096. * 12.), 5.2e-6 * 2. * M * lg(M) + 1.9e-5 * q))
+                 np.where(pow2, 0.40 * q * lg(q) / (4096. * 12.), 5.2e-6 * 2. * M * lg(M) + 1.9e-5 * q))
     c[-1] *= 0.5
     cost = np.array([c[pair_lo[r]:pair_lo[r + 1]].sum() for r in range(nranks)])
     if nside >= 2048:
