@@ -145,6 +145,10 @@ int plk_scalar_ratio_dev(const double *num, const double *den, double scale, dou
 int plk_alm_copy_dev(int lmax_in, const void *in, int lmax_out, void *out, void *stream);
 /* out (lmax_hi) = lo for l <= lsplit, hi for l > lsplit */
 int plk_alm_splice_dev(int lmax_lo, const void *lo, int lmax_hi, const void *hi, int lsplit, void *out, void *stream);
+/* out = lo for l <= lsplit, fl[l] * hi above: multigrid.pre_op_split with a `diag_cl` high-l branch (multigrid.py:163-182,
+ * opfilt_tt.py:76-93) in one pass */
+int plk_alm_splice_xfl_dev(int lmax_lo, const void *lo, int lmax_hi, const void *hi, const double *fl, int nfl, int lsplit,
+                           void *out, void *stream);
 
 /* out = ca * x + cb * y  (y may be NULL);  eblm / cd_solve vector arithmetic (util_alm.py:66-86, cd_solve.py:57-86) */
 int plk_alm_lincomb_dev(long long n, double ca, const void *x, double cb, const void *y, void *out, void *stream);
@@ -154,6 +158,8 @@ int plk_alm_combine_dev(int lmax, int nterm, const void *const *in, const double
                         void *out, void *stream);
 /* real-harmonic packing of the dense preconditioner (qcinv/dense.py:16-53) and its mat-vec (dense.py:118-119) */
 int plk_alm2rlm_dev(int lmax, const void *alm, double *rlm, void *stream);
+/* same, reading the l <= lmax block of an alm stored with lmax_src >= lmax (multigrid.py:174: no intermediate alm_copy) */
+int plk_alm2rlm_from_dev(int lmax, int lmax_src, const void *alm, double *rlm, void *stream);
 int plk_rlm2alm_dev(int lmax, const double *rlm, void *alm, void *stream);
 int plk_dense_matvec_dev(int n, const double *A, const double *x, double *y, void *stream);
 

@@ -50,6 +50,8 @@ _SIGS = {
     'plk_alm_lincomb_dev': (c_int, [c_ll, c_dbl, vp, c_dbl, vp, vp, vp]),
     'plk_alm_combine_dev': (c_int, [c_int, c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(c_int), vp, vp]),
     'plk_alm2rlm_dev': (c_int, [c_int, vp, vp, vp]),
+    'plk_alm2rlm_from_dev': (c_int, [c_int, c_int, vp, vp, vp]),
+    'plk_alm_splice_xfl_dev': (c_int, [c_int, vp, c_int, vp, vp, c_int, c_int, vp, vp]),
     'plk_rlm2alm_dev': (c_int, [c_int, vp, vp, vp]),
     'plk_dense_matvec_dev': (c_int, [c_int, vp, vp, vp, vp]),
     'plk_dist_partition': (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),

@@ -1141,7 +1141,24 @@ extern "C" int plk_alm_combine_dev(int lmax, int nterm, const void *const *in, c
 extern "C" int plk_alm2rlm_dev(int lmax, const void *alm, double *rlm, void *stream) {
   if (!alm || !rlm) return fail(PLK_EINVAL, "NULL buffer");
   dim3 g((lmax + 256) / 256, lmax + 1);
-  alm2rlm_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax, (const cplx *)alm, rlm);
+  alm2rlm_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax, (const cplx *)alm, rlm, lmax);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm2rlm_from_dev(int lmax, int lmax_src, const void *alm, double *rlm, void *stream) {
+  if (!alm || !rlm) return fail(PLK_EINVAL, "NULL buffer");
+  if (lmax_src < lmax) return fail(PLK_EINVAL, "source lmax (%d) below the packed lmax (%d)", lmax_src, lmax);
+  dim3 g((lmax + 256) / 256, lmax + 1);
+  alm2rlm_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax, (const cplx *)alm, rlm, lmax_src);
+  LAUNCHED();
+  return PLK_OK;
+}
+extern "C" int plk_alm_splice_xfl_dev(int lmax_lo, const void *lo, int lmax_hi, const void *hi, const double *fl, int nfl,
+                                      int lsplit, void *out, void *stream) {
+  if (!lo || !hi || !fl || !out) return fail(PLK_EINVAL, "NULL buffer");
+  if (lsplit > lmax_lo || lsplit > lmax_hi) return fail(PLK_EINVAL, "lsplit exceeds lmax");
+  dim3 g((lmax_hi + 256) / 256, lmax_hi + 1);
+  alm_splice_xfl_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lmax_lo, (const cplx *)lo, lmax_hi, (const cplx *)hi, fl, nfl, lsplit, (cplx *)out);
   LAUNCHED();
   return PLK_OK;
 }

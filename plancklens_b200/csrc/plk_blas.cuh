@@ -239,6 +239,20 @@ __global__ void alm_splice_kernel(int lmax_lo, const cplx *__restrict__ lo, int 
   out[i] = (l <= lsplit) ? lo[alm_idx(lmax_lo, l, m)] : hi[i];
 }
 
+// out (lmax_hi) = lo for l <= lsplit, fl[l] * hi above: the diagonal high-l branch of multigrid.pre_op_split
+// (multigrid.py:163-182 with `diag_cl`) and the splice in one pass -- same numbers as almxfl followed by alm_splice
+__global__ void alm_splice_xfl_kernel(int lmax_lo, const cplx *__restrict__ lo, int lmax_hi, const cplx *__restrict__ hi,
+                                      const double *__restrict__ fl, int nfl, int lsplit, cplx *__restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l > lmax_hi || l < m) return;
+  const int64_t i = alm_idx(lmax_hi, l, m);
+  if (l <= lsplit) { out[i] = lo[alm_idx(lmax_lo, l, m)]; return; }
+  const double f = l < nfl ? fl[l] : 0.0;
+  const cplx a = hi[i];
+  out[i] = mk(f * a.x, f * a.y);
+}
+
 // ------------------------------------------------------------------ per-pixel passes
 // partial[b] = sum over the block's grid-stride share of a_p b_p (fixed grid -> fixed summation order)
 __global__ void map_dot_partial_kernel(long long n, const double *__restrict__ a, const double *__restrict__ b,
@@ -519,11 +533,12 @@ __global__ void udgrade_sum_kernel(int nside_in, const double *__restrict__ in, 
 }
 
 // real-harmonic packing used by the dense preconditioner (reference: qcinv/dense.py:16-53)
-__global__ void alm2rlm_kernel(int lmax, const cplx *__restrict__ alm, double *__restrict__ rlm) {
+// lmax_src >= lmax: layout of the alm array read from (the low-l block of a longer vector is packed without a copy)
+__global__ void alm2rlm_kernel(int lmax, const cplx *__restrict__ alm, double *__restrict__ rlm, int lmax_src) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (l > lmax || l < m) return;
-  const cplx a = alm[alm_idx(lmax, l, m)];
+  const cplx a = alm[alm_idx(lmax_src, l, m)];
   const double rt2 = 1.4142135623730951;
   if (m == 0) rlm[(size_t)l * l] = a.x;
   else { rlm[(size_t)l * l + 2 * m - 1] = a.x * rt2; rlm[(size_t)l * l + 2 * m] = a.y * rt2; }

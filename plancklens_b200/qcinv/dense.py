@@ -154,6 +154,14 @@ class _pre_op_dense:
     def calc(self, talm):
         return self._unpack(_matvec(self._minv_d, self._pack(talm)))
 
+    def calc_low(self, talm, lsplit):
+        """the same on the l <= lsplit block of a longer single-component vector, packed without the truncating copy"""
+        assert self.ncomp == 1 and lsplit == self.lmax and talm.lmax >= lsplit
+        n1 = (self.lmax + 1) ** 2
+        r = torch.empty(n1, dtype=torch.float64, device='cuda')
+        sht.check(sht._lib.load().plk_alm2rlm_from_dev(self.lmax, talm.lmax, sht._ptr(talm.t), sht._ptr(r), sht._stream()))
+        return self._unpack(_matvec(self._minv_d, r))
+
 
 class pre_op_dense_tt(_pre_op_dense):
     """reference: dense.py:57-119"""

@@ -252,6 +252,14 @@ class pre_op_split:
 
     def calc(self, talm):
         self.iter += 1
+        filt = getattr(self.pre_op_hgh, '_filt_d', None)
+        if isinstance(talm, util_alm.dalm) and filt is not None and talm.lmax == self.lmax:
+            # device vector, `diag_cl` above lsplit (opfilt_tt.pre_op_diag): the high-l almxfl and the splice are one
+            # kernel, and the operators read their argument without the defensive copies (none of them modifies it)
+            low = self.pre_op_low.calc_low(talm, self.lsplit) if hasattr(self.pre_op_low, 'calc_low') \
+                else self.pre_op_low(talm if talm.lmax == self.lsplit else util_alm.alm_copy(talm, lmax=self.lsplit))
+            from .. import sht
+            return util_alm.dalm(sht.alm_splice_xfl(low.t, talm.t, filt, self.lsplit), self.lmax)
         talm_low = self.pre_op_low(util_alm.alm_copy(talm, lmax=self.lsplit))
         talm_hgh = self.pre_op_hgh(util_alm.alm_copy(talm, lmax=self.lmax))
         return util_alm.alm_splice(talm_low, talm_hgh, self.lsplit)
@@ -281,6 +289,11 @@ class pre_op_multigrid:
     def calc(self, talm):
         if self.fixed:
             soltn = talm * 0.0
+            if getattr(talm, 'lmax', None) == self.lmax:
+                # the stage works at the lmax of its argument (every row of the default chains): no truncating copy
+                # before, no splice after -- cd_solve_fixed copies its right-hand side itself and never writes to it
+                cd_solve.cd_solve_fixed(soltn, talm, self.fwd_op, self.pre_ops, self.opfilt.dot_op(), self.iter_max)
+                return soltn
             cd_solve.cd_solve_fixed(soltn, util_alm.alm_copy(talm, lmax=self.lmax), self.fwd_op, self.pre_ops,
                                     self.opfilt.dot_op(), self.iter_max)
             return util_alm.alm_splice(soltn, talm, self.lmax)

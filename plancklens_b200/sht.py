@@ -362,6 +362,14 @@ def alm_splice(lo, hi, lsplit):
     return out
 
 
+def alm_splice_xfl(lo, hi, fl, lsplit):
+    """lo for l <= lsplit, fl[l] * hi above (one kernel; same numbers as almxfl followed by alm_splice)"""
+    out = torch.empty_like(hi)
+    check(_lib.load().plk_alm_splice_xfl_dev(alm_lmax(lo.numel()), _ptr(lo), alm_lmax(hi.numel()), _ptr(hi), _ptr(fl), int(fl.numel()),
+                                            int(lsplit), _ptr(out), _stream()))
+    return out
+
+
 def map_axpy(y, x, a):
     """y += a x on real maps (even number of pixels)"""
     assert y.numel() % 2 == 0

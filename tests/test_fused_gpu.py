@@ -137,3 +137,25 @@ def test_qe_fused_products_equal_separate_kernels(monkeypatch):
     for a, b in zip(out['1'], out['0']):
         for x, y in zip(a, b):
             assert rel_l2(x.cpu().numpy(), y.cpu().numpy()) < 1e-13
+
+
+@pytest.mark.parametrize("lmax,lsplit", [(8, 8), (64, 20), (256, 64), (300, 0)])
+def test_split_preconditioner_kernels(lmax, lsplit):
+    """multigrid.pre_op_split with a diagonal high-l branch: `alm_splice_xfl` = almxfl then alm_splice, and the dense
+    branch packs the l <= lsplit block of the longer vector exactly as it packs a truncated copy (multigrid.py:163-182)"""
+    import torch
+    from plancklens_b200 import _lib, hp, sht
+    from plancklens_b200.qcinv import util_alm
+    rng = np.random.default_rng(lmax + lsplit)
+    lo, hi = rand_alm(rng, lsplit), rand_alm(rng, lmax)
+    fl = rng.standard_normal(lmax + 1)
+    got = sht.alm_splice_xfl(sht.dev_alm(lo), sht.dev_alm(hi), sht.dev_fl(fl, lmax), lsplit).cpu().numpy()
+    want = util_alm.alm_splice(lo, hp.almxfl(hi, fl), lsplit)
+    assert np.array_equal(got, want)
+    r0 = torch.empty((lsplit + 1) ** 2, dtype=torch.float64, device='cuda')
+    r1 = torch.empty_like(r0)
+    cut = sht.dev_alm(util_alm.alm_copy(hi, lmax=lsplit))
+    sht.check(_lib.load().plk_alm2rlm_dev(lsplit, sht._ptr(cut), sht._ptr(r0), sht._stream()))
+    sht.check(_lib.load().plk_alm2rlm_from_dev(lsplit, lmax, sht._ptr(sht.dev_alm(hi)), sht._ptr(r1), sht._stream()))
+    assert torch.equal(r0, r1)
+    assert _lib.load().plk_alm2rlm_from_dev(lsplit + 1, lsplit, sht._ptr(cut), sht._ptr(r0), sht._stream()) != 0
