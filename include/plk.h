@@ -89,6 +89,12 @@ int plk_map2alm_add_dev(plk_plan *plan, int spin, const double *map1, const doub
  * (Q - iU)(G3 + iC3) - (Q + iU)(G1 - iC1)) and the N^-1 multiply of the one-map polarization filter
  * (opfilt_pp.py:272-303) fused into the transform that consumes them.  add1 == NULL: no additive term. */
 #define PLK_MAX_PIX_TERMS 6
+/* Lanes: independent chains of launches issued concurrently from different host threads / streams (the temperature and
+ * the polarization filter of one simulation; no counterpart in the reference, where filt_cinv.py:196-203 and :275-289 run
+ * one after the other).  The lane is a thread-local index; each lane owns the library's reduction scratch it uses. */
+#define PLK_MAX_LANES 4
+int plk_set_lane(int lane);
+int plk_get_lane(void);
 typedef struct plk_pixprog {
   int nterm;
   const double *a[PLK_MAX_PIX_TERMS];

@@ -49,6 +49,8 @@ _SIGS = {
     'plk_alm_splice_dev': (c_int, [c_int, vp, c_int, vp, c_int, vp, vp]),
     'plk_alm_lincomb_dev': (c_int, [c_ll, c_dbl, vp, c_dbl, vp, vp, vp]),
     'plk_alm_combine_dev': (c_int, [c_int, c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(c_int), vp, vp]),
+    'plk_set_lane': (c_int, [c_int]),
+    'plk_get_lane': (c_int, []),
     'plk_alm2rlm_dev': (c_int, [c_int, vp, vp, vp]),
     'plk_alm2rlm_from_dev': (c_int, [c_int, c_int, vp, vp, vp]),
     'plk_alm_splice_xfl_dev': (c_int, [c_int, vp, c_int, vp, vp, c_int, c_int, vp, vp]),

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -924,16 +925,33 @@ extern "C" int plk_map2alm_host(plk_plan *p, int spin, const double *map1, const
 static double *g_scratch = nullptr;   // per-process reduction scratch (current device at first use)
 static unsigned int *g_ticket = nullptr;   // ticket counters of the last-block reductions (zero between launches)
 static const size_t kScratchDoubles = 1 << 17;
+// Lanes: work issued concurrently from several host threads on several streams (the T and the P filter of one simulation,
+// filt_simple.library_sepTP.get_sim_teblm_dev) must not share reduction scratch.  A lane is a thread-local index chosen by
+// the caller (plk_set_lane); each lane owns its slice of the scratch and its ticket counters, and launches recorded into a
+// CUDA graph keep the slice of the lane they were captured in.
+static thread_local int t_lane = 0;
+static double *scr() { return g_scratch + (size_t)t_lane * kScratchDoubles; }
+static unsigned int *tick() { return g_ticket + t_lane * 64; }
+static std::mutex g_scratch_mu;
 static int scratch() {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
   if (g_scratch) return 0;
-  cudaError_t e = cudaMalloc((void **)&g_scratch, kScratchDoubles * sizeof(double));
+  double *s = nullptr;
+  cudaError_t e = cudaMalloc((void **)&s, PLK_MAX_LANES * kScratchDoubles * sizeof(double));
   if (e != cudaSuccess) return fail(PLK_ENOMEM, "cudaMalloc(scratch) failed: %s", cudaGetErrorString(e));
-  e = cudaMalloc((void **)&g_ticket, 64 * sizeof(unsigned int));
+  e = cudaMalloc((void **)&g_ticket, PLK_MAX_LANES * 64 * sizeof(unsigned int));
   if (e != cudaSuccess) return fail(PLK_ENOMEM, "cudaMalloc(ticket) failed: %s", cudaGetErrorString(e));
-  e = cudaMemset(g_ticket, 0, 64 * sizeof(unsigned int));
+  e = cudaMemset(g_ticket, 0, PLK_MAX_LANES * 64 * sizeof(unsigned int));
   if (e != cudaSuccess) return fail(PLK_ECUDA, "cudaMemset(ticket) failed: %s", cudaGetErrorString(e));
+  g_scratch = s;
   return 0;
 }
+extern "C" int plk_set_lane(int lane) {
+  if (lane < 0 || lane >= PLK_MAX_LANES) return fail(PLK_EINVAL, "lane %d outside [0, %d)", lane, PLK_MAX_LANES);
+  t_lane = lane;
+  return PLK_OK;
+}
+extern "C" int plk_get_lane(void) { return t_lane; }
 static int flat_grid(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
 
 extern "C" int plk_almxfl_dev(int lmax, const void *in, const double *fl, int nfl, void *out, void *stream) {
@@ -954,9 +972,9 @@ extern "C" int plk_alm_dot_dev(int lmax, int lmin, const void *a, const void *b,
   int rc = scratch();
   if (rc) return rc;
   if ((size_t)lmax + 1 > kScratchDoubles) return fail(PLK_EINVAL, "lmax too large");
-  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a, (const cplx *)b, g_scratch);
+  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a, (const cplx *)b, scr());
   LAUNCHED();
-  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, lmax + 1, 1, result_dev);
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(scr(), lmax + 1, 1, result_dev);
   LAUNCHED();
   return PLK_OK;
 }
@@ -966,11 +984,11 @@ extern "C" int plk_alm_dot2_dev(int lmax, int lmin, const void *a1, const void *
   int rc = scratch();
   if (rc) return rc;
   if (2 * ((size_t)lmax + 1) > kScratchDoubles) return fail(PLK_EINVAL, "lmax too large");
-  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a1, (const cplx *)b1, g_scratch);
+  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a1, (const cplx *)b1, scr());
   LAUNCHED();
-  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a2, (const cplx *)b2, g_scratch + lmax + 1);
+  dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a2, (const cplx *)b2, scr() + lmax + 1);
   LAUNCHED();
-  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, 2 * (lmax + 1), 1, result_dev);
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(scr(), 2 * (lmax + 1), 1, result_dev);
   LAUNCHED();
   return PLK_OK;
 }
@@ -983,10 +1001,10 @@ extern "C" int plk_alm_dotn_dev(int lmax, int lmin, int n, const void *const *a,
   for (int j = 0; j < n; ++j) {
     if (!a[j] || !b[j]) return fail(PLK_EINVAL, "NULL component");
     dot_partial_kernel<<<lmax + 1, 256, 0, (cudaStream_t)stream>>>(lmax, lmin, (const cplx *)a[j], (const cplx *)b[j],
-                                                                    g_scratch + (size_t)j * (lmax + 1));
+                                                                    scr() + (size_t)j * (lmax + 1));
     LAUNCHED();
   }
-  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, n * (lmax + 1), 1, result_dev);
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(scr(), n * (lmax + 1), 1, result_dev);
   LAUNCHED();
   return PLK_OK;
 }
@@ -1005,7 +1023,7 @@ extern "C" int plk_alm_dot_fused_dev(int lmax, int lmin, int n, const void *cons
     q.a[j] = (const cplx *)a[j]; q.b[j] = (const cplx *)b[j];
   }
   // second half of the scratch: the first half belongs to the two-kernel dots, which may be in flight on the stream
-  dot_fused_kernel<<<n * (lmax + 1), 256, 0, (cudaStream_t)stream>>>(q, lmax, lmin, g_scratch + kScratchDoubles / 2, g_ticket,
+  dot_fused_kernel<<<n * (lmax + 1), 256, 0, (cudaStream_t)stream>>>(q, lmax, lmin, scr() + kScratchDoubles / 2, tick(),
                                                                       num, den, scale, out3);
   LAUNCHED();
   return PLK_OK;
@@ -1056,9 +1074,9 @@ extern "C" int plk_map_dot_dev(long long n, const double *a, const double *b, do
   int rc = scratch();
   if (rc) return rc;
   const int nb = 148 * 8;
-  map_dot_partial_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(n, a, b, g_scratch);
+  map_dot_partial_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(n, a, b, scr());
   LAUNCHED();
-  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g_scratch, nb, 1, result_dev);
+  final_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(scr(), nb, 1, result_dev);
   LAUNCHED();
   return PLK_OK;
 }
@@ -1104,7 +1122,7 @@ extern "C" int plk_map_modes_dot_dev(plk_plan *p, double *m, const double *w, do
   int rc = ensure(p->partial, (size_t)4 * p->nring * sizeof(double));
   if (rc) return rc;
   if ((rc = scratch())) return rc;
-  modes_dot_kernel<<<p->nring, 256, 0, (cudaStream_t)stream>>>(p->rings, m, w, (double *)p->partial.p, g_ticket + 1, sums_dev);
+  modes_dot_kernel<<<p->nring, 256, 0, (cudaStream_t)stream>>>(p->rings, m, w, (double *)p->partial.p, tick() + 1, sums_dev);
   LAUNCHED();
   return PLK_OK;
 }

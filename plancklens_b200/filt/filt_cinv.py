@@ -194,6 +194,9 @@ class cinv_p(cinv):
                               marge_umaps=marge_umaps, marge_qmaps=marge_qmaps)
         self.chain_descr = chain_descr
         self.chain = util.jit(multigrid.multigrid_chain, opfilt_pp, chain_descr, cl, n_inv_filt)
+        # B200: this filter's solves run in lane 1 (own transform plans and reduction scratch, `sht.use_lane`), so that
+        # library_cinv_sepTP can run them next to the temperature filter's (lane 0) on a second stream
+        self.lane = 1
         if mpi.rank == 0:
             if not os.path.exists(lib_dir):
                 os.makedirs(lib_dir)
@@ -236,7 +239,8 @@ class cinv_p(cinv):
         else:
             talm = util_alm.eblm([util_alm.dalm.zeros(self.lmax), util_alm.dalm.zeros(self.lmax)])
         assert len(tmap) == 2
-        self.chain.solve(talm, [tmap[0], tmap[1]])
+        with sht.use_lane(self.lane):
+            self.chain.solve(talm, [tmap[0], tmap[1]])
         return talm.elm.t, talm.blm.t
 
     def _calc_febl(self):
@@ -468,6 +472,15 @@ class library_cinv_sepTP(filt_simple.library_sepTP):
 
     def _apply_ivf_p(self, pmap, soltn=None):
         return self.cinv_p.apply_ivf(pmap, soltn=soltn)
+
+    _TP_CONCURRENT = True          # the T and P solves of one simulation run side by side (filt_simple.library_sepTP)
+
+    def _tp_ready(self):
+        """Side by side only once both chains have captured their preconditioner graphs: the first solves create plans and
+        tables (cudaMalloc, synchronous uploads), which CUDA refuses while a stream of the process is capturing."""
+        def warm(c):
+            return all(not isinstance(op, multigrid.graphed_op) or op.graph is not None for op in c.chain.bstage.pre_ops)
+        return warm(self.cinv_t) and warm(self.cinv_p)
 
     def _apply_ivf_t_dev(self, tmap, soltn=None):
         return self.cinv_t.apply_ivf_dev(tmap, soltn=soltn)

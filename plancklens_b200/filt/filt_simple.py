@@ -171,40 +171,94 @@ class library_sepTP(object):
             f.result()
         self._io_pending = []
 
+    # T and P filters that are worth running side by side (two host threads, two streams): set by library_cinv_sepTP,
+    # whose conjugate-gradient solves each leave much of the GPU idle in their multigrid preconditioners
+    _TP_CONCURRENT = False
+
+    def _filter_t_dev(self, idx, tmap=None):
+        from .. import sht
+        soltn = None if self.soltn_lib is None else self.soltn_lib.get_sim_tmliklm(idx)
+        if hasattr(self, '_apply_ivf_t_dev'):
+            return self._apply_ivf_t_dev(self._sim_map_dev(idx, 't') if tmap is None else tmap, soltn=soltn)
+        return sht.dev_alm(self._apply_ivf_t(self.sim_lib.get_sim_tmap(idx), soltn=soltn))
+
+    def _filter_p_dev(self, idx, pmap=None):
+        from .. import sht
+        soltn = None
+        if self.soltn_lib is not None:
+            soltn = np.array([self.soltn_lib.get_sim_emliklm(idx), self.soltn_lib.get_sim_bmliklm(idx)])
+        if hasattr(self, '_apply_ivf_p_dev'):
+            return self._apply_ivf_p_dev(self._sim_map_dev(idx, 'p') if pmap is None else pmap, soltn=soltn)
+        e, b = self._apply_ivf_p(self.sim_lib.get_sim_pmap(idx), soltn=soltn)
+        return sht.dev_alm(e), sht.dev_alm(b)
+
+    def _filter_tp_concurrent(self, idx):
+        """T filter on the calling thread and stream, P filter on a worker thread and a second stream: the simulated maps
+        are made first (calling stream), the worker's stream waits for them, the calling stream waits for the worker's
+        results.  The two filters share no mutable device state (`sht.use_lane`)."""
+        import concurrent.futures as cf
+        import torch
+        if not hasattr(self, '_p_pool'):
+            self._p_pool = cf.ThreadPoolExecutor(max_workers=1)
+            # The temperature solve is the longer chain (13-16 top-level iterations against 5 at Planck-like noise): its
+            # stream outranks the polarization solve's, whose kernels then fill the SMs the temperature chain leaves idle
+            # in its multigrid preconditioner instead of queueing in front of its full-resolution transforms.
+            self._t_stream = torch.cuda.Stream(priority=int(os.environ.get('PLK_TP_TPRIO', '-2')))
+            self._p_stream = torch.cuda.Stream(priority=0)
+        tmap, pmap = self._sim_map_dev(idx, 't'), self._sim_map_dev(idx, 'p')
+        main = torch.cuda.current_stream()
+        dev = torch.cuda.current_device()
+        ready = torch.cuda.Event()
+        ready.record(main)
+
+        def work():
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(self._p_stream):
+                self._p_stream.wait_event(ready)
+                e, b = self._filter_p_dev(idx, pmap)
+                done = torch.cuda.Event()
+                done.record(self._p_stream)
+            return e, b, done
+        fut = self._p_pool.submit(work)
+        try:
+            with torch.cuda.stream(self._t_stream):
+                self._t_stream.wait_event(ready)
+                t = self._filter_t_dev(idx, tmap)
+                done_t = torch.cuda.Event()
+                done_t.record(self._t_stream)
+        finally:
+            e, b, done = fut.result()                          # re-raises what the worker raised
+        main.wait_event(done_t)
+        main.wait_event(done)
+        for x in (t, e, b):
+            x.record_stream(main)                              # allocated on the filters' streams, used on this one
+        return t, e, b
+
     def get_sim_teblm_dev(self, idx, fields='teb'):
         """Inverse-variance filtered alms of simulation idx as complex128 CUDA tensors, in the order of `fields`."""
         from .. import sht
         store = self._dev_store()
         ent = store.setdefault(idx, {})
         store.move_to_end(idx)
-        if 't' in fields and 't' not in ent:
-            fn = self._fname(idx, 't')
-            if os.path.exists(fn):
-                ent['t'] = sht.dev_alm(hp.read_alm(fn))
-            else:
-                soltn = None if self.soltn_lib is None else self.soltn_lib.get_sim_tmliklm(idx)
-                if hasattr(self, '_apply_ivf_t_dev'):
-                    ent['t'] = self._apply_ivf_t_dev(self._sim_map_dev(idx, 't'), soltn=soltn)
-                else:
-                    ent['t'] = sht.dev_alm(self._apply_ivf_t(self.sim_lib.get_sim_tmap(idx), soltn=soltn))
-                if self.cache:
-                    self._write_async(fn, ent['t'])
-        if ('e' in fields or 'b' in fields) and 'e' not in ent:
-            fn_e, fn_b = self._fname(idx, 'e'), self._fname(idx, 'b')
-            if os.path.exists(fn_e) and os.path.exists(fn_b):
-                ent['e'], ent['b'] = sht.dev_alm(hp.read_alm(fn_e)), sht.dev_alm(hp.read_alm(fn_b))
-            else:
-                soltn = None
-                if self.soltn_lib is not None:
-                    soltn = np.array([self.soltn_lib.get_sim_emliklm(idx), self.soltn_lib.get_sim_bmliklm(idx)])
-                if hasattr(self, '_apply_ivf_p_dev'):
-                    ent['e'], ent['b'] = self._apply_ivf_p_dev(self._sim_map_dev(idx, 'p'), soltn=soltn)
-                else:
-                    e, b = self._apply_ivf_p(self.sim_lib.get_sim_pmap(idx), soltn=soltn)
-                    ent['e'], ent['b'] = sht.dev_alm(e), sht.dev_alm(b)
-                if self.cache:
-                    self._write_async(fn_e, ent['e'])
-                    self._write_async(fn_b, ent['b'])
+        fn_t, fn_e, fn_b = (self._fname(idx, f) for f in 'teb')
+        need_t = 't' in fields and 't' not in ent
+        need_p = ('e' in fields or 'b' in fields) and 'e' not in ent
+        if need_t and os.path.exists(fn_t):
+            ent['t'], need_t = sht.dev_alm(hp.read_alm(fn_t)), False
+        if need_p and os.path.exists(fn_e) and os.path.exists(fn_b):
+            ent['e'], ent['b'], need_p = sht.dev_alm(hp.read_alm(fn_e)), sht.dev_alm(hp.read_alm(fn_b)), False
+        if need_t and need_p and self._TP_CONCURRENT and os.environ.get('PLK_TP_CONCURRENT', '1') != '0' \
+                and getattr(self, '_tp_ready', lambda: True)():
+            ent['t'], ent['e'], ent['b'] = self._filter_tp_concurrent(idx)
+        else:
+            if need_t:
+                ent['t'] = self._filter_t_dev(idx)
+            if need_p:
+                ent['e'], ent['b'] = self._filter_p_dev(idx)
+        if self.cache:
+            for f, need in (('t', need_t), ('e', need_p), ('b', need_p)):
+                if need:
+                    self._write_async(self._fname(idx, f), ent[f])
         while len(store) > self._DEV_CACHE_SIMS:
             store.popitem(last=False)
         return tuple(ent[f] for f in fields)

@@ -9,6 +9,7 @@ import gc
 import os
 import re
 import sys
+import threading
 
 import torch
 
@@ -128,6 +129,9 @@ def _vec_clone(v):
     return util_alm.eblm([_vec_clone(v.elm), _vec_clone(v.blm)])
 
 
+_CAPTURE_LOCK = threading.Lock()      # torch.cuda.graph synchronises and trims the allocator on entry: one capture at a time
+
+
 class graphed_op:
     """Applies a host-synchronisation-free preconditioner through a CUDA graph.
 
@@ -140,6 +144,12 @@ class graphed_op:
         self.calls = 0
         self.graph = None
         self.v_in = self.v_out = None
+        # The preconditioner is a chain of small dependent kernels.  When another lane's full-resolution transforms are in
+        # flight (filt_simple.library_sepTP runs the T and the P filter side by side) it goes through a high-priority
+        # stream: the block scheduler then places its few blocks ahead of the pending blocks of the big grid instead of
+        # behind all of them.  PLK_CG_PRIO=0 replays on the calling stream.
+        self.prio = os.environ.get('PLK_CG_PRIO', '1') != '0'
+        self.stream = None
 
     def __call__(self, v):
         return self.calc(v)
@@ -156,16 +166,32 @@ class graphed_op:
             gc.collect()
             gc_was_on = gc.isenabled()
             gc.disable()
+            # own capture stream: torch's default one is shared by every capture of the process, and two lanes may be
+            # capturing at the same time
+            # lane 0 (temperature, the longer solve) outranks lane 1 (polarization); within a lane the preconditioner
+            # outranks the full-resolution operator of the other lane's level
+            from .. import sht
+            self.stream = torch.cuda.Stream(priority=(-3 if sht.lane() == 0 else -1) if self.prio else 0)
             try:
-                with torch.cuda.graph(g, capture_error_mode='thread_local'):
-                    self.v_out = self.op(self.v_in)
+                with _CAPTURE_LOCK:
+                    with torch.cuda.graph(g, stream=self.stream, capture_error_mode='thread_local'):
+                        self.v_out = self.op(self.v_in)
             finally:
                 if gc_was_on:
                     gc.enable()
             self.graph = g
-        for dst, src in zip(_vec_tensors(self.v_in), _vec_tensors(v)):
-            dst.copy_(src)
-        self.graph.replay()
+        if not self.prio:
+            for dst, src in zip(_vec_tensors(self.v_in), _vec_tensors(v)):
+                dst.copy_(src)
+            self.graph.replay()
+            return _vec_clone(self.v_out)
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for dst, src in zip(_vec_tensors(self.v_in), _vec_tensors(v)):
+                dst.copy_(src)
+            self.graph.replay()
+        cur.wait_stream(self.stream)
         return _vec_clone(self.v_out)
 
 

@@ -2,7 +2,9 @@
 
 torch tensors are only carriers for device memory and streams; every FLOP runs in libplk_b200.so.
 """
+import contextlib
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -11,6 +13,30 @@ from . import _lib
 from ._lib import check, vp
 
 _PLANS = {}
+_TLS = threading.local()
+MAX_LANES = 4
+
+
+def lane():
+    """lane of the calling thread (0 unless inside `use_lane`)"""
+    return getattr(_TLS, 'lane', 0)
+
+
+@contextlib.contextmanager
+def use_lane(k):
+    """Runs the enclosed calls of this thread in lane k: its own plans (`get_plan`: work buffers are per plan) and its own
+    reduction scratch in the library, so that two host threads on two CUDA streams -- the T and the P filter of one
+    simulation -- never share mutable device state.  Objects bind to a lane by wrapping their work in it (`filt_cinv`)."""
+    k = int(k)
+    assert 0 <= k < MAX_LANES
+    old = lane()
+    _TLS.lane = k
+    check(_lib.load().plk_set_lane(k))
+    try:
+        yield
+    finally:
+        _TLS.lane = old
+        check(_lib.load().plk_set_lane(old))
 
 
 def _require_cuda():
@@ -243,7 +269,7 @@ class Plan:
 
 
 def get_plan(nside, lmax):
-    key = (int(nside), int(lmax), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    key = (int(nside), int(lmax), torch.cuda.current_device() if torch.cuda.is_available() else -1, lane())
     if key not in _PLANS:
         _PLANS[key] = Plan(nside, lmax)
     return _PLANS[key]

@@ -115,6 +115,76 @@ def test_library_cinv_sepTP_matches_reference(case, libs):
     assert rel_l2(gi.alm_sample(tlm2, lmax), g['tlm2_sample']) < 1e-7
 
 
+def test_t_and_p_filters_side_by_side(case, libs, tmp_path, monkeypatch):
+    """library_cinv_sepTP runs the T and the P solve of one simulation on two host threads and two streams once both
+    chains are warm (filt_simple.library_sepTP._filter_tp_concurrent): same bits as one after the other, same iteration
+    counts, and the next simulations keep agreeing (lanes: no shared plans or reduction scratch)."""
+    import torch
+    from plancklens_b200.filt import filt_cinv
+    cinv_t, cinv_p, _ = libs
+    sims = gi.fixed_sim_lib(case)
+    seq = filt_cinv.library_cinv_sepTP(str(tmp_path / 'seq'), sims, cinv_t, cinv_p, case['cls'])
+    con = filt_cinv.library_cinv_sepTP(str(tmp_path / 'con'), sims, cinv_t, cinv_p, case['cls'])
+    monkeypatch.setenv('PLK_TP_CONCURRENT', '0')
+    want = {}
+    for idx in (3, 4, 5):
+        want[idx] = [x.clone() for x in seq.get_sim_teblm_dev(idx)] + [cinv_t.chain.niter, cinv_p.chain.niter]
+    assert not hasattr(seq, '_p_pool') and seq._tp_ready()
+    monkeypatch.setenv('PLK_TP_CONCURRENT', '1')
+    for idx in (3, 4, 5):
+        t, e, b = con.get_sim_teblm_dev(idx)
+        assert hasattr(con, '_p_pool')
+        torch.cuda.synchronize()
+        for got, ref, name in zip((t, e, b), want[idx], 'teb'):
+            assert torch.equal(got, ref), (idx, name)
+        assert [cinv_t.chain.niter, cinv_p.chain.niter] == want[idx][3:]
+    con.flush()
+    seq.flush()
+    from plancklens_b200 import hp
+    assert np.array_equal(hp.read_alm(os.path.join(con.lib_dir, 'sim_0004_elm.fits')), want[4][1].cpu().numpy())
+    # one field at a time still goes through the plain path
+    t6, = con.get_sim_teblm_dev(6, 't')
+    e6, b6 = con.get_sim_teblm_dev(6, 'eb')
+    monkeypatch.setenv('PLK_TP_CONCURRENT', '0')
+    ref6 = seq.get_sim_teblm_dev(6)
+    assert torch.equal(t6, ref6[0]) and torch.equal(e6, ref6[1]) and torch.equal(b6, ref6[2])
+
+
+def test_lanes_have_their_own_plans_and_scratch():
+    import threading
+    import torch
+    from plancklens_b200 import _lib, sht
+    from helpers import rand_alm
+    p0 = sht.get_plan(32, 64)
+    with sht.use_lane(1):
+        assert sht.lane() == 1 and _lib.load().plk_get_lane() == 1
+        p1 = sht.get_plan(32, 64)
+        with sht.use_lane(2):
+            assert sht.get_plan(32, 64) is not p1
+        assert sht.lane() == 1 and _lib.load().plk_get_lane() == 1
+    assert sht.lane() == 0 and _lib.load().plk_get_lane() == 0 and p1 is not p0 and sht.get_plan(32, 64) is p0
+    assert _lib.load().plk_set_lane(sht.MAX_LANES) != 0
+    # the lane is per thread, and dots issued from two lanes on two streams at once agree with the serial ones
+    rng = np.random.default_rng(5)
+    a = [sht.dev_alm(rand_alm(rng, 700)) for _ in range(4)]
+    want = [sht.alm_dot_fused([a[i]], [a[i + 1]])[0:1].clone() for i in (0, 2)]
+    torch.cuda.synchronize()
+    out, seen = {}, {}
+
+    def work(k):
+        with sht.use_lane(k), torch.cuda.stream(torch.cuda.Stream()):
+            seen[k] = (sht.lane(), _lib.load().plk_get_lane())
+            for _ in range(300):
+                r = sht.alm_dot_fused([a[2 * k]], [a[2 * k + 1]])
+            torch.cuda.current_stream().synchronize()
+            out[k] = r[0:1].clone()
+    th = [threading.Thread(target=work, args=(k,)) for k in (0, 1)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert seen == {0: (0, 0), 1: (1, 1)}
+    assert torch.equal(out[0], want[0]) and torch.equal(out[1], want[1])
+
+
 def test_inner_stage_traces_match_reference(case, libs):
     """the reference logs every inner multigrid stage as well (1105 lines for one T solve); with the host-scalar path
     (PLK_CG_FIXED=0, PLK_CG_GRAPH=0: same kernels, step lengths read back like the reference's) the whole log agrees"""
