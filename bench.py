@@ -810,7 +810,7 @@ def main():
                                         "HBM and bf16 peaks only, neither bounds this kernel" % (sm_max, sm_run),
                          "executed_share_of_volume": act, "achieved_full_volume": full, "frac_full_volume": full / peak_nominal,
                          "note": "achieved = DFMA rate the kernel sustains: 24 flop x the (l, m, ring pair) volume it walks / launch "
-                                 "time; it skips the share of the volume below the 2^-120 start threshold near the poles.  "
+                                 "time; it skips the share of the volume below the 2^-60 start threshold near the poles.  "
                                  "achieved_full_volume credits the whole volume (the SURVEY.md section 8d count)",
                          "launch_ms": k_ms, "launches_timed": cnt, "flop_per_launch_full_volume": fs,
                          "traffic": traffic, "traffic_source": traffic_src,

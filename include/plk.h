@@ -59,8 +59,8 @@ int plk_plan_create(plk_plan **plan, int nside, int lmax, int mmax);
 int plk_plan_destroy(plk_plan *plan);
 /* bytes of device memory currently held by the plan (tables + scratch) */
 long long plk_plan_device_bytes(const plk_plan *plan);
-/* Start threshold 2^exp2 of the on-the-fly Legendre recurrences (default 2^-120; libsharp, which healpy / ducc0 wrap
- * behind plancklens/shts.py:33-35, starts accumulating at 2^-60).  (l, m, ring) contributions below it are skipped
+/* Start threshold 2^exp2 of the on-the-fly Legendre recurrences (default 2^-60, the value at which libsharp, which
+ * healpy / ducc0 wrap behind plancklens/shts.py:33-35, starts accumulating).  (l, m, ring) contributions below it are skipped
  * near the poles; results must not depend on it at the 1e-10 level, which the full-size parity tests check by
  * varying it.  Rebuilds the per-spin seed tables on next use; exp2 in [-900, -20]. */
 int plk_plan_set_seed_threshold(plk_plan *plan, int exp2);
@@ -261,7 +261,7 @@ int plk_wignercoeff_dev(const double *f, const double *x, int nx, int s1, int s2
 int plk_profile_enable(int on);
 int plk_profile_read(int *counts5, double *total_ms5);
 int plk_fp64_peak(double *tflops, int reps);
-/* share of the (l, m, ring pair) volume the Legendre kernels walk for this spin (the rest lies below the 2^-120
+/* share of the (l, m, ring pair) volume the Legendre kernels walk for this spin (the rest lies below the 2^-60
  * start threshold near the poles and is skipped) */
 int plk_plan_active_fraction(plk_plan *plan, int spin, double *frac);
 

@@ -1315,7 +1315,7 @@ extern "C" int plk_profile_read(int *counts, double *total_ms) {
 }
 
 // Share of the (l, m, ring pair) volume the Legendre kernels actually walk for this spin: 1 - the part below the
-// 2^-120 start threshold near the poles (skipped).  bench.py reports the roofline both on the algorithmic count of
+// 2^-60 start threshold near the poles (skipped).  bench.py reports the roofline both on the algorithmic count of
 // SURVEY.md section 8d (full volume) and on this executed share.
 extern "C" int plk_plan_active_fraction(plk_plan *p, int spin, double *frac) {
   CHECK_PLAN(p);

@@ -37,8 +37,11 @@ constexpr int kChunk = PLK_CHUNK;      // l values per TMA stage (even)
 constexpr int kStages = 4;
 constexpr int kNCW = 4;          // compute warps per block
 constexpr int kLegThreads = (kNCW + PLK_PRODUCER_WARP) * 32;
-constexpr int kSeedThrExp = -120;  // default start threshold: accumulation starts once |p_l| >= 2^-120 (libsharp itself
-                                   // uses 2^-60); per plan through plk_plan_set_seed_threshold (parity tests vary it)
+constexpr int kSeedThrExp = -60;   // default start threshold: accumulation starts once |p_l| >= 2^-60, libsharp's own
+                                   // sharp_ftol.  Measured at nside = lmax = 2048 against 2^-200: rel. L2 3e-17, max-abs 6e-16
+                                   // of the largest value (2^-120 and 2^-90: bit-identical to 2^-200) while the walked volume
+                                   // drops from 0.739 to 0.711 (scripts/time_threshold.py).  Per plan through
+                                   // plk_plan_set_seed_threshold (the parity tests vary it)
 
 struct DevGeom {
   int nside, npair, nring;

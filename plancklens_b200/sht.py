@@ -117,7 +117,7 @@ class Plan:
         return float(v.value)
 
     def set_seed_threshold(self, exp2):
-        """start threshold 2^exp2 of the Legendre recurrences (default 2^-120); seed tables are rebuilt on next use"""
+        """start threshold 2^exp2 of the Legendre recurrences (default 2^-60); seed tables are rebuilt on next use"""
         check(self.lib.plk_plan_set_seed_threshold(self._h, int(exp2)))
 
     def device_bytes(self):

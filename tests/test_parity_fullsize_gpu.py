@@ -3,7 +3,7 @@ not through adjointness (synthesis and analysis share one start / skip table, so
 self-adjoint and invisible to an adjointness test).
 
 The oracle starts its recurrences at 2^-900 (it skips nothing that a double can hold) while the CUDA kernels start at
-2^-120 and drop ring pairs that never get there: agreement at 1e-10 on columns that include m ~ lmax, and on the rings
+2^-60 and drop ring pairs that never get there: agreement at 1e-10 on columns that include m ~ lmax, and on the rings
 next to the poles, is what shows the skip is harmless.  The oracle runs on an m sample (`legendre_*_mlist`, a few
 seconds) because the full band costs minutes on the CPU; one case per direction runs the whole transform.
 
@@ -99,11 +99,11 @@ def test_legendre_analysis_fullsize(sht, oracle_sht, nside, lmax, spin):
     del Xd
 
 
-@pytest.mark.parametrize("exp2", [-60, -200])
+@pytest.mark.parametrize("exp2", [-120, -200])
 @pytest.mark.parametrize("spin", [0, 2])
 def test_start_threshold_insensitivity(sht, oracle_sht, exp2, spin):
-    """The 2^-120 start threshold is a performance knob, not a numerical one: at the north_star size (nside 2048,
-    lmax 3000) results with 2^-60 (libsharp's own) and 2^-200 agree with the oracle as well as the default does."""
+    """The start threshold (default 2^-60, libsharp's own) is a performance knob, not a numerical one: at the north_star
+    size (nside 2048, lmax 3000) results with 2^-120 and 2^-200 agree with the oracle as well as the default does."""
     import torch
     nside, lmax = 2048, 3000
     rng = np.random.default_rng(77 + spin)
@@ -114,7 +114,7 @@ def test_start_threshold_insensitivity(sht, oracle_sht, exp2, spin):
     c = rand_alm(rng, lmax, spin) if spin else None
     R1, R2 = oracle_sht.legendre_synth_mlist(nside, spin, lmax, g, c, ms)
     frac = {}
-    for e in (-120, exp2):
+    for e in (-60, exp2):
         plan.set_seed_threshold(e)
         frac[e] = plan.active_fraction(spin)
         X1, X2 = plan.legendre_synth(spin, sht.dev_alm(g), sht.dev_alm(c) if spin else None)
@@ -128,14 +128,14 @@ def test_start_threshold_insensitivity(sht, oracle_sht, exp2, spin):
             t[:, ms.astype(np.int64)] = torch.from_numpy(x).cuda()
             Xd.append(t)
         a1, a2 = plan.legendre_anal(spin, Xd[0], Xd[1] if spin else None)
-        if e == -120:
+        if e == -60:
             base = a1.clone()
         else:
             rows = torch.from_numpy(_alm_rows(lmax, ms)).cuda()
             assert float(torch.linalg.norm(a1[rows] - base[rows]) / torch.linalg.norm(base[rows])) < 1e-13
         del X1, X2, Xd
     # the knob does what it says: a higher threshold walks less of the (l, m, ring) volume
-    assert (frac[exp2] < frac[-120]) == (exp2 > -120), frac
+    assert frac[exp2] > frac[-60], frac
     del plan
 
 
