@@ -397,14 +397,16 @@ class library:
         """Pipelined `eval_qlm` over many simulations: yields (idx, G, C) in order (numpy out, same legs on both
         sides -- the `qlms_dd` case).
 
-        Three things run concurrently: the host -> device copy of simulation i + 1's filtered alms (copy stream),
-        the transforms of simulation i (compute stream), and the device -> host copy plus the caller's handling of
+        Three things run concurrently: the host -> device copy of simulation i + 1's filtered alms (upload stream),
+        the transforms of simulation i (compute stream), and the device -> host copy (download stream) plus the caller's handling of
         estimate i - 1.  Inputs and outputs are double buffered; pinned host arrays (torch `pin_memory`) are copied
         asynchronously, pageable ones go through pinned staging buffers."""
         assert k in ['ptt', 'p_p', 'p'], k
         assert self.f2map1.ivfs is self.f2map2.ivfs, "pipelined evaluation covers identical legs; use eval_qlm otherwise"
         ivfs, f2 = self.f2map1.ivfs, self.f2map2
-        main, cs = torch.cuda.current_stream(), torch.cuda.Stream()
+        # one stream per copy direction: on a single copy stream the upload of simulation i + 1 would queue behind the
+        # download of estimate i, which waits for the transforms of simulation i -- no overlap left
+        main, cs, cs_out = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
         ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]
         h2d_done, comp_done, d2h_done = ev(), ev(), ev()
         dev_in, pin_in, pin_out, live = [None, None], [None, None], [None, None], [None, None]
@@ -457,11 +459,11 @@ class library:
             comp_done[s].record(main)
             if pin_out[s] is None:
                 pin_out[s] = [torch.empty(G.numel(), dtype=torch.complex128, pin_memory=True) for _ in range(2)]
-            cs.wait_event(comp_done[s])
-            with torch.cuda.stream(cs):
+            cs_out.wait_event(comp_done[s])
+            with torch.cuda.stream(cs_out):
                 pin_out[s][0].copy_(G, non_blocking=True)
                 pin_out[s][1].copy_(C, non_blocking=True)
-                d2h_done[s].record(cs)
+                d2h_done[s].record(cs_out)
             live[s].append((G, C))                       # device results stay allocated until their copy is done
             if prev is not None:
                 yield finish(*prev)
