@@ -39,6 +39,36 @@ def test_product_fails_loudly_without_gpu():
         hp.alm2map(np.zeros(alm_size(4), dtype=complex), 2)
 
 
+def test_lanes_are_thread_local_and_nest():
+    """sht.use_lane / plk_set_lane (no GPU needed): the lane is per host thread, nests, is restored on exit and is
+    bounded by PLK_MAX_LANES -- what keeps the T and the P filter of one simulation apart when they run side by side"""
+    import threading
+    from plancklens_b200 import _lib, sht
+    lib = _lib.load()
+    assert sht.lane() == 0 and lib.plk_get_lane() == 0
+    seen = {}
+
+    def other():
+        seen['start'] = (sht.lane(), lib.plk_get_lane())
+        with sht.use_lane(2):
+            seen['in'] = (sht.lane(), lib.plk_get_lane())
+    with sht.use_lane(1):
+        assert (sht.lane(), lib.plk_get_lane()) == (1, 1)
+        t = threading.Thread(target=other)
+        t.start()
+        t.join()
+        with sht.use_lane(3):
+            assert (sht.lane(), lib.plk_get_lane()) == (3, 3)
+        assert (sht.lane(), lib.plk_get_lane()) == (1, 1)
+        with pytest.raises(AssertionError):
+            with sht.use_lane(sht.MAX_LANES):
+                pass
+        assert (sht.lane(), lib.plk_get_lane()) == (1, 1)
+    assert (sht.lane(), lib.plk_get_lane()) == (0, 0)
+    assert seen == {'start': (0, 0), 'in': (2, 2)}
+    assert lib.plk_set_lane(-1) != 0 and lib.plk_set_lane(sht.MAX_LANES) != 0 and lib.plk_get_lane() == 0
+
+
 def test_product_never_imports_oracle():
     """The product path must not route through the oracle (tier framing, section 3)."""
     bad = []
