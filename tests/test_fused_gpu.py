@@ -159,3 +159,16 @@ def test_split_preconditioner_kernels(lmax, lsplit):
     sht.check(_lib.load().plk_alm2rlm_from_dev(lsplit, lmax, sht._ptr(sht.dev_alm(hi)), sht._ptr(r1), sht._stream()))
     assert torch.equal(r0, r1)
     assert _lib.load().plk_alm2rlm_from_dev(lsplit + 1, lsplit, sht._ptr(cut), sht._ptr(r0), sht._stream()) != 0
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 200, 1089, 4225])
+def test_dense_product(n):
+    """plk_dense_matvec_dev (dense coarse preconditioner, dense.py:110-119): A x against numpy, bit-reproducible from call to call"""
+    import torch
+    from plancklens_b200.qcinv import dense
+    rng = np.random.default_rng(n)
+    a, x = rng.standard_normal((n, n)), rng.standard_normal(n)
+    A, X = torch.from_numpy(a).cuda(), torch.from_numpy(x).cuda()
+    y = dense._matvec(A, X)
+    assert np.all(np.abs(y.cpu().numpy() - a @ x) <= 4e-16 * n ** 0.5 * (np.abs(a) @ np.abs(x)) + 1e-300)
+    assert torch.equal(dense._matvec(A, X), y)
