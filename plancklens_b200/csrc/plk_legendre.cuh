@@ -209,6 +209,20 @@ struct StageBytes {
   static constexpr int stage = per_l * kChunk;
 };
 
+// The synthesis loop takes the l of a row two at a time: behind a chunk that ends on an odd count (only the last chunk of a
+// row of odd length can: kChunk is even) the producer appends one ZERO record and one zero UV pair, copied by the same
+// engine onto the same mbarrier as the data -- the compute warps never write to the stage themselves.
+__device__ __align__(16) double g_zero_rec[4] = {0.0, 0.0, 0.0, 0.0};   // never written
+template <bool SPIN, bool SYNTH>
+PLK_D uint32_t pad_bytes(int n) { return (SYNTH && (n & 1)) ? (uint32_t)(StageBytes<SPIN, SYNTH>::rec + 16) : 0u; }
+template <bool SPIN, bool SYNTH>
+PLK_D void pad_odd_row(unsigned char *dst, int n, uint64_t *bar) {
+  using SB = StageBytes<SPIN, SYNTH>;
+  if (!SYNTH || !(n & 1)) return;
+  tma_load_1d(dst + (size_t)n * SB::rec, g_zero_rec, (uint32_t)SB::rec, bar);
+  tma_load_1d(dst + SB::rec * kChunk + (size_t)n * 16, g_zero_rec, 16u, bar);
+}
+
 // Producer warp body: streams chunks [c0, nchunk) of row m into the stage ring.  One lane works; while the
 // ring is full it sleeps (nanosleep back-off) instead of burning issue slots the FP64 warps need.
 template <bool SPIN, bool SYNTH>
@@ -227,9 +241,10 @@ PLK_D void producer_loop(unsigned char *stage_base, uint64_t *full, uint64_t *em
     const int n = min(kChunk, K - k0);
     unsigned char *dst = stage_base + (size_t)st * SB::stage;
     const uint32_t bytes = (uint32_t)n * SB::per_l;
-    mbar_expect_tx(&full[st], bytes);
+    mbar_expect_tx(&full[st], bytes + pad_bytes<SPIN, SYNTH>(n));
     if (SYNTH) tma_load_1d(dst, (const unsigned char *)rec_row + (size_t)k0 * SB::rec, (uint32_t)n * SB::rec, &full[st]);
     tma_load_1d(dst + SB::rec * kChunk, uv_row + k0, (uint32_t)n * 16, &full[st]);
+    pad_odd_row<SPIN, SYNTH>(dst, n, &full[st]);
   }
 }
 
@@ -242,9 +257,10 @@ PLK_D void issue_chunk(unsigned char *stage_base, uint64_t *full, const void *re
   const int k0 = c * kChunk;
   const int n = min(kChunk, K - k0);
   unsigned char *dst = stage_base + (size_t)st * SB::stage;
-  mbar_expect_tx(&full[st], (uint32_t)n * SB::per_l);
+  mbar_expect_tx(&full[st], (uint32_t)n * SB::per_l + pad_bytes<SPIN, SYNTH>(n));
   if (SYNTH) tma_load_1d(dst, (const unsigned char *)rec_row + (size_t)k0 * SB::rec, (uint32_t)n * SB::rec, &full[st]);
   tma_load_1d(dst + SB::rec * kChunk, uv_row + k0, (uint32_t)n * 16, &full[st]);
+  pad_odd_row<SPIN, SYNTH>(dst, n, &full[st]);
 }
 // Producer duties folded into compute warp 0 (PLK_PRODUCER_WARP == 0).  Called by every thread of warp 0 after it
 // has released chunk c: refills the stage of chunk c - 1 -- which the other warps have almost always left by now,
@@ -362,15 +378,7 @@ legendre_synth_kernel(DevGeom g, DevSpin t, const void *__restrict__ rec, cplx *
     const int k0 = c * kChunk;
     const int kend = min(k0 + kChunk, K);
     unsigned char *sb = stage_base + (size_t)st * SB::stage;
-    if ((kend & 1) && kend == K) {
-      // odd row length: the (k, k+1) loop below reads one record past the row; make it a zero record
-      if (lane == 0) {
-        if (SPIN) reinterpret_cast<double4 *>(sb)[kend - k0] = make_double4(0.0, 0.0, 0.0, 0.0);
-        else reinterpret_cast<double2 *>(sb)[kend - k0] = make_double2(0.0, 0.0);
-        reinterpret_cast<double2 *>(sb + SB::rec * kChunk)[kend - k0] = make_double2(0.0, 0.0);
-      }
-      __syncwarp();
-    }
+    // (odd row length: the (k, k+1) loop below reads one record past the row -- a zero record the producer appended)
     if (kend > kw_min) {
       const double2 *uvs = reinterpret_cast<const double2 *>(sb + SB::rec * kChunk);
       for (int k = max(k0, kw_min); k < kend; k += 2) {
