@@ -1,4 +1,4 @@
-"""Start threshold of the Legendre recurrences (default 2^-120; libsharp's sharp_ftol is 2^-60): walked share of the
+"""Start threshold of the Legendre recurrences (default 2^-60, libsharp's sharp_ftol; 2^-120 until late in round 2): walked share of the
 (l, m, ring pair) volume, kernel-stage times and the change of the results, nside = lmax = 2048 (or argv[1], argv[2])."""
 import os, sys
 import numpy as np
