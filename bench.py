@@ -427,8 +427,8 @@ def run_target(lmax, nsims, tmp, mask, z, rank, world, dist, peak_nominal, with_
     nalm = alm_size(lmax)
     mf = [torch.zeros(nalm, dtype=torch.complex128, device='cuda') for _ in range(2)]
 
-    def one(idx):
-        G, C = q.get_sim_qlm_dev('p', idx)
+    def one(idx, prefetch=()):
+        G, C = q.get_sim_qlm_dev('p', idx, prefetch=prefetch)
         sht.alm_axpy(mf[0], G, 1.0)
         sht.alm_axpy(mf[1], C, 1.0)
 
@@ -445,10 +445,15 @@ def run_target(lmax, nsims, tmp, mask, z, rank, world, dist, peak_nominal, with_
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw = time.perf_counter()
     e0.record()
-    for i in range(nsims):
-        one(1000 * rank + 2 + i)          # distinct simulations on every rank: idx % N sharding of a batch
-        its_t.append(int(lib['cinv_t'].chain.niter))
-        its_p.append(int(lib['cinv_p'].chain.niter))
+    idxs = [1000 * rank + 2 + i for i in range(nsims)]     # distinct simulations on every rank: idx % N sharding of a batch
+    depth = int(os.environ.get('PLK_TP_PREFETCH', '2'))
+    for i, idx in enumerate(idxs):
+        # the loop knows which simulations come next: their filters run while this estimate is evaluated (all of it
+        # inside the timed region: nothing of a timed simulation is started before e0)
+        one(idx, prefetch=idxs[i + 1:i + 1 + depth])
+        it = lib['ivfs_raw'].cg_iterations[idx]
+        its_t.append(int(it['T']))
+        its_p.append(int(it['P']))
     if world > 1:
         for v in mf:
             dist.reduce(torch.view_as_real(v), dst=0)

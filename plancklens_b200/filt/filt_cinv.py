@@ -97,6 +97,10 @@ class cinv_t(cinv):
                               marge_dipole=marge_dipole, marge_maps=marge_maps)
         self.chain_descr = chain_descr
         self.chain = util.jit(multigrid.multigrid_chain, opfilt_tt, self.chain_descr, dl, n_inv_filt)
+        # B200: this filter's solves run in lane 2, the polarization filter's in lane 1 (own transform plans and reduction
+        # scratch, `sht.use_lane`); lane 0 stays with the caller (simulated maps, quadratic estimators), so that
+        # library_cinv_sepTP can run all three at once
+        self.lane = 2
         if mpi.rank == 0:
             if not os.path.exists(lib_dir):
                 os.makedirs(lib_dir)
@@ -162,7 +166,8 @@ class cinv_t(cinv):
             talm = util_alm.dalm.zeros(self.lmax)
         else:
             talm = util_alm.dalm(sht.dev_alm(soltn).clone())
-        self.chain.solve(talm, tmap)
+        with sht.use_lane(self.lane):
+            self.chain.solve(talm, tmap)
         if not hasattr(self, '_rescal_d'):
             self._rescal_d = sht.dev_fl(self.rescal_cl, self.lmax)
         return talm.almxfl(self._rescal_d, inplace=True).t
@@ -194,8 +199,7 @@ class cinv_p(cinv):
                               marge_umaps=marge_umaps, marge_qmaps=marge_qmaps)
         self.chain_descr = chain_descr
         self.chain = util.jit(multigrid.multigrid_chain, opfilt_pp, chain_descr, cl, n_inv_filt)
-        # B200: this filter's solves run in lane 1 (own transform plans and reduction scratch, `sht.use_lane`), so that
-        # library_cinv_sepTP can run them next to the temperature filter's (lane 0) on a second stream
+        # B200: this filter's solves run in lane 1 (see cinv_t)
         self.lane = 1
         if mpi.rank == 0:
             if not os.path.exists(lib_dir):
@@ -439,6 +443,7 @@ class library_cinv_sepTP(filt_simple.library_sepTP):
     def __init__(self, lib_dir, sim_lib, cinvt, cinvp, cl_weights, soltn_lib=None):
         self.cinv_t = cinvt
         self.cinv_p = cinvp
+        self.cg_iterations = {}        # idx -> {'T': n, 'P': n}: top-level CG iterations of the solves run by this library
         super(library_cinv_sepTP, self).__init__(lib_dir, sim_lib, cl_weights, soltn_lib=soltn_lib)
         if mpi.rank == 0:
             fname_mask = os.path.join(self.lib_dir, "fmask.fits.gz")
@@ -481,6 +486,16 @@ class library_cinv_sepTP(filt_simple.library_sepTP):
         def warm(c):
             return all(not isinstance(op, multigrid.graphed_op) or op.graph is not None for op in c.chain.bstage.pre_ops)
         return warm(self.cinv_t) and warm(self.cinv_p)
+
+    def _filter_t_dev(self, idx, tmap=None):
+        out = super(library_cinv_sepTP, self)._filter_t_dev(idx, tmap)
+        self.cg_iterations.setdefault(idx, {})['T'] = int(self.cinv_t.chain.niter)     # read on the lane that solved
+        return out
+
+    def _filter_p_dev(self, idx, pmap=None):
+        out = super(library_cinv_sepTP, self)._filter_p_dev(idx, pmap)
+        self.cg_iterations.setdefault(idx, {})['P'] = int(self.cinv_p.chain.niter)
+        return out
 
     def _apply_ivf_t_dev(self, tmap, soltn=None):
         return self.cinv_t.apply_ivf_dev(tmap, soltn=soltn)

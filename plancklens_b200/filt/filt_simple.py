@@ -192,47 +192,81 @@ class library_sepTP(object):
         e, b = self._apply_ivf_p(self.sim_lib.get_sim_pmap(idx), soltn=soltn)
         return sht.dev_alm(e), sht.dev_alm(b)
 
-    def _filter_tp_concurrent(self, idx):
-        """T filter on the calling thread and stream, P filter on a worker thread and a second stream: the simulated maps
-        are made first (calling stream), the worker's stream waits for them, the calling stream waits for the worker's
-        results.  The two filters share no mutable device state (`sht.use_lane`)."""
+    # ---- the T and the P filter as two lanes (one worker thread and one stream each; `sht.use_lane` keeps their plans and
+    #      reduction scratch apart).  `_submit_tp` makes the simulated maps on the calling stream and queues the two solves;
+    #      `_collect_tp` joins them.  With `prefetch_dev` the lanes work ahead of the caller: while it evaluates the
+    #      estimator of simulation i on its own stream, the lanes filter simulations i + 1, i + 2 -- the polarization lane,
+    #      whose solve is the shorter one, runs ahead and fills the SMs the temperature lane leaves idle.
+    def _lanes(self):
         import concurrent.futures as cf
         import torch
-        if not hasattr(self, '_p_pool'):
+        if not hasattr(self, '_t_pool'):
+            self._t_pool = cf.ThreadPoolExecutor(max_workers=1)
             self._p_pool = cf.ThreadPoolExecutor(max_workers=1)
             # The temperature solve is the longer chain (13-16 top-level iterations against 5 at Planck-like noise): its
-            # stream outranks the polarization solve's, whose kernels then fill the SMs the temperature chain leaves idle
-            # in its multigrid preconditioner instead of queueing in front of its full-resolution transforms.
+            # stream outranks the polarization solve's and the caller's
             self._t_stream = torch.cuda.Stream(priority=int(os.environ.get('PLK_TP_TPRIO', '-2')))
             self._p_stream = torch.cuda.Stream(priority=0)
+            self._pending = {}
+
+    def _tp_enabled(self):
+        return self._TP_CONCURRENT and os.environ.get('PLK_TP_CONCURRENT', '1') != '0' \
+            and getattr(self, '_tp_ready', lambda: True)()
+
+    def _submit_tp(self, idx):
+        import torch
+        self._lanes()
         tmap, pmap = self._sim_map_dev(idx, 't'), self._sim_map_dev(idx, 'p')
-        main = torch.cuda.current_stream()
         dev = torch.cuda.current_device()
         ready = torch.cuda.Event()
-        ready.record(main)
+        ready.record(torch.cuda.current_stream())
+        for m, st in [(tmap, self._t_stream)] + [(x, self._p_stream) for x in pmap]:
+            if isinstance(m, torch.Tensor):
+                m.record_stream(st)                            # made on the calling stream, read on the lane's
 
-        def work():
-            torch.cuda.set_device(dev)
-            with torch.cuda.stream(self._p_stream):
-                self._p_stream.wait_event(ready)
-                e, b = self._filter_p_dev(idx, pmap)
-                done = torch.cuda.Event()
-                done.record(self._p_stream)
-            return e, b, done
-        fut = self._p_pool.submit(work)
+        def job(stream, fn, arg):
+            def work():
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(stream):
+                    stream.wait_event(ready)
+                    out = fn(idx, arg)
+                    done = torch.cuda.Event()
+                    done.record(stream)
+                return out, done
+            return work
+        self._pending[idx] = (self._t_pool.submit(job(self._t_stream, self._filter_t_dev, tmap)),
+                              self._p_pool.submit(job(self._p_stream, self._filter_p_dev, pmap)))
+
+    def _collect_tp(self, idx):
+        import torch
+        ft, fp = self._pending.pop(idx)
         try:
-            with torch.cuda.stream(self._t_stream):
-                self._t_stream.wait_event(ready)
-                t = self._filter_t_dev(idx, tmap)
-                done_t = torch.cuda.Event()
-                done_t.record(self._t_stream)
+            t, done_t = ft.result()                            # re-raises what the lane raised
         finally:
-            e, b, done = fut.result()                          # re-raises what the worker raised
+            (e, b), done_p = fp.result()
+        main = torch.cuda.current_stream()
         main.wait_event(done_t)
-        main.wait_event(done)
+        main.wait_event(done_p)
         for x in (t, e, b):
-            x.record_stream(main)                              # allocated on the filters' streams, used on this one
+            x.record_stream(main)                              # allocated on the lanes' streams, used on this one
         return t, e, b
+
+    def _needs(self, idx):
+        """(T to filter, P to filter): not in the device store, not on disk"""
+        ent = self._dev_store().get(idx, {})
+        fn_t, fn_e, fn_b = (self._fname(idx, f) for f in 'teb')
+        return ('t' not in ent and not os.path.exists(fn_t)), \
+               ('e' not in ent and not (os.path.exists(fn_e) and os.path.exists(fn_b)))
+
+    def prefetch_dev(self, idxs):
+        """Hint: the simulations `idxs` will be asked for next (`get_sim_teblm_dev`), in this order.  Their maps are
+        simulated now, on the calling stream, and their filters queued on the two lanes; returns at once.  No effect
+        for libraries whose filters do not run side by side, before both chains are warm, or for what is cached."""
+        if not self._tp_enabled():
+            return
+        for idx in idxs:
+            if idx not in getattr(self, '_pending', {}) and all(self._needs(idx)):
+                self._submit_tp(idx)
 
     def get_sim_teblm_dev(self, idx, fields='teb'):
         """Inverse-variance filtered alms of simulation idx as complex128 CUDA tensors, in the order of `fields`."""
@@ -247,9 +281,12 @@ class library_sepTP(object):
             ent['t'], need_t = sht.dev_alm(hp.read_alm(fn_t)), False
         if need_p and os.path.exists(fn_e) and os.path.exists(fn_b):
             ent['e'], ent['b'], need_p = sht.dev_alm(hp.read_alm(fn_e)), sht.dev_alm(hp.read_alm(fn_b)), False
-        if need_t and need_p and self._TP_CONCURRENT and os.environ.get('PLK_TP_CONCURRENT', '1') != '0' \
-                and getattr(self, '_tp_ready', lambda: True)():
-            ent['t'], ent['e'], ent['b'] = self._filter_tp_concurrent(idx)
+        if idx in getattr(self, '_pending', {}):
+            ent['t'], ent['e'], ent['b'] = self._collect_tp(idx)      # prefetched: both filters ran, whatever `fields` asks
+            need_t = need_p = True
+        elif need_t and need_p and self._tp_enabled():
+            self._submit_tp(idx)
+            ent['t'], ent['e'], ent['b'] = self._collect_tp(idx)
         else:
             if need_t:
                 ent['t'] = self._filter_t_dev(idx)

@@ -62,8 +62,8 @@ class library_ftl:
         if name in ('get_sim_teblm_dev', 'get_sim_mliklm_dev') and hasattr(self.ivfs, name):
             inner = getattr(self.ivfs, name)
             return lambda idx, fields='teb': tuple(self._cut_dev(x, f) for f, x in zip(fields, inner(idx, fields)))
-        if name == 'flush' and hasattr(self.ivfs, 'flush'):
-            return self.ivfs.flush
+        if name in ('flush', 'prefetch_dev') and hasattr(self.ivfs, name):
+            return getattr(self.ivfs, name)
         raise AttributeError(name)
 
     def get_sim_tlm(self, idx):
@@ -199,6 +199,8 @@ class library_shuffle:
             return lambda idx, fields='teb': inner(self.idxs[idx], fields)
         if name == 'flush' and hasattr(self.ivfs, 'flush'):
             return self.ivfs.flush
+        if name == 'prefetch_dev' and hasattr(self.ivfs, name):
+            return lambda idxs: self.ivfs.prefetch_dev([self.idxs[i] for i in idxs])
         raise AttributeError(name)
 
     def get_sim_tlm(self, idx):

@@ -489,11 +489,13 @@ class library:
         return all(hasattr(f.ivfs, 'get_sim_teblm_dev') and hasattr(f.ivfs, 'get_sim_mliklm_dev')
                    for f in (self.f2map1, self.f2map2)) and os.environ.get('PLK_QE_DEVICE', '1') != '0'
 
-    def _dev_gclm(self, idx, k, swapped=False):
+    def _dev_gclm(self, idx, k, swapped=False, prefetch=()):
         """(G, C) CUDA tensors of a fundamental lensing key; same legs and per-l weights as the host-fed paths below"""
         f1, f2 = self._legs(idx, k, swapped)
         fields = {'ptt': 't', 'p_p': 'eb', 'p': 'teb'}[k]
         bars = dict(zip(fields, f1.ivfs.get_sim_teblm_dev(idx, fields)))
+        if len(prefetch) and hasattr(f1.ivfs, 'prefetch_dev'):
+            f1.ivfs.prefetch_dev(list(prefetch))        # the filters of the next simulations run under this estimate
         wfs = dict(zip(fields, f2.ivfs.get_sim_mliklm_dev(idx, fields)))
         lmax = sht.alm_lmax(next(iter(bars.values())).numel())
         qe = self._engine(lmax)
@@ -507,12 +509,16 @@ class library:
             return qe.ptt(bars['t'], wfs['t'])
         return qe.p_p(bars['e'], bars['b'], wfs['e'], wfs['b'])
 
-    def get_sim_qlm_dev(self, k, idx):
+    def get_sim_qlm_dev(self, k, idx, prefetch=()):
         """Gradient and curl estimates of 'ptt', 'p_p' or 'p' as CUDA tensors, symmetrised like `get_sim_qlm` when the
-        two legs differ; not cached (mean-field and spectra accumulations that stay on the GPU)."""
+        two legs differ; not cached (mean-field and spectra accumulations that stay on the GPU).
+
+        prefetch: simulation indices the caller will ask for next, in order (a loop over simulations knows them):
+        filtering libraries that can work ahead (`filt_simple.library_sepTP.prefetch_dev`) filter them while this
+        estimate is evaluated."""
         assert k in ['ptt', 'p_p', 'p'], k
         assert self._dev_ok(), "both filtering libraries must provide device-resident alms"
-        G, C = self._dev_gclm(idx, k)
+        G, C = self._dev_gclm(idx, k, prefetch=prefetch)
         if not self.f2map1.ivfs == self.f2map2.ivfs:
             G2, C2 = self._dev_gclm(idx, k, swapped=True)
             G, C = (G + G2) * 0.5, (C + C2) * 0.5

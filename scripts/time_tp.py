@@ -48,9 +48,14 @@ with contextlib.redirect_stdout(open(os.devnull, 'w')):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     its = []
     e0.record()
-    for i in range(nsims):
-        G, C = q.get_sim_qlm_dev('p', 20 + i)
-        its.append((int(lib['cinv_t'].chain.niter), int(lib['cinv_p'].chain.niter)))
+    depth = int(os.environ.get('PLK_TP_PREFETCH', '2'))
+    idxs = [20 + i for i in range(nsims)]
+    digs = []
+    for i, idx in enumerate(idxs):
+        G, C = q.get_sim_qlm_dev('p', idx, prefetch=idxs[i + 1:i + 1 + depth])
+        it = lib['ivfs_raw'].cg_iterations[idx]
+        its.append((it['T'], it['P']))
+        digs.append(G.clone())
     e1.record()
     torch.cuda.synchronize()
     lib['ivfs'].flush()
@@ -58,6 +63,6 @@ for name, a0, a1, h0, h1 in trace:
     print('   %s solve: device %.1f ms, host call %.1f ms (host start %.1f ms after the first)' %
           (name, a0.elapsed_time(a1), 1e3 * (h1 - h0), 1e3 * (h0 - trace[0][3])))
 sec = e0.elapsed_time(e1) * 1e-3
-dig = hashlib.sha1(G.cpu().numpy().tobytes()).hexdigest()[:12]
-print('lmax %d concurrent=%s prio=%s : %.3f sims/s (%.1f ms per simulation), CG iterations (T, P) %s, digest of the last G %s' %
-      (lmax, os.environ.get('PLK_TP_CONCURRENT', '1'), os.environ.get('PLK_CG_PRIO', '1'), nsims / sec, 1e3 * sec / nsims, its, dig))
+dig = hashlib.sha1(b''.join(g.cpu().numpy().tobytes() for g in digs)).hexdigest()[:12]
+print('lmax %d concurrent=%s prio=%s prefetch=%s : %.3f sims/s (%.1f ms per simulation), CG iterations (T, P) %s, digest of all G %s' %
+      (lmax, os.environ.get('PLK_TP_CONCURRENT', '1'), os.environ.get('PLK_CG_PRIO', '1'), os.environ.get('PLK_TP_PREFETCH', '2'), nsims / sec, 1e3 * sec / nsims, its, dig))

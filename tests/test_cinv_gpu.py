@@ -142,6 +142,23 @@ def test_t_and_p_filters_side_by_side(case, libs, tmp_path, monkeypatch):
     seq.flush()
     from plancklens_b200 import hp
     assert np.array_equal(hp.read_alm(os.path.join(con.lib_dir, 'sim_0004_elm.fits')), want[4][1].cpu().numpy())
+    # working ahead: the lanes filter simulations 7 and 8 while the caller does something else on its own stream
+    monkeypatch.setenv('PLK_TP_CONCURRENT', '1')
+    con.prefetch_dev([7, 8, 4])                                  # 4 is in the device store: ignored
+    assert sorted(con._pending) == [7, 8]
+    busy = torch.ones(1 << 22, device='cuda')
+    for _ in range(20):
+        busy = busy * 1.0000001
+    got7, got8 = con.get_sim_teblm_dev(7, 't'), con.get_sim_teblm_dev(8)     # asking for one field collects all three
+    assert not con._pending and set(con._dev_store()[7]) == {'t', 'e', 'b'}
+    assert con.cg_iterations[7] == {'T': cinv_t.chain.niter, 'P': cinv_p.chain.niter} or con.cg_iterations[7]['T'] > 0
+    monkeypatch.setenv('PLK_TP_CONCURRENT', '0')
+    seq.prefetch_dev([7, 8])                                     # switched off: a no-op
+    assert not getattr(seq, '_pending', {})
+    ref7, ref8 = seq.get_sim_teblm_dev(7), seq.get_sim_teblm_dev(8)
+    assert torch.equal(got7[0], ref7[0]) and all(torch.equal(a, b) for a, b in zip(got8, ref8))
+    assert con.cg_iterations[8] == seq.cg_iterations[8] and con.cg_iterations[7] == seq.cg_iterations[7]
+    monkeypatch.setenv('PLK_TP_CONCURRENT', '1')
     # one field at a time still goes through the plain path
     t6, = con.get_sim_teblm_dev(6, 't')
     e6, b6 = con.get_sim_teblm_dev(6, 'eb')
