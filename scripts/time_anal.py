@@ -1,7 +1,6 @@
 """Times the Legendre analysis kernels alone (spin 0 and spin 2, nside = lmax = 2048) and checks them against the
 in-tree library's result: A/B of experimental builds (PLK_LIB_PATH=variants/x.so)."""
 import os, sys
-import numpy as np
 import torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from plancklens_b200 import sht

@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import rand_alm, rel_l2
+from helpers import rand_alm
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 

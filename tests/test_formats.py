@@ -1,7 +1,6 @@
 """On-disk formats: FITS binary tables for alm / maps in healpy's layout, the sqlite
 `npdb` / `fldb` caches of the reference.  CPU only."""
 import gzip
-import os
 import sqlite3
 
 import numpy as np

@@ -6,7 +6,6 @@ import subprocess
 import sys
 import tempfile
 
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

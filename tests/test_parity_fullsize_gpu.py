@@ -13,7 +13,7 @@ Sizes: nside 2048 / lmax 2048 (configs[0-3]), nside 2048 / lmax 3000 (north_star
 import numpy as np
 import pytest
 
-from helpers import alm_size, rand_alm, rel_l2
+from helpers import rand_alm, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10

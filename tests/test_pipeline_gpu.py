@@ -131,7 +131,7 @@ def test_cinv_tp_joint_filter_pipeline(tmp_path):
     constructor accepts (nside 512, lmax 1024): the returned alms solve the normal equations to the requested eps,
     and feed a joint-filtered QE library."""
     import torch
-    from plancklens_b200 import hp, qest, sht, utils
+    from plancklens_b200 import hp, qest, utils
     from plancklens_b200.filt import filt_cinv
     from plancklens_b200.qcinv import cd_solve, opfilt_tp, util_alm
     import golden_inputs as gi
